@@ -1,0 +1,175 @@
+// api.cu -- extern "C" surface of libddw_b200.so (declared in include/ddw.h)
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ddw {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return DDW_ERR_CUDA;
+    }
+    return 0;
+}
+
+// implemented in markowitz.cu / rowproj.cu / covariance.cu
+size_t markowitz_workspace_bytes(long long B, int N, int tsize);
+template <typename T>
+int markowitz_fwd_t(const void *, const void *, const void *, const void *, double, long long, int, void *, int8_t *,
+                    int32_t *, void *, size_t, cudaStream_t);
+template <typename T>
+int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, const void *, const void *, long long,
+                    int, void *, void *, void *, void *, void *, size_t, cudaStream_t);
+template <typename T>
+int row_op_t(int, const void *, const void *, double, double, long long, int, const void *, const void *, void *,
+             void *, void *, cudaStream_t);
+size_t covariance_workspace_bytes(long long B, int L, int N, int tsize, int do_sqrt);
+template <typename T>
+int covariance_fwd_t(const void *, const void *, int, int, long long, int, int, void *, void *, void *, int32_t *,
+                     void *, size_t, cudaStream_t);
+template <typename T>
+int covariance_bwd_t(const void *, const void *, const void *, int, int, const void *, const void *, long long, int,
+                     int, void *, void *, void *, size_t, cudaStream_t);
+
+static int check_dims(const char *fn, int64_t B, int64_t N, int64_t nmax, int dtype) {
+    if (dtype != DDW_F32 && dtype != DDW_F64) { set_error("%s: dtype must be DDW_F32 or DDW_F64", fn); return DDW_ERR_ARG; }
+    if (B < 0 || B >= (1LL << 31)) { set_error("%s: batch size %lld out of range", fn, (long long)B); return DDW_ERR_ARG; }
+    if (N < 1 || N > nmax) { set_error("%s: n_assets=%lld outside [1, %lld]", fn, (long long)N, (long long)nmax); return DDW_ERR_UNSUPPORTED; }
+    return 0;
+}
+
+}  // namespace ddw
+
+using namespace ddw;
+
+extern "C" {
+
+int ddw_version(void) { return DDW_VERSION; }
+
+const char *ddw_last_error(void) { return g_err; }
+
+size_t ddw_markowitz_workspace_bytes(int64_t B, int64_t N, int dtype) {
+    if (B <= 0 || N <= 0 || N > 1024) return 0;
+    return markowitz_workspace_bytes(B, (int)N, dtype == DDW_F64 ? 8 : 4);
+}
+
+int ddw_markowitz_fwd(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                      double max_weight, int64_t B, int64_t N, int dtype, void *w, int8_t *state, int32_t *status,
+                      void *workspace, size_t workspace_bytes, void *stream) {
+    g_err[0] = 0;
+    int rc = check_dims("ddw_markowitz_fwd", B, N, 1024, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!rets || !covmat_sqrt || !gamma_sqrt || !alpha || !w || !state || !status) { set_error("ddw_markowitz_fwd: null pointer"); return DDW_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64
+               ? markowitz_fwd_t<double>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st)
+               : markowitz_fwd_t<float>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st);
+}
+
+int ddw_markowitz_bwd(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt,
+                      const void *gamma_sqrt, const void *alpha, double max_weight, int64_t B, int64_t N, int dtype,
+                      void *d_rets, void *d_covmat_sqrt, void *d_gamma_sqrt, void *d_alpha, void *workspace,
+                      size_t workspace_bytes, void *stream) {
+    (void)max_weight;
+    g_err[0] = 0;
+    int rc = check_dims("ddw_markowitz_bwd", B, N, 1024, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!grad_w || !w || !state || !covmat_sqrt || !gamma_sqrt || !alpha || !d_rets || !d_covmat_sqrt || !d_alpha) { set_error("ddw_markowitz_bwd: null pointer"); return DDW_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64
+               ? markowitz_bwd_t<double>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st)
+               : markowitz_bwd_t<float>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st);
+}
+
+static int row_call(const char *fn, int which, const void *x, const void *temperature, double tscalar, double u,
+                    int64_t B, int64_t N, int dtype, const void *grad_w, const void *w, void *out, void *d_x,
+                    void *d_t, void *stream) {
+    g_err[0] = 0;
+    int rc = check_dims(fn, B, N, 2048, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!x || (!temperature && !(tscalar != 0.0))) { set_error("%s: null input or zero temperature", fn); return DDW_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64 ? row_op_t<double>(which, x, temperature, tscalar, u, B, (int)N, grad_w, w, out, d_x, d_t, st)
+                            : row_op_t<float>(which, x, temperature, tscalar, u, B, (int)N, grad_w, w, out, d_x, d_t, st);
+}
+
+int ddw_capped_simplex_fwd(const void *x, const void *temperature, double temperature_scalar, double max_weight,
+                           int64_t B, int64_t N, int dtype, void *w, void *stream) {
+    if (!w) { set_error("ddw_capped_simplex_fwd: null output"); return DDW_ERR_ARG; }
+    return row_call("ddw_capped_simplex_fwd", 0, x, temperature, temperature_scalar, max_weight, B, N, dtype, nullptr, nullptr, w, nullptr, nullptr, stream);
+}
+
+int ddw_capped_simplex_bwd(const void *grad_w, const void *w, const void *x, const void *temperature,
+                           double temperature_scalar, double max_weight, int64_t B, int64_t N, int dtype, void *d_x,
+                           void *d_temperature, void *stream) {
+    if (!grad_w || !w || !d_x) { set_error("ddw_capped_simplex_bwd: null pointer"); return DDW_ERR_ARG; }
+    return row_call("ddw_capped_simplex_bwd", 1, x, temperature, temperature_scalar, max_weight, B, N, dtype, grad_w, w, nullptr, d_x, d_temperature, stream);
+}
+
+int ddw_capped_softmax_fwd(const void *x, const void *temperature, double temperature_scalar, double max_weight,
+                           int64_t B, int64_t N, int dtype, void *w, void *stream) {
+    if (!w) { set_error("ddw_capped_softmax_fwd: null output"); return DDW_ERR_ARG; }
+    return row_call("ddw_capped_softmax_fwd", 2, x, temperature, temperature_scalar, max_weight, B, N, dtype, nullptr, nullptr, w, nullptr, nullptr, stream);
+}
+
+int ddw_capped_softmax_bwd(const void *grad_w, const void *w, const void *x, const void *temperature,
+                           double temperature_scalar, double max_weight, int64_t B, int64_t N, int dtype, void *d_x,
+                           void *d_temperature, void *stream) {
+    if (!grad_w || !w || !d_x) { set_error("ddw_capped_softmax_bwd: null pointer"); return DDW_ERR_ARG; }
+    return row_call("ddw_capped_softmax_bwd", 3, x, temperature, temperature_scalar, max_weight, B, N, dtype, grad_w, w, nullptr, d_x, d_temperature, stream);
+}
+
+size_t ddw_covariance_workspace_bytes(int64_t B, int64_t L, int64_t N, int dtype, int do_sqrt) {
+    if (B <= 0 || N <= 0 || L <= 0 || N > 1024) return 0;
+    return covariance_workspace_bytes(B, (int)L, (int)N, dtype == DDW_F64 ? 8 : 4, do_sqrt);
+}
+
+int ddw_covariance_fwd(const void *x, const void *coef, int strategy, int do_sqrt, int64_t B, int64_t L, int64_t N,
+                       int dtype, void *out, void *eigvec, void *eigval, int32_t *sweeps, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+    g_err[0] = 0;
+    int rc = check_dims("ddw_covariance_fwd", B, N, 1024, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (L < 2 || L >= (1LL << 24)) { set_error("ddw_covariance_fwd: need 2 <= dim < 2^24 observations, got %lld", (long long)L); return DDW_ERR_ARG; }
+    if (strategy < DDW_SHRINK_NONE || strategy > DDW_SHRINK_SCALED_IDENTITY) { set_error("ddw_covariance_fwd: bad strategy %d", strategy); return DDW_ERR_ARG; }
+    if (!x || !out || (strategy != DDW_SHRINK_NONE && !coef)) { set_error("ddw_covariance_fwd: null pointer"); return DDW_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64
+               ? covariance_fwd_t<double>(x, coef, strategy, do_sqrt, B, (int)L, (int)N, out, eigvec, eigval, sweeps, workspace, workspace_bytes, st)
+               : covariance_fwd_t<float>(x, coef, strategy, do_sqrt, B, (int)L, (int)N, out, eigvec, eigval, sweeps, workspace, workspace_bytes, st);
+}
+
+int ddw_covariance_bwd(const void *grad_out, const void *x, const void *coef, int strategy, int do_sqrt,
+                       const void *eigvec, const void *eigval, int64_t B, int64_t L, int64_t N, int dtype, void *d_x,
+                       void *d_coef, void *workspace, size_t workspace_bytes, void *stream) {
+    g_err[0] = 0;
+    int rc = check_dims("ddw_covariance_bwd", B, N, 1024, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (L < 2 || L >= (1LL << 24)) { set_error("ddw_covariance_bwd: need 2 <= dim < 2^24 observations, got %lld", (long long)L); return DDW_ERR_ARG; }
+    if (strategy < DDW_SHRINK_NONE || strategy > DDW_SHRINK_SCALED_IDENTITY) { set_error("ddw_covariance_bwd: bad strategy %d", strategy); return DDW_ERR_ARG; }
+    if (!grad_out || !x || !d_x || (strategy != DDW_SHRINK_NONE && !coef) || (do_sqrt && (!eigvec || !eigval))) { set_error("ddw_covariance_bwd: null pointer"); return DDW_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64
+               ? covariance_bwd_t<double>(grad_out, x, coef, strategy, do_sqrt, eigvec, eigval, B, (int)L, (int)N, d_x, d_coef, workspace, workspace_bytes, st)
+               : covariance_bwd_t<float>(grad_out, x, coef, strategy, do_sqrt, eigvec, eigval, B, (int)L, (int)N, d_x, d_coef, workspace, workspace_bytes, st);
+}
+
+}  // extern "C"

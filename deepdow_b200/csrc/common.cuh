@@ -1,0 +1,91 @@
+// common.cuh -- shared device helpers for the sm_100a kernels of libddw_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "ddw.h"
+
+namespace ddw {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+    static __device__ __forceinline__ float eps() { return 1.1920929e-7f; }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ float tiny() { return 1e-30f; }
+};
+template <> struct Num<double> {
+    static __device__ __forceinline__ double eps() { return 2.220446049250313e-16; }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ double tiny() { return 1e-300; }
+};
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+template <typename T> __device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { T t = __shfl_xor_sync(kFullMask, v, o); v = t > v ? t : v; }
+    return v;
+}
+template <typename T> __device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { T t = __shfl_xor_sync(kFullMask, v, o); v = t < v ? t : v; }
+    return v;
+}
+// (value, index) arg-min over a warp; ties resolved towards the smaller index
+template <typename T> __device__ __forceinline__ void warp_argmin(T &v, int &i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T tv = __shfl_xor_sync(kFullMask, v, o);
+        int ti = __shfl_xor_sync(kFullMask, i, o);
+        if (tv < v || (tv == v && ti < i)) { v = tv; i = ti; }
+    }
+}
+
+// block-wide sum; `red` is a shared array of at least kThreads/32 elements.  Two barriers.
+template <typename T, int kThreads> __device__ __forceinline__ T block_sum(T v, T *red) {
+    constexpr int kWarps = kThreads / 32;
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) s += red[i];
+    __syncthreads();
+    return s;
+}
+
+template <typename T> __device__ __forceinline__ T clampT(T v, T lo, T hi) { return v < lo ? lo : (v > hi ? hi : v); }
+template <typename T> __device__ __forceinline__ T absT(T v) { return v < 0 ? -v : v; }
+
+__device__ __forceinline__ float rsqrtT(float v) { return rsqrtf(v); }
+__device__ __forceinline__ double rsqrtT(double v) { return rsqrt(v); }
+__device__ __forceinline__ float sqrtT(float v) { return sqrtf(v); }
+__device__ __forceinline__ double sqrtT(double v) { return sqrt(v); }
+__device__ __forceinline__ float expT(float v) { return expf(v); }
+__device__ __forceinline__ double expT(double v) { return exp(v); }
+
+// 4 consecutive elements, 16-byte aligned for float / 32-byte for double
+template <typename T> struct Vec4 { T v[4]; };
+__device__ __forceinline__ Vec4<float> ld4(const float *p) {
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    Vec4<float> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+__device__ __forceinline__ Vec4<double> ld4(const double *p) {
+    double2 a = *reinterpret_cast<const double2 *>(p);
+    double2 b = *reinterpret_cast<const double2 *>(p + 2);
+    Vec4<double> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; return r;
+}
+
+__host__ __device__ __forceinline__ int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// host-side error plumbing (api.cu)
+void set_error(const char *fmt, ...);
+int check_launch(const char *what);
+
+}  // namespace ddw

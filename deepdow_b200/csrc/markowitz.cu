@@ -1,0 +1,888 @@
+// markowitz.cu -- batched box-and-simplex QP solver and its implicit-differentiation backward.
+//
+// Replaces the CvxpyLayer call of NumericalMarkowitz.forward (reference
+// deepdow/layers/allocate.py:240-273; problem stated at :220-232) and the diffcp adjoint behind it.
+//
+//   minimise  w'Qw - r'w   s.t. 1'w = 1, 0 <= w <= u,     Q = A'A + |alpha| I,
+//   A[j,k] = gamma_sqrt[(b N^2 + j N + k) % B] * covmat_sqrt[b,j,k]      (the repeat/view tiling, :268-270)
+//
+// One CTA per portfolio.  Q (lower triangle) and the factor of the reduced KKT system share one
+// N x LD shared-memory array: Q(i,j), j <= i, at Qs[i*LD + j]; the factor L(i,k), k <= i, of the
+// free-set block plus two right-hand-side rows at Qs[k*LD + i + 1] (the strictly upper part).
+//
+// Forward = primal-dual active set (semismooth Newton on the KKT system) warm-started from the
+// diagonal approximation of Q; every iterate is an exact reduced-KKT solve, so the converged
+// answer is the exact optimum of the program that SCS only approximates.  Problems on which the
+// active set cycles are handed to a Mehrotra interior-point kernel (same primitives) and polished.
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace ddw {
+
+constexpr int kMaxPdas = 24;   // active-set iterations before the fallback is asked for
+constexpr int kMaxIpm = 40;
+
+template <typename T> struct MkFwdParams {
+    const T *rets, *C, *gamma, *alpha;
+    T u;
+    long long B;
+    int N, LD, AS, CH;
+    T *w;
+    int8_t *state;
+    int32_t *status;
+    T *ws;            // global Q/L storage when the matrix does not fit shared memory
+    int *fail_count;  // [0] = number of problems that need the fallback
+    int *fail_list;   // their indices
+};
+
+template <typename T> __device__ __forceinline__ T sym_at(const T *Qs, int LD, int i, int j) {
+    return i >= j ? Qs[i * LD + j] : Qs[j * LD + i];
+}
+
+// Shared-memory carve-up used by the forward kernels
+template <typename T> struct MkSmem {
+    T *Qs, *As, *r, *wv, *g, *dinv, *red;
+    int *idx, *idxU, *misc;
+    int8_t *st;
+};
+
+template <typename T, bool kGlobal>
+__device__ __forceinline__ MkSmem<T> carve(unsigned char *raw, int N, int LD, int AS, int CH, T *ws, long long b) {
+    MkSmem<T> s;
+    const int NP = round_up(N + 2, 32);
+    T *p = reinterpret_cast<T *>(raw);
+    if (kGlobal) s.Qs = ws + b * (long long)N * LD;
+    else { s.Qs = p; p += round_up(N * LD, 4); }
+    s.As = p; p += 2 * CH * AS;
+    s.r = p; p += NP;
+    s.wv = p; p += NP;
+    s.g = p; p += NP;
+    s.dinv = p; p += NP;
+    s.red = p; p += 64;
+    int *q = reinterpret_cast<int *>(p);
+    s.idx = q; q += NP;
+    s.idxU = q; q += NP;
+    s.misc = q; q += 8;
+    s.st = reinterpret_cast<int8_t *>(q);
+    return s;
+}
+
+static size_t mk_smem_bytes(int N, int LD, int AS, int CH, int tsize, bool global_q) {
+    const int NP = round_up(N + 2, 32);
+    size_t elems = (global_q ? 0 : (size_t)round_up(N * LD, 4)) + (size_t)2 * CH * AS + (size_t)4 * NP + 64;
+    return elems * tsize + ((size_t)2 * NP + 8) * sizeof(int) + (size_t)NP;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One reduced-KKT solve + state update (a primal-dual active-set step).  Returns `changed`.
+//   w_L = 0, w_U = u, [[2 Q_FF, 1],[1', 0]] [w_F; nu] = [r_F - 2 u Q_FU 1; 1 - u |U|]
+// ------------------------------------------------------------------------------------------------
+template <typename T, int kThreads, int NREG>
+__device__ __forceinline__ int pdas_step(const MkSmem<T> &s, int N, int LD, T u, T dmin, T tolw, int &lifted) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kThreads / 32;
+    T *Qs = s.Qs, *Lb = s.Qs + 1;
+    // (a) ordered index lists of the free and the capped assets
+    if (warp == 0) {
+        int nf = 0, nu = 0;
+        for (int base = 0; base < N; base += 32) {
+            const int i = base + lane;
+            const int v = i < N ? (int)s.st[i] : 2;
+            const unsigned mf = __ballot_sync(kFullMask, v == 0), mu = __ballot_sync(kFullMask, v == 1);
+            const unsigned lt = (1u << lane) - 1u;
+            if (v == 0) s.idx[nf + __popc(mf & lt)] = i;
+            if (v == 1) s.idxU[nu + __popc(mu & lt)] = i;
+            nf += __popc(mf); nu += __popc(mu);
+        }
+        if (lane == 0) { s.misc[0] = nf; s.misc[1] = nu; }
+    }
+    for (int i = tid; i < N; i += kThreads) s.wv[i] = s.st[i] > 0 ? u : T(0);
+    __syncthreads();
+    const int nF = s.misc[0], nU = s.misc[1];
+    const T c = T(1) - u * (T)nU;
+    int changed = 0;
+    T nu_mult = T(0);
+    if (nF > 0) {
+        // (b) gather Q_FF and the two right-hand sides
+        for (int cc = warp; cc < nF; cc += kWarps) {
+            const int jc = s.idx[cc];
+            for (int a = cc + lane; a < nF; a += 32) Lb[cc * LD + a] = Qs[s.idx[a] * LD + jc];
+        }
+        for (int a = tid; a < nF; a += kThreads) {
+            const int i = s.idx[a];
+            T acc = T(0);
+            for (int m = 0; m < nU; ++m) acc += sym_at(Qs, LD, i, s.idxU[m]);
+            Lb[a * LD + nF] = s.r[i] - T(2) * u * acc;
+            Lb[a * LD + nF + 1] = T(1);
+        }
+        __syncthreads();
+        // (c) factor, eliminating the right-hand sides on the way
+        lifted |= factor_ldl<T, kThreads>(Lb, LD, nF, 2, s.dinv, dmin);
+        // (d,e) multiplier of the budget constraint and back substitution -- warp 0
+        if (warp == 0) {
+            T s12 = T(0), s22 = T(0);
+            for (int k = lane; k < nF; k += 32) {
+                const T y1 = Lb[k * LD + nF], y2 = Lb[k * LD + nF + 1], di = s.dinv[k];
+                s12 = fma(y1 * y2, di, s12);
+                s22 = fma(y2 * y2, di, s22);
+            }
+            s12 = warp_sum(s12); s22 = warp_sum(s22);
+            const T nu = (s12 - T(2) * c) / s22;
+            T zt[NREG];
+#pragma unroll
+            for (int m = 0; m < NREG; ++m) {
+                const int k = lane + 32 * m;
+                zt[m] = k < nF ? T(0.5) * (Lb[k * LD + nF] - nu * Lb[k * LD + nF + 1]) : T(0);
+            }
+            backsub_warp<T, NREG>(Lb, LD, nF, s.dinv, zt);
+#pragma unroll
+            for (int m = 0; m < NREG; ++m) {
+                const int k = lane + 32 * m;
+                if (k < nF) s.wv[s.idx[k]] = zt[m];
+            }
+            if (lane == 0) s.red[32] = nu;
+        }
+        __syncthreads();
+        nu_mult = s.red[32];
+        // (f,g) gradient of the Lagrangian and the new active set
+        for (int i = tid; i < N; i += kThreads) {
+            T acc = T(0);
+            for (int m = 0; m < nF; ++m) { const int j = s.idx[m]; acc = fma(sym_at(Qs, LD, i, j), s.wv[j], acc); }
+            for (int m = 0; m < nU; ++m) acc = fma(sym_at(Qs, LD, i, s.idxU[m]), u, acc);
+            const T gi = T(2) * acc - s.r[i] + nu_mult;
+            const int8_t so = s.st[i];
+            int8_t sn = so;
+            if (so == 0) {
+                const T wi = s.wv[i];
+                if (wi < -tolw) sn = -1;
+                else if (wi > u + tolw) sn = 1;
+            } else if (so < 0) { if (gi < T(0)) sn = 0; }
+            else { if (gi > T(0)) sn = 0; }
+            if (sn != so) { s.st[i] = sn; changed = 1; }
+        }
+    } else {
+        // no free asset: w is fixed by the caps; optimal iff max_L(-h) <= min_U(-h) and u |U| = 1
+        for (int i = tid; i < N; i += kThreads) {
+            T acc = T(0);
+            for (int m = 0; m < nU; ++m) acc = fma(sym_at(Qs, LD, i, s.idxU[m]), u, acc);
+            s.g[i] = T(2) * acc - s.r[i];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            T hl = Num<T>::inf(), hu = Num<T>::inf();  // min h over L, min (-h) over U
+            int il = 0x7fffffff, iu = 0x7fffffff;
+            for (int i = lane; i < N; i += 32) {
+                const T h = s.g[i];
+                if (s.st[i] < 0) { if (h < hl) { hl = h; il = i; } }
+                else if (s.st[i] > 0) { if (-h < hu) { hu = -h; iu = i; } }
+            }
+            warp_argmin(hl, il); warp_argmin(hu, iu);
+            const T ctol = T(4) * Num<T>::eps() * (T)N;
+            int ch = 0;
+            if (lane == 0) {
+                if (c > ctol && il < N) { s.st[il] = 0; ch = 1; }
+                else if (c < -ctol && iu < N) { s.st[iu] = 0; ch = 1; }
+                else if (il < N && iu < N && -hl > hu) { s.st[il] = 0; s.st[iu] = 0; ch = 1; }
+                s.misc[2] = ch;
+            }
+        }
+        __syncthreads();
+        changed = s.misc[2];
+    }
+    return __syncthreads_or(changed);
+}
+
+// Safeguarded Newton on nu for the separable problem with diag(Q): initial active set.  Warp 0.
+template <typename T, int NREG>
+__device__ __forceinline__ void diag_init_warp(const MkSmem<T> &s, int N, int LD, T u, T *dmax_out) {
+    const int lane = threadIdx.x & 31;
+    T i2q[NREG], rr[NREG];
+    T lo = Num<T>::inf(), hi = -Num<T>::inf(), sa = T(0), sb = T(0), dmax = T(0);
+#pragma unroll
+    for (int m = 0; m < NREG; ++m) {
+        const int i = lane + 32 * m;
+        if (i < N) {
+            T q = s.Qs[i * LD + i];
+            dmax = q > dmax ? q : dmax;
+            q = q > Num<T>::tiny() ? q : Num<T>::tiny();
+            i2q[m] = T(0.5) / q; rr[m] = s.r[i];
+            const T l = rr[m] - T(2) * q * u;
+            lo = l < lo ? l : lo; hi = rr[m] > hi ? rr[m] : hi;
+            sa = fma(rr[m], i2q[m], sa); sb += i2q[m];
+        } else { i2q[m] = T(0); rr[m] = T(0); }
+    }
+    lo = warp_min(lo); hi = warp_max(hi); sa = warp_sum(sa); sb = warp_sum(sb); dmax = warp_max(dmax);
+    T nu = (sa - T(1)) / sb;
+    nu = clampT(nu, lo, hi);
+    T dxold = hi - lo, dx = dxold;
+    for (int it = 0; it < 60; ++it) {
+        T sum = T(0), slope = T(0);
+#pragma unroll
+        for (int m = 0; m < NREG; ++m) {
+            const T v = (rr[m] - nu) * i2q[m];
+            sum += clampT(v, T(0), u);
+            slope += (v > T(0) && v < u) ? i2q[m] : T(0);
+        }
+        sum = warp_sum(sum); slope = warp_sum(slope);
+        if (absT(sum - T(1)) <= T(1e-6)) break;
+        if (sum > T(1)) lo = nu; else hi = nu;
+        T nn = nu;
+        bool ok = false;
+        if (slope > T(0)) {
+            nn = nu + (sum - T(1)) / slope;
+            ok = nn > lo && nn < hi && absT(T(2) * (nn - nu)) <= absT(dxold);
+        }
+        dxold = dx;
+        if (ok) dx = nn - nu;
+        else { dx = T(0.5) * (hi - lo); nn = lo + dx; }
+        if (nn == nu) break;
+        nu = nn;
+    }
+#pragma unroll
+    for (int m = 0; m < NREG; ++m) {
+        const int i = lane + 32 * m;
+        if (i < N) {
+            const T v = (rr[m] - nu) * i2q[m];
+            s.st[i] = v <= T(0) ? -1 : (v >= u ? 1 : 0);
+        }
+    }
+    *dmax_out = dmax;
+}
+
+// write the result of a converged / abandoned active-set iteration
+template <typename T, int kThreads>
+__device__ __forceinline__ void write_result(const MkSmem<T> &s, int N, T u, T *w_out, int8_t *st_out) {
+    for (int i = threadIdx.x; i < N; i += kThreads) {
+        const int8_t st = s.st[i];
+        const T wi = st == 0 ? clampT(s.wv[i], T(0), u) : (st > 0 ? u : T(0));
+        w_out[i] = wi;
+        st_out[i] = st;
+    }
+}
+
+// returns 1 when the problem was decided by the box alone (infeasible or a single feasible point)
+template <typename T, int kThreads>
+__device__ __forceinline__ int trivial_cases(int N, T u, T *w_out, int8_t *st_out, int32_t *status) {
+    const T cap = u * (T)N;
+    const T tol = T(8) * Num<T>::eps() * (T)N;
+    if (cap < T(1) - tol || !(u > T(0))) {
+        for (int i = threadIdx.x; i < N; i += kThreads) { w_out[i] = Num<T>::inf() - Num<T>::inf(); st_out[i] = 0; }
+        if (threadIdx.x == 0) *status = DDW_STATUS_INFEASIBLE;
+        return 1;
+    }
+    if (cap <= T(1) + tol) {
+        for (int i = threadIdx.x; i < N; i += kThreads) { w_out[i] = u; st_out[i] = 1; }
+        if (threadIdx.x == 0) *status = DDW_STATUS_OK;
+        return 1;
+    }
+    return 0;
+}
+
+template <typename T, int kThreads, int NREG, bool kGlobal>
+__global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long long b = blockIdx.x;
+    const int N = p.N, LD = p.LD, tid = threadIdx.x;
+    T *w_out = p.w + b * N;
+    int8_t *st_out = p.state + b * N;
+    if (trivial_cases<T, kThreads>(N, p.u, w_out, st_out, p.status + b)) return;
+    MkSmem<T> s = carve<T, kGlobal>(smem_raw, N, LD, p.AS, p.CH, p.ws, b);
+    for (int i = tid; i < N; i += kThreads) s.r[i] = p.rets[b * N + i];
+    const T aabs = absT(p.alpha[b]);
+    gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, b * (long long)N * N, p.B, N, N, nullptr,
+                                   nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
+    if (tid < 32) {
+        T dmax;
+        diag_init_warp<T, NREG>(s, N, LD, p.u, &dmax);
+        if (tid == 0) s.red[33] = dmax;
+    }
+    __syncthreads();
+    const T dmin = T(4) * Num<T>::eps() * s.red[33] + Num<T>::tiny();
+    const T tolw = T(8) * Num<T>::eps();
+    int lifted = 0, converged = 0;
+    for (int it = 0; it < kMaxPdas; ++it) {
+        if (!pdas_step<T, kThreads, NREG>(s, N, LD, p.u, dmin, tolw, lifted)) { converged = 1; break; }
+    }
+    write_result<T, kThreads>(s, N, p.u, w_out, st_out);
+    if (tid == 0) {
+        int st = lifted ? DDW_STATUS_REGULARIZED : 0;
+        if (!converged) {
+            st |= DDW_STATUS_FALLBACK | DDW_STATUS_INEXACT;
+            const int slot = atomicAdd(p.fail_count, 1);
+            p.fail_list[slot] = (int)b;
+        }
+        p.status[b] = st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fallback: Mehrotra predictor-corrector interior point on the same data, then active-set polish.
+// Launched with a fixed small grid; CTAs walk the list of failed problems.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int kThreads, int NREG, bool kGlobal>
+__global__ void __launch_bounds__(kThreads) markowitz_ipm_kernel(MkFwdParams<T> p, T *ipm_ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = p.N, LD = p.LD, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NP = round_up(N + 2, 32);
+    const int nfail = *p.fail_count;
+    for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
+        const long long b = p.fail_list[f];
+        MkSmem<T> s = carve<T, kGlobal>(smem_raw, N, LD, p.AS, p.CH, p.ws, b);
+        // per-CTA vectors of the interior point method live in global scratch (rare path)
+        T *wk = ipm_ws + (long long)blockIdx.x * 8 * NP;
+        T *w = wk, *lam = wk + NP, *mu = wk + 2 * NP, *h = wk + 3 * NP, *dw = wk + 4 * NP, *dl = wk + 5 * NP,
+          *dm = wk + 6 * NP, *y2 = wk + 7 * NP;
+        const T u = p.u;
+        __syncthreads();
+        for (int i = tid; i < N; i += kThreads) s.r[i] = p.rets[b * N + i];
+        const T aabs = absT(p.alpha[b]);
+        gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, b * (long long)N * N, p.B, N, N, nullptr,
+                                       nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
+        // objective scale so that gradients are O(1)
+        T sc = T(0);
+        for (int i = tid; i < N; i += kThreads) {
+            const T a = absT(s.r[i]), q2 = T(2) * s.Qs[i * LD + i];
+            sc = a > sc ? a : sc; sc = q2 > sc ? q2 : sc;
+        }
+        sc = warp_max(sc);
+        if (lane == 0) s.red[warp] = sc;
+        __syncthreads();
+        sc = T(0);
+        for (int i = 0; i < kThreads / 32; ++i) sc = s.red[i] > sc ? s.red[i] : sc;
+        __syncthreads();
+        if (!(sc > T(0))) sc = T(1);
+        const T isc = T(1) / sc;
+        const bool useU = u < T(1);
+        const T ncomp = (T)(N * (useU ? 2 : 1));
+        for (int i = tid; i < N; i += kThreads) {
+            w[i] = T(1) / (T)N;
+            lam[i] = (T)N;
+            mu[i] = useU ? T(1) / (u - w[i]) : T(0);
+        }
+        T nu = T(0);
+        T *Qs = s.Qs, *Lb = s.Qs + 1;
+        const T gtol = T(64) * Num<T>::eps();
+        __syncthreads();
+        for (int it = 0; it < kMaxIpm; ++it) {
+            // residuals: h = (2 Q w - r)/sc + nu
+            T lgap = T(0), lrp = T(0);
+            for (int i = tid; i < N; i += kThreads) {
+                T acc = T(0);
+                for (int j = 0; j < N; ++j) acc = fma(sym_at(Qs, LD, i, j), w[j], acc);
+                h[i] = (T(2) * acc - s.r[i]) * isc + nu;
+                lgap += lam[i] * w[i] + (useU ? mu[i] * (u - w[i]) : T(0));
+                lrp += w[i];
+            }
+            const T gap = block_sum<T, kThreads>(lgap, s.red) / ncomp;
+            const T rp = block_sum<T, kThreads>(lrp, s.red) - T(1);
+            if (gap < gtol) break;
+            // H = 2Q/sc + diag(lam/w + mu/t); rhs rows: [1, -h]
+            for (int cc = warp; cc < N; cc += kThreads / 32)
+                for (int a = cc + lane; a < N; a += 32) {
+                    T v = T(2) * Qs[a * LD + cc] * isc;
+                    if (a == cc) v += lam[a] / w[a] + (useU ? mu[a] / (u - w[a]) : T(0));
+                    Lb[cc * LD + a] = v;
+                }
+            for (int a = tid; a < N; a += kThreads) { Lb[a * LD + N] = T(1); Lb[a * LD + N + 1] = -h[a]; }
+            __syncthreads();
+            factor_ldl<T, kThreads>(Lb, LD, N, 2, s.dinv, Num<T>::tiny());
+            T s2 = T(0), s1 = T(0);
+            if (warp == 0) {
+                T z1[NREG], z2[NREG];
+#pragma unroll
+                for (int m = 0; m < NREG; ++m) {
+                    const int k = lane + 32 * m;
+                    z1[m] = k < N ? Lb[k * LD + N] : T(0);
+                    z2[m] = k < N ? Lb[k * LD + N + 1] : T(0);
+                }
+                backsub_warp<T, NREG>(Lb, LD, N, s.dinv, z1);
+                backsub_warp<T, NREG>(Lb, LD, N, s.dinv, z2);
+#pragma unroll
+                for (int m = 0; m < NREG; ++m) {
+                    const int k = lane + 32 * m;
+                    if (k < N) { y2[k] = z1[m]; dw[k] = z2[m]; s2 += z1[m]; s1 += z2[m]; }
+                }
+                s2 = warp_sum(s2); s1 = warp_sum(s1);
+                if (lane == 0) { s.red[34] = s2; s.red[35] = s1; }
+            }
+            __syncthreads();
+            s2 = s.red[34]; s1 = s.red[35];
+            const T dnu = (s1 + rp) / s2;
+            // predictor step and its maximal step length
+            T amax = T(1);
+            for (int i = tid; i < N; i += kThreads) {
+                const T d = dw[i] - dnu * y2[i];
+                dw[i] = d;
+                const T dli = -lam[i] - lam[i] / w[i] * d;
+                dl[i] = dli;
+                if (d < T(0)) amax = min(amax, -w[i] / d);
+                if (dli < T(0)) amax = min(amax, -lam[i] / dli);
+                if (useU) {
+                    const T t = u - w[i];
+                    const T dmi = -mu[i] + mu[i] / t * d;
+                    dm[i] = dmi;
+                    if (d > T(0)) amax = min(amax, t / d);
+                    if (dmi < T(0)) amax = min(amax, -mu[i] / dmi);
+                } else dm[i] = T(0);
+            }
+            amax = warp_min(amax);
+            if (lane == 0) s.red[warp] = amax;
+            __syncthreads();
+            amax = T(1);
+            for (int i = 0; i < kThreads / 32; ++i) amax = min(amax, s.red[i]);
+            __syncthreads();
+            T lga = T(0);
+            for (int i = tid; i < N; i += kThreads)
+                lga += (lam[i] + amax * dl[i]) * (w[i] + amax * dw[i]) +
+                       (useU ? (mu[i] + amax * dm[i]) * (u - w[i] - amax * dw[i]) : T(0));
+            const T gap_aff = block_sum<T, kThreads>(lga, s.red) / ncomp;
+            T sigma = gap_aff / gap;
+            sigma = sigma * sigma * sigma;
+            // corrector right-hand side, forward + backward substitution with the same factor
+            for (int i = tid; i < N; i += kThreads) {
+                const T cl = (sigma * gap - dw[i] * dl[i]) / w[i];
+                const T cu = useU ? (sigma * gap + dw[i] * dm[i]) / (u - w[i]) : T(0);
+                s.g[i] = -h[i] + cl - cu;   // rhs
+                s.wv[i] = cl;               // cu is recomputed below
+            }
+            __syncthreads();
+            if (warp == 0) {
+                T z[NREG];
+#pragma unroll
+                for (int m = 0; m < NREG; ++m) { const int k = lane + 32 * m; z[m] = k < N ? s.g[k] : T(0); }
+                fwdsub_warp<T, NREG>(Lb, LD, N, s.dinv, z);
+                backsub_warp<T, NREG>(Lb, LD, N, s.dinv, z);
+                T ss = T(0);
+#pragma unroll
+                for (int m = 0; m < NREG; ++m) { const int k = lane + 32 * m; if (k < N) { s.g[k] = z[m]; ss += z[m]; } }
+                ss = warp_sum(ss);
+                if (lane == 0) s.red[36] = ss;
+            }
+            __syncthreads();
+            const T dnu2 = (s.red[36] + rp) / s2;
+            amax = T(1);
+            for (int i = tid; i < N; i += kThreads) {
+                const T d2 = s.g[i] - dnu2 * y2[i];
+                const T cl = s.wv[i];
+                const T cu = useU ? (sigma * gap + dw[i] * dm[i]) / (u - w[i]) : T(0);
+                const T dl2 = -lam[i] + cl - lam[i] / w[i] * d2;
+                s.g[i] = d2; dl[i] = dl2;
+                if (d2 < T(0)) amax = min(amax, -w[i] / d2);
+                if (dl2 < T(0)) amax = min(amax, -lam[i] / dl2);
+                if (useU) {
+                    const T t = u - w[i];
+                    const T dm2 = -mu[i] + cu + mu[i] / t * d2;
+                    dm[i] = dm2;
+                    if (d2 > T(0)) amax = min(amax, t / d2);
+                    if (dm2 < T(0)) amax = min(amax, -mu[i] / dm2);
+                }
+            }
+            amax = warp_min(amax);
+            if (lane == 0) s.red[warp] = amax;
+            __syncthreads();
+            amax = T(1);
+            for (int i = 0; i < kThreads / 32; ++i) amax = min(amax, s.red[i]);
+            __syncthreads();
+            const T a = min(T(1), T(0.99) * amax);
+            for (int i = tid; i < N; i += kThreads) {
+                w[i] += a * s.g[i];
+                lam[i] += a * dl[i];
+                if (useU) mu[i] += a * dm[i];
+            }
+            nu += a * dnu2;
+            __syncthreads();
+        }
+        // active-set identification + exact polish
+        for (int i = tid; i < N; i += kThreads) {
+            int8_t st = 0;
+            if (w[i] < lam[i]) st = -1;
+            if (useU && (u - w[i]) < mu[i]) st = 1;
+            s.st[i] = st;
+            y2[i] = w[i];  // keep the interior-point iterate
+        }
+        if (tid < 32) {
+            T dmax = T(0);
+            for (int i = lane; i < N; i += 32) dmax = max(dmax, Qs[i * LD + i]);
+            dmax = warp_max(dmax);
+            if (lane == 0) s.red[37] = dmax;
+        }
+        __syncthreads();
+        const T dmin = T(4) * Num<T>::eps() * s.red[37] + Num<T>::tiny();
+        int lifted = 0, converged = 0;
+        for (int it = 0; it < kMaxPdas; ++it) {
+            if (!pdas_step<T, kThreads, NREG>(s, N, LD, u, dmin, T(8) * Num<T>::eps(), lifted)) { converged = 1; break; }
+        }
+        if (converged) {
+            write_result<T, kThreads>(s, N, u, p.w + b * N, p.state + b * N);
+            if (tid == 0) p.status[b] = DDW_STATUS_FALLBACK | (lifted ? DDW_STATUS_REGULARIZED : 0);
+        } else {
+            const T thr = T(1e3) * Num<T>::eps();
+            for (int i = tid; i < N; i += kThreads) {
+                const T wi = clampT(y2[i], T(0), u);
+                p.w[b * N + i] = wi;
+                p.state[b * N + i] = wi <= thr ? -1 : (u - wi <= thr ? 1 : 0);
+            }
+            if (tid == 0) p.status[b] = DDW_STATUS_FALLBACK | DDW_STATUS_INEXACT;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward: implicit differentiation of the KKT system on the active set saved by the forward.
+//   F = {state == 0};  [[2 Q_FF, 1],[1', 0]] [d_F; eta] = [g_F; 0],  d = 0 off F
+//   d_rets = d;  dA = -2 [(A d) w' + (A w) d'];  d_covmat_sqrt = gamma_ * dA;  d_alpha = sign(alpha)(-2 d.w)
+// The (A d, A w) vectors are also written to `vecs` (B,2,N) for the gamma scatter pass.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct MkBwdParams {
+    const T *grad_w, *w, *C, *gamma, *alpha;
+    const int8_t *state;
+    long long B;
+    int N, LDW, AS, CH;
+    T *d_rets, *d_C, *d_alpha, *vecs;
+    T *ws;  // global factor storage when it does not fit shared memory
+};
+
+static size_t mk_bwd_smem_bytes(int N, int LDW, int AS, int CH, int tsize, bool global_l) {
+    const int NP = round_up(N + 2, 32);
+    size_t elems = (global_l ? 0 : (size_t)round_up(N * LDW, 4)) + (size_t)2 * CH * AS + (size_t)5 * NP + 32;
+    return elems * tsize + ((size_t)2 * NP + 8) * sizeof(int);
+}
+
+template <typename T, int kThreads, int NREG, bool kGlobal>
+__global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long long b = blockIdx.x;
+    const int N = p.N, LDW = p.LDW, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kThreads / 32;
+    const int NP = round_up(N + 2, 32);
+    T *ptr = reinterpret_cast<T *>(smem_raw);
+    T *Lb;
+    if (kGlobal) Lb = p.ws + b * (long long)N * LDW;
+    else { Lb = ptr; ptr += round_up(N * LDW, 4); }
+    T *As = ptr; ptr += 2 * p.CH * p.AS;
+    T *wv = ptr; ptr += NP;
+    T *dv = ptr; ptr += NP;
+    T *gv = ptr; ptr += NP;
+    T *dinv = ptr; ptr += NP;
+    T *qv = ptr; ptr += NP;
+    T *red = ptr; ptr += 32;
+    int *idx = reinterpret_cast<int *>(ptr);
+    int *pos = idx + NP;
+    int *misc = pos + NP;
+
+    if (warp == 0) {
+        int nf = 0;
+        for (int base = 0; base < N; base += 32) {
+            const int i = base + lane;
+            const int v = i < N ? (int)p.state[b * N + i] : 2;
+            const unsigned mf = __ballot_sync(kFullMask, v == 0);
+            const int a = nf + __popc(mf & ((1u << lane) - 1u));
+            if (i < N) pos[i] = v == 0 ? a : -1;
+            if (v == 0) idx[a] = i;
+            nf += __popc(mf);
+        }
+        if (lane == 0) misc[0] = nf;
+    }
+    for (int i = tid; i < N; i += kThreads) {
+        wv[i] = p.w[b * N + i];
+        gv[i] = p.grad_w[b * N + i];
+        dv[i] = T(0);
+    }
+    __syncthreads();
+    const int nF = misc[0];
+    const T *Cb = p.C + b * (long long)N * N;
+    const long long gflat0 = b * (long long)N * N;
+    const T alpha = p.alpha[b];
+    if (nF > 0) {
+        gram_lower<T, kThreads, true>(Cb, p.gamma, gflat0, p.B, N, N, nullptr, pos, nF, As, p.AS, p.CH, Lb, LDW,
+                                      absT(alpha));
+        T dmax = T(0);
+        for (int a = tid; a < nF; a += kThreads) {
+            Lb[a * LDW + nF] = gv[idx[a]];
+            Lb[a * LDW + nF + 1] = T(1);
+            dmax = max(dmax, Lb[a * LDW + a]);
+        }
+        dmax = warp_max(dmax);
+        if (lane == 0) red[warp] = dmax;
+        __syncthreads();
+        dmax = T(0);
+        for (int i = 0; i < kWarps; ++i) dmax = max(dmax, red[i]);
+        const T dmin = T(4) * Num<T>::eps() * dmax + Num<T>::tiny();
+        factor_ldl<T, kThreads>(Lb, LDW, nF, 2, dinv, dmin);
+        if (warp == 0) {
+            T s12 = T(0), s22 = T(0);
+            for (int k = lane; k < nF; k += 32) {
+                const T y1 = Lb[k * LDW + nF], y2 = Lb[k * LDW + nF + 1], di = dinv[k];
+                s12 = fma(y1 * y2, di, s12);
+                s22 = fma(y2 * y2, di, s22);
+            }
+            s12 = warp_sum(s12); s22 = warp_sum(s22);
+            const T eta = s12 / s22;
+            T zt[NREG];
+#pragma unroll
+            for (int m = 0; m < NREG; ++m) {
+                const int k = lane + 32 * m;
+                zt[m] = k < nF ? T(0.5) * (Lb[k * LDW + nF] - eta * Lb[k * LDW + nF + 1]) : T(0);
+            }
+            backsub_warp<T, NREG>(Lb, LDW, nF, dinv, zt);
+#pragma unroll
+            for (int m = 0; m < NREG; ++m) {
+                const int k = lane + 32 * m;
+                if (k < nF) dv[idx[k]] = zt[m];
+            }
+        }
+        __syncthreads();
+    }
+    // d_rets, d_alpha
+    T ldot = T(0);
+    for (int i = tid; i < N; i += kThreads) { p.d_rets[b * N + i] = dv[i]; ldot = fma(dv[i], wv[i], ldot); }
+    const T dot = block_sum<T, kThreads>(ldot, red);
+    if (tid == 0) p.d_alpha[b] = (alpha > T(0) ? T(1) : (alpha < T(0) ? T(-1) : T(0))) * (T(-2) * dot);
+    // p = A d, q = A w: one warp per row, coalesced reads of covmat_sqrt (L2 resident after the Gram)
+    T *pv = gv;  // grad_w no longer needed
+    for (int j = warp; j < N; j += kWarps) {
+        T sp = T(0), sq = T(0);
+        const long long rowflat = gflat0 + (long long)j * N;
+        unsigned gi = (unsigned)((rowflat + lane) % p.B);
+        const unsigned gstep = (unsigned)(32 % p.B);
+        for (int k = lane; k < N; k += 32) {
+            const T a = Cb[(long long)j * N + k] * p.gamma[gi];
+            sp = fma(a, dv[k], sp); sq = fma(a, wv[k], sq);
+            gi += gstep; if (gi >= (unsigned)p.B) gi -= (unsigned)p.B;
+        }
+        sp = warp_sum(sp); sq = warp_sum(sq);
+        if (lane == 0) { pv[j] = sp; qv[j] = sq; }
+    }
+    __syncthreads();
+    if (p.vecs) for (int i = tid; i < N; i += kThreads) { p.vecs[(b * 2) * N + i] = pv[i]; p.vecs[(b * 2 + 1) * N + i] = qv[i]; }
+    // d_covmat_sqrt = gamma_ * (-2) (p w' + q d')
+    {
+        T *dC = p.d_C + gflat0;
+        const int total = N * N;
+        int j = tid / N, k = tid - j * N;
+        const int dj = kThreads / N, dkk = kThreads % N;
+        unsigned gi = (unsigned)((gflat0 + tid) % p.B);
+        const unsigned gstep = (unsigned)(kThreads % p.B);
+        for (int e = tid; e < total; e += kThreads) {
+            dC[e] = p.gamma[gi] * T(-2) * fma(pv[j], wv[k], qv[j] * dv[k]);
+            k += dkk; j += dj;
+            if (k >= N) { k -= N; ++j; }
+            gi += gstep; if (gi >= (unsigned)p.B) gi -= (unsigned)p.B;
+        }
+    }
+}
+
+// d_gamma[m] = sum over flat = q B + m of covmat_sqrt[flat] * dA[flat]   (backward of the tiling)
+// grid: (ceil(B / 128), nsplit); each thread owns one m and a slice of q; partial sums via atomics.
+template <typename T>
+__global__ void __launch_bounds__(128) markowitz_gamma_kernel(const T *__restrict__ C, const T *__restrict__ w,
+                                                              const T *__restrict__ d, const T *__restrict__ vecs,
+                                                              long long B, int N, int q_per_split, T *d_gamma) {
+    const long long m = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (m >= B) return;
+    const long long NN = (long long)N * N;
+    const long long q0 = (long long)blockIdx.y * q_per_split;
+    const long long q1 = min(q0 + q_per_split, NN);
+    if (q0 >= q1) return;
+    // flat = q B + m walks with stride B; keep (b, j, k) incrementally instead of dividing per element
+    const long long flat0 = q0 * B + m;
+    long long b = flat0 / NN;
+    int rem = (int)(flat0 - b * NN);
+    int j = rem / N, k = rem - j * N;
+    const long long Bq = B / NN;
+    const int Br = (int)(B - Bq * NN), Brj = Br / N, Brk = Br - Brj * N;
+    const int NNi = (int)NN;
+    T acc = T(0);
+    long long flat = flat0;
+    for (long long q = q0; q < q1; ++q) {
+        const T pj = vecs[(b * 2) * N + j], qj = vecs[(b * 2 + 1) * N + j];
+        const T dA = T(-2) * fma(pj, w[b * N + k], qj * d[b * N + k]);
+        acc = fma(C[flat], dA, acc);
+        flat += B; b += Bq; rem += Br; j += Brj; k += Brk;
+        if (k >= N) { k -= N; ++j; }
+        if (rem >= NNi) { rem -= NNi; j -= N; ++b; }
+    }
+    atomicAdd(d_gamma + m, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+struct MkPlan {
+    int threads, nreg, LD, AS, CH;
+    bool global_q;
+    size_t smem;
+};
+
+static int smem_limit() {
+    static int lim = -1;
+    if (lim < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) lim = 48 * 1024;
+        cudaGetLastError();
+    }
+    return lim;
+}
+
+static MkPlan plan_fwd(int N, int tsize) {
+    MkPlan pl;
+    pl.threads = N <= 128 ? 128 : (N <= 256 ? 256 : 512);
+    pl.nreg = N <= 128 ? 4 : (N <= 256 ? 8 : (N <= 512 ? 16 : 32));
+    pl.LD = (N + 3) | 1;
+    pl.AS = round_up(N, 4);
+    pl.CH = max(1, min(N, pl.threads * kPre / N));
+    pl.global_q = false;
+    pl.smem = mk_smem_bytes(N, pl.LD, pl.AS, pl.CH, tsize, false);
+    if (pl.smem > (size_t)smem_limit()) {
+        pl.global_q = true;
+        pl.smem = mk_smem_bytes(N, pl.LD, pl.AS, pl.CH, tsize, true);
+    }
+    return pl;
+}
+
+static MkPlan plan_bwd(int N, int tsize) {
+    MkPlan pl = plan_fwd(N, tsize);
+    pl.LD = (N + 2) | 1;
+    pl.global_q = false;
+    pl.smem = mk_bwd_smem_bytes(N, pl.LD, pl.AS, pl.CH, tsize, false);
+    if (pl.smem > (size_t)smem_limit()) {
+        pl.global_q = true;
+        pl.smem = mk_bwd_smem_bytes(N, pl.LD, pl.AS, pl.CH, tsize, true);
+    }
+    return pl;
+}
+
+constexpr int kIpmGrid = 296;
+
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
+    const MkPlan pf = plan_fwd(N, tsize), pb = plan_bwd(N, tsize);
+    const int NP = round_up(N + 2, 32);
+    size_t bytes = 0;
+    bytes += align256(sizeof(int) * (size_t)(B + 1));                      // fail_count + fail_list
+    bytes += align256((size_t)kIpmGrid * 8 * NP * tsize);                  // interior-point vectors
+    bytes += align256((size_t)B * 2 * N * tsize);                          // (A d, A w) for the gamma pass
+    size_t q = 0;
+    if (pf.global_q) q = (size_t)B * N * pf.LD * tsize;
+    if (pb.global_q) q = max(q, (size_t)B * N * pb.LD * tsize);
+    bytes += align256(q);
+    return bytes;
+}
+
+template <typename T> struct WsLayout {
+    int *fail_count, *fail_list;
+    T *ipm, *vecs, *q;
+};
+template <typename T> static WsLayout<T> ws_layout(void *ws, long long B, int N) {
+    const int NP = round_up(N + 2, 32);
+    WsLayout<T> l;
+    unsigned char *p = reinterpret_cast<unsigned char *>(ws);
+    l.fail_count = reinterpret_cast<int *>(p);
+    l.fail_list = l.fail_count + 1;
+    p += align256(sizeof(int) * (size_t)(B + 1));
+    l.ipm = reinterpret_cast<T *>(p); p += align256((size_t)kIpmGrid * 8 * NP * sizeof(T));
+    l.vecs = reinterpret_cast<T *>(p); p += align256((size_t)B * 2 * N * sizeof(T));
+    l.q = reinterpret_cast<T *>(p);
+    return l;
+}
+
+template <typename T, int kThreads, int NREG, bool kGlobal>
+static int launch_fwd_variant(const MkFwdParams<T> &p, const MkPlan &pl, T *ipm_ws, cudaStream_t st) {
+    auto kf = markowitz_fwd_kernel<T, kThreads, NREG, kGlobal>;
+    auto ki = markowitz_ipm_kernel<T, kThreads, NREG, kGlobal>;
+    if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess ||
+        cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(markowitz_fwd)");
+    cudaMemsetAsync(p.fail_count, 0, sizeof(int), st);
+    kf<<<(unsigned)p.B, kThreads, pl.smem, st>>>(p);
+    int rc = check_launch("markowitz_fwd_kernel");
+    if (rc) return rc;
+    const unsigned grid = (unsigned)min((long long)kIpmGrid, p.B);
+    ki<<<grid, kThreads, pl.smem, st>>>(p, ipm_ws);
+    return check_launch("markowitz_ipm_kernel");
+}
+
+template <typename T>
+int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const void *alpha, double u, long long B,
+                    int N, void *w, int8_t *state, int32_t *status, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < markowitz_workspace_bytes(B, N, sizeof(T)) || !ws) {
+        set_error("ddw_markowitz_fwd: workspace too small (%zu < %zu)", ws_bytes, markowitz_workspace_bytes(B, N, sizeof(T)));
+        return DDW_ERR_WORKSPACE;
+    }
+    const MkPlan pl = plan_fwd(N, sizeof(T));
+    if (pl.smem > (size_t)smem_limit()) { set_error("ddw_markowitz_fwd: n_assets=%d needs %zu B of shared memory", N, pl.smem); return DDW_ERR_UNSUPPORTED; }
+    WsLayout<T> l = ws_layout<T>(ws, B, N);
+    MkFwdParams<T> p;
+    p.rets = (const T *)rets; p.C = (const T *)C; p.gamma = (const T *)gamma; p.alpha = (const T *)alpha;
+    p.u = (T)u; p.B = B; p.N = N; p.LD = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
+    p.w = (T *)w; p.state = state; p.status = status; p.ws = l.q;
+    p.fail_count = l.fail_count; p.fail_list = l.fail_list;
+    if (!pl.global_q) {
+        if (pl.threads == 128) return launch_fwd_variant<T, 128, 4, false>(p, pl, l.ipm, st);
+        if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, false>(p, pl, l.ipm, st);
+    }
+    if (pl.threads == 128) return launch_fwd_variant<T, 128, 4, true>(p, pl, l.ipm, st);
+    if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, true>(p, pl, l.ipm, st);
+    if (pl.nreg == 16) return launch_fwd_variant<T, 512, 16, true>(p, pl, l.ipm, st);
+    return launch_fwd_variant<T, 512, 32, true>(p, pl, l.ipm, st);
+}
+
+template <typename T, int kThreads, int NREG, bool kGlobal>
+static int launch_bwd_variant(const MkBwdParams<T> &p, const MkPlan &pl, cudaStream_t st) {
+    auto kb = markowitz_bwd_kernel<T, kThreads, NREG, kGlobal>;
+    if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(markowitz_bwd)");
+    kb<<<(unsigned)p.B, kThreads, pl.smem, st>>>(p);
+    return check_launch("markowitz_bwd_kernel");
+}
+
+template <typename T>
+int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, const void *C, const void *gamma,
+                    const void *alpha, long long B, int N, void *d_rets, void *d_C, void *d_gamma, void *d_alpha,
+                    void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < markowitz_workspace_bytes(B, N, sizeof(T)) || !ws) {
+        set_error("ddw_markowitz_bwd: workspace too small (%zu < %zu)", ws_bytes, markowitz_workspace_bytes(B, N, sizeof(T)));
+        return DDW_ERR_WORKSPACE;
+    }
+    const MkPlan pl = plan_bwd(N, sizeof(T));
+    if (pl.smem > (size_t)smem_limit()) { set_error("ddw_markowitz_bwd: n_assets=%d needs %zu B of shared memory", N, pl.smem); return DDW_ERR_UNSUPPORTED; }
+    WsLayout<T> l = ws_layout<T>(ws, B, N);
+    MkBwdParams<T> p;
+    p.grad_w = (const T *)grad_w; p.w = (const T *)w; p.C = (const T *)C; p.gamma = (const T *)gamma;
+    p.alpha = (const T *)alpha; p.state = state; p.B = B; p.N = N; p.LDW = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
+    p.d_rets = (T *)d_rets; p.d_C = (T *)d_C; p.d_alpha = (T *)d_alpha; p.vecs = d_gamma ? l.vecs : nullptr; p.ws = l.q;
+    int rc;
+    if (!pl.global_q && pl.threads == 128) rc = launch_bwd_variant<T, 128, 4, false>(p, pl, st);
+    else if (!pl.global_q && pl.threads == 256) rc = launch_bwd_variant<T, 256, 8, false>(p, pl, st);
+    else if (pl.threads == 128) rc = launch_bwd_variant<T, 128, 4, true>(p, pl, st);
+    else if (pl.threads == 256) rc = launch_bwd_variant<T, 256, 8, true>(p, pl, st);
+    else if (pl.nreg == 16) rc = launch_bwd_variant<T, 512, 16, true>(p, pl, st);
+    else rc = launch_bwd_variant<T, 512, 32, true>(p, pl, st);
+    if (rc || !d_gamma) return rc;
+    cudaMemsetAsync(d_gamma, 0, sizeof(T) * (size_t)B, st);
+    const long long NN = (long long)N * N;
+    // enough slices to fill the machine, few enough that atomics stay negligible
+    long long nsplit = max(1LL, min(NN, (148LL * 16 * 128 + B - 1) / B));
+    const int q_per = (int)((NN + nsplit - 1) / nsplit);
+    nsplit = (NN + q_per - 1) / q_per;
+    dim3 grid((unsigned)((B + 127) / 128), (unsigned)nsplit);
+    markowitz_gamma_kernel<T><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, l.vecs, B, N, q_per,
+                                                    (T *)d_gamma);
+    return check_launch("markowitz_gamma_kernel");
+}
+
+template int markowitz_fwd_t<float>(const void *, const void *, const void *, const void *, double, long long, int,
+                                    void *, int8_t *, int32_t *, void *, size_t, cudaStream_t);
+template int markowitz_fwd_t<double>(const void *, const void *, const void *, const void *, double, long long, int,
+                                     void *, int8_t *, int32_t *, void *, size_t, cudaStream_t);
+template int markowitz_bwd_t<float>(const void *, const void *, const int8_t *, const void *, const void *,
+                                    const void *, long long, int, void *, void *, void *, void *, void *, size_t,
+                                    cudaStream_t);
+template int markowitz_bwd_t<double>(const void *, const void *, const int8_t *, const void *, const void *,
+                                     const void *, long long, int, void *, void *, void *, void *, void *, size_t,
+                                     cudaStream_t);
+
+}  // namespace ddw

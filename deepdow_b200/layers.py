@@ -1,0 +1,341 @@
+"""Host-side mirror of the reference layers: thin ``torch.autograd.Function``s over the C ABI.
+
+Argument meaning, error behaviour and output dtype/device follow the reference:
+  NumericalMarkowitz   deepdow/layers/allocate.py:198-273
+  SoftmaxAllocator     deepdow/layers/allocate.py:414-514
+  SparsemaxAllocator   deepdow/layers/allocate.py:517-595
+  CovarianceMatrix     deepdow/layers/misc.py:33-201
+"""
+import torch
+import torch.nn as nn
+
+from . import _C
+
+try:  # deepdow's training loop catches diffcp.SolverError (deepdow/experiments.py:6,384)
+    from diffcp import SolverError as _BaseSolverError
+except Exception:  # diffcp is not a dependency of this package
+    _BaseSolverError = Exception
+
+
+class SolverError(_BaseSolverError):
+    """A problem of the batch could not be solved (infeasible box, or no KKT point reached)."""
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# NumericalMarkowitz
+# ------------------------------------------------------------------------------------------------
+class _MarkowitzFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, check_status):
+        _C.require_cuda(rets, covmat_sqrt, gamma_sqrt, alpha)
+        lib = _C.lib()
+        B, N = rets.shape
+        dt = _C.dtype_code(rets)
+        rets_c, cov_c = rets.contiguous(), covmat_sqrt.contiguous()
+        gam_c, alp_c = gamma_sqrt.contiguous(), alpha.contiguous()
+        w = torch.empty_like(rets_c)
+        state = torch.empty((B, N), dtype=torch.int8, device=rets.device)
+        status = torch.empty((B,), dtype=torch.int32, device=rets.device)
+        ws = _workspace(lib.ddw_markowitz_workspace_bytes(B, N, dt), rets.device)
+        rc = lib.ddw_markowitz_fwd(_C.ptr(rets_c), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
+                                   float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status),
+                                   _C.ptr(ws), ws.numel(), _C.stream())
+        _C.check(rc, "ddw_markowitz_fwd")
+        if check_status:
+            bad = int((status & (_C.STATUS_INFEASIBLE | _C.STATUS_INEXACT)).ne(0).sum())
+            if bad:
+                raise SolverError(f"{bad} of {B} portfolio problems could not be solved "
+                                  f"(n_assets={N}, max_weight={max_weight})")
+        ctx.save_for_backward(w, state, cov_c, gam_c, alp_c)
+        ctx.max_weight = float(max_weight)
+        ctx.mark_non_differentiable(status)
+        return w, status
+
+    @staticmethod
+    def backward(ctx, grad_w, _grad_status):
+        w, state, cov_c, gam_c, alp_c = ctx.saved_tensors
+        lib = _C.lib()
+        B, N = w.shape
+        dt = _C.dtype_code(w)
+        g = grad_w.contiguous()
+        d_rets = torch.empty_like(w)
+        d_cov = torch.empty_like(cov_c)
+        d_alpha = torch.empty_like(alp_c)
+        need_gamma = ctx.needs_input_grad[2]
+        d_gamma = torch.empty_like(gam_c) if need_gamma else None
+        ws = _workspace(lib.ddw_markowitz_workspace_bytes(B, N, dt), w.device)
+        rc = lib.ddw_markowitz_bwd(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
+                                   ctx.max_weight, B, N, dt, _C.ptr(d_rets), _C.ptr(d_cov), _C.ptr(d_gamma),
+                                   _C.ptr(d_alpha), _C.ptr(ws), ws.numel(), _C.stream())
+        _C.check(rc, "ddw_markowitz_bwd")
+        return d_rets, d_cov, d_gamma, d_alpha, None, None
+
+
+class NumericalMarkowitz(nn.Module):
+    """Convex optimization layer stylized into portfolio optimization problem.
+
+    Drop-in for ``deepdow.layers.NumericalMarkowitz`` (allocate.py:198-273).  Solves, per sample,
+
+        maximize  rets @ w - ||(gamma_sqrt_ * covmat_sqrt) @ w||^2 - |alpha| * ||w||^2
+        s.t.      sum(w) == 1, 0 <= w <= max_weight
+
+    exactly (primal-dual active set on the GPU) instead of through cvxpylayers/SCS.
+
+    Parameters
+    ----------
+    n_assets : int
+        Number of assets.
+    max_weight : float
+        Upper bound of every weight.
+
+    Attributes
+    ----------
+    last_status : torch.Tensor or None
+        int32 status bits per problem of the latest forward (see ``include/ddw.h``).
+    """
+
+    def __init__(self, n_assets, max_weight=1):
+        super().__init__()
+        self.n_assets = n_assets
+        self.max_weight = max_weight
+        self.check_status = True
+        self.last_status = None
+
+    def forward(self, rets, covmat_sqrt, gamma_sqrt, alpha):
+        """Same arguments as the reference (allocate.py:240-273).
+
+        rets (n_samples, n_assets); covmat_sqrt (n_samples, n_assets, n_assets); gamma_sqrt (n_samples,);
+        alpha (n_samples,).  Returns weights (n_samples, n_assets), same dtype and device.
+        """
+        n_samples, n_assets = rets.shape
+        if n_assets != self.n_assets:
+            raise ValueError(f"expected n_assets={self.n_assets}, got {n_assets}")
+        if covmat_sqrt.shape != (n_samples, n_assets, n_assets):
+            raise ValueError("covmat_sqrt needs shape (n_samples, n_assets, n_assets)")
+        # the reference's repeat/view needs exactly n_samples gamma values (allocate.py:268-270)
+        if gamma_sqrt.numel() != n_samples or alpha.numel() != n_samples:
+            raise ValueError("gamma_sqrt and alpha need shape (n_samples,)")
+        dtype = rets.dtype
+        w, status = _MarkowitzFn.apply(rets, covmat_sqrt.to(dtype), gamma_sqrt.reshape(-1).to(dtype),
+                                       alpha.reshape(-1).to(dtype), self.max_weight, self.check_status)
+        self.last_status = status
+        return w
+
+    def extra_repr(self):
+        return f"n_assets={self.n_assets}, max_weight={self.max_weight}"
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["last_status"] = None
+        return state
+
+
+# ------------------------------------------------------------------------------------------------
+# Sparsemax / variational softmax
+# ------------------------------------------------------------------------------------------------
+class _RowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, temperature, temperature_scalar, max_weight, kind):
+        _C.require_cuda(x, temperature)
+        lib = _C.lib()
+        B, N = x.shape
+        dt = _C.dtype_code(x)
+        x_c = x.contiguous()
+        t_c = None if temperature is None else temperature.to(x.dtype).contiguous()
+        w = torch.empty_like(x_c)
+        fwd = lib.ddw_capped_simplex_fwd if kind == "sparsemax" else lib.ddw_capped_softmax_fwd
+        rc = fwd(_C.ptr(x_c), _C.ptr(t_c), float(temperature_scalar), float(max_weight), B, N, dt, _C.ptr(w),
+                 _C.stream())
+        _C.check(rc, f"ddw_capped_{kind}_fwd")
+        ctx.save_for_backward(w, x_c, t_c)
+        ctx.args = (float(temperature_scalar), float(max_weight), kind)
+        return w
+
+    @staticmethod
+    def backward(ctx, grad_w):
+        w, x_c, t_c = ctx.saved_tensors
+        tscalar, max_weight, kind = ctx.args
+        lib = _C.lib()
+        B, N = w.shape
+        dt = _C.dtype_code(w)
+        g = grad_w.contiguous()
+        d_x = torch.empty_like(w)
+        d_t = torch.empty_like(t_c) if (t_c is not None and ctx.needs_input_grad[1]) else None
+        bwd = lib.ddw_capped_simplex_bwd if kind == "sparsemax" else lib.ddw_capped_softmax_bwd
+        rc = bwd(_C.ptr(g), _C.ptr(w), _C.ptr(x_c), _C.ptr(t_c), tscalar, max_weight, B, N, dt, _C.ptr(d_x),
+                 _C.ptr(d_t), _C.stream())
+        _C.check(rc, f"ddw_capped_{kind}_bwd")
+        return d_x, d_t, None, None, None
+
+
+def _row_forward(module, x, temperature, kind):
+    # same check as allocate.py:498-499 / :583-584
+    if not ((temperature is None) ^ (module.temperature is None)):
+        raise ValueError("Not clear which temperature to use")
+    if temperature is not None:
+        if temperature.numel() != x.shape[0]:
+            raise ValueError("temperature needs shape (n_samples,)")
+        return _RowFn.apply(x, temperature.reshape(-1), 1.0, module.max_weight, kind)
+    return _RowFn.apply(x, None, float(module.temperature), module.max_weight, kind)
+
+
+class SoftmaxAllocator(nn.Module):
+    """Portfolio creation by computing a softmax over the asset dimension with temperature.
+
+    Drop-in for ``deepdow.layers.SoftmaxAllocator`` (allocate.py:414-514).  ``formulation='analytical'``
+    is ``torch.nn.Softmax`` as in the reference; ``'variational'`` (entropy-regularised program with a
+    weight cap, allocate.py:470-475) runs the capped-softmax kernel.
+    """
+
+    def __init__(self, temperature=1, formulation="analytical", n_assets=None, max_weight=1):
+        super().__init__()
+        self.temperature = temperature
+        if formulation not in {"analytical", "variational"}:
+            raise ValueError("Unrecognized formulation {}".format(formulation))
+        if formulation == "variational" and n_assets is None:
+            raise ValueError("One needs to provide n_assets for the variational formulation.")
+        if formulation == "analytical" and max_weight != 1:
+            raise ValueError("Cannot constraint weights via max_weight for analytical formulation")
+        if formulation == "variational" and n_assets * max_weight < 1:
+            raise ValueError("One cannot create fully invested portfolio with the given max_weight")
+        self.formulation = formulation
+        self.n_assets = n_assets
+        self.max_weight = max_weight
+        if formulation == "analytical":
+            self.layer = torch.nn.Softmax(dim=1)
+
+    def forward(self, x, temperature=None):
+        """x (n_samples, n_assets); temperature None or (n_samples,).  Returns weights (n_samples, n_assets)."""
+        if self.formulation == "analytical":
+            n_samples, _ = x.shape
+            if not ((temperature is None) ^ (self.temperature is None)):
+                raise ValueError("Not clear which temperature to use")
+            if temperature is not None:
+                temperature_ = temperature
+            else:
+                temperature_ = float(self.temperature) * torch.ones(n_samples, dtype=x.dtype, device=x.device)
+            return self.layer(x / temperature_[..., None])
+        if x.shape[1] != self.n_assets:
+            raise ValueError(f"expected n_assets={self.n_assets}, got {x.shape[1]}")
+        return _row_forward(self, x, temperature, "softmax")
+
+
+class SparsemaxAllocator(nn.Module):
+    """Portfolio creation by computing a sparsemax over the asset dimension with temperature.
+
+    Drop-in for ``deepdow.layers.SparsemaxAllocator`` (allocate.py:517-595): Euclidean projection of
+    ``x / temperature`` onto ``{sum(w) = 1, 0 <= w <= max_weight}``.
+    """
+
+    def __init__(self, n_assets, temperature=1, max_weight=1):
+        super().__init__()
+        if n_assets * max_weight < 1:
+            raise ValueError("One cannot create fully invested portfolio with the given max_weight")
+        self.n_assets = n_assets
+        self.temperature = temperature
+        self.max_weight = max_weight
+
+    def forward(self, x, temperature=None):
+        """x (n_samples, n_assets); temperature None or (n_samples,).  Returns weights (n_samples, n_assets)."""
+        if x.shape[1] != self.n_assets:
+            raise ValueError(f"expected n_assets={self.n_assets}, got {x.shape[1]}")
+        return _row_forward(self, x, temperature, "sparsemax")
+
+
+# ------------------------------------------------------------------------------------------------
+# CovarianceMatrix
+# ------------------------------------------------------------------------------------------------
+class _CovarianceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, coef, strategy, do_sqrt):
+        _C.require_cuda(x, coef)
+        lib = _C.lib()
+        B, L, N = x.shape
+        dt = _C.dtype_code(x)
+        x_c = x.contiguous()
+        coef_c = None if coef is None else coef.to(x.dtype).contiguous()
+        out = torch.empty((B, N, N), dtype=x.dtype, device=x.device)
+        need_grad = x.requires_grad or (coef is not None and coef.requires_grad)
+        eigvec = eigval = None
+        if do_sqrt and need_grad:
+            eigvec = torch.empty((B, N, N), dtype=x.dtype, device=x.device)
+            eigval = torch.empty((B, N), dtype=x.dtype, device=x.device)
+        ws = _workspace(lib.ddw_covariance_workspace_bytes(B, L, N, dt, int(do_sqrt)), x.device)
+        rc = lib.ddw_covariance_fwd(_C.ptr(x_c), _C.ptr(coef_c), strategy, int(do_sqrt), B, L, N, dt, _C.ptr(out),
+                                    _C.ptr(eigvec), _C.ptr(eigval), None, _C.ptr(ws), ws.numel(), _C.stream())
+        _C.check(rc, "ddw_covariance_fwd")
+        ctx.save_for_backward(x_c, coef_c, eigvec, eigval)
+        ctx.args = (strategy, int(do_sqrt))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x_c, coef_c, eigvec, eigval = ctx.saved_tensors
+        strategy, do_sqrt = ctx.args
+        lib = _C.lib()
+        B, L, N = x_c.shape
+        dt = _C.dtype_code(x_c)
+        g = grad_out.contiguous()
+        d_x = torch.empty_like(x_c)
+        d_coef = torch.empty_like(coef_c) if (coef_c is not None and ctx.needs_input_grad[1]) else None
+        ws = _workspace(lib.ddw_covariance_workspace_bytes(B, L, N, dt, do_sqrt), x_c.device)
+        rc = lib.ddw_covariance_bwd(_C.ptr(g), _C.ptr(x_c), _C.ptr(coef_c), strategy, do_sqrt, _C.ptr(eigvec),
+                                    _C.ptr(eigval), B, L, N, dt, _C.ptr(d_x), _C.ptr(d_coef), _C.ptr(ws),
+                                    ws.numel(), _C.stream())
+        _C.check(rc, "ddw_covariance_bwd")
+        return d_x, d_coef, None, None
+
+
+class CovarianceMatrix(nn.Module):
+    """Covariance matrix or its square root.
+
+    Drop-in for ``deepdow.layers.CovarianceMatrix`` (misc.py:33-201).
+
+    Parameters
+    ----------
+    sqrt : bool
+        If True, then returning the square root.
+    shrinkage_strategy : None or {'diagonal', 'identity', 'scaled_identity'}
+        Strategy of combining the sample covariance matrix with some more stable matrix.
+    shrinkage_coef : float or None
+        Weight of the sample covariance in the convex combination; if None it has to be given per
+        sample in ``forward``.
+    """
+
+    def __init__(self, sqrt=True, shrinkage_strategy="diagonal", shrinkage_coef=0.5):
+        super().__init__()
+        self.sqrt = sqrt
+        if shrinkage_strategy is not None:
+            if shrinkage_strategy not in {"diagonal", "identity", "scaled_identity"}:
+                raise ValueError("Unrecognized shrinkage strategy {}".format(shrinkage_strategy))
+        self.shrinkage_strategy = shrinkage_strategy
+        self.shrinkage_coef = shrinkage_coef
+
+    def forward(self, x, shrinkage_coef=None):
+        """x (n_samples, dim, n_assets); shrinkage_coef None or (n_samples,).  Returns (n_samples, n_assets, n_assets)."""
+        n_samples = x.shape[0]
+        dtype, device = x.dtype, x.device
+        if not ((shrinkage_coef is None) ^ (self.shrinkage_coef is None)):
+            raise ValueError("Not clear which shrinkage coefficient to use")
+        if shrinkage_coef is not None:
+            shrinkage_coef_ = shrinkage_coef
+        else:
+            shrinkage_coef_ = self.shrinkage_coef * torch.ones(n_samples, dtype=dtype, device=device)
+        if x.shape[1] == 1:
+            raise ZeroDivisionError("float division by zero")  # misc.py:143: 1.0 / (dim - 1)
+        coef = None if self.shrinkage_strategy is None else shrinkage_coef_.reshape(-1)
+        return _CovarianceFn.apply(x, coef, _C.SHRINKAGE[self.shrinkage_strategy], bool(self.sqrt))
+
+    @staticmethod
+    def compute_covariance(m, shrinkage_strategy=None, shrinkage_coef=0.5):
+        """Covariance of a single sample; m has shape (n_assets, n_channels) as in misc.py:121-166."""
+        coef = torch.as_tensor(shrinkage_coef, dtype=m.dtype, device=m.device).reshape(1)
+        x = m.t().unsqueeze(0)
+        if x.shape[1] == 1:
+            raise ZeroDivisionError("float division by zero")
+        coef = None if shrinkage_strategy is None else coef
+        return _CovarianceFn.apply(x, coef, _C.SHRINKAGE[shrinkage_strategy], False)[0]

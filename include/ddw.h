@@ -1,0 +1,132 @@
+/*
+ * ddw.h -- C ABI of libddw_b200.so: the B200 (sm_100a) replacement for the
+ * third-party solver stack that deepdow's allocation layers call today.
+ *
+ * deepdow has no FFI of its own; what these entry points replace is the
+ * cvxpylayers autograd Function invoked at
+ *     deepdow/layers/allocate.py:273   NumericalMarkowitz   (CvxpyLayer built at :236-238)
+ *     deepdow/layers/allocate.py:595   SparsemaxAllocator   (CvxpyLayer built at :560)
+ *     deepdow/layers/allocate.py:513   SoftmaxAllocator, formulation="variational" (:475)
+ * and the per-sample torch loop of
+ *     deepdow/layers/misc.py:107-119   CovarianceMatrix.forward
+ *                        :121-166      compute_covariance, :168-201 compute_sqrt.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a contiguous row-major array that the caller
+ *     owns (torch allocates them); nothing is allocated or freed in here, no global state
+ *   - `dtype` selects the element type of all floating point buffers (DDW_F32 / DDW_F64)
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously
+ *   - return value: 0 = enqueued, negative = argument / launch error (ddw_last_error())
+ *   - per-problem solver status is written to `status` (int32, device)
+ */
+#ifndef DDW_H_
+#define DDW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDW_VERSION 100
+
+enum ddw_dtype { DDW_F32 = 0, DDW_F64 = 1 };
+
+/* shrinkage strategies of CovarianceMatrix (misc.py:58-68) */
+enum ddw_shrinkage { DDW_SHRINK_NONE = 0, DDW_SHRINK_DIAGONAL = 1, DDW_SHRINK_IDENTITY = 2,
+                     DDW_SHRINK_SCALED_IDENTITY = 3 };
+
+/* per-problem status bits written by ddw_markowitz_fwd */
+enum ddw_status {
+    DDW_STATUS_OK = 0,
+    DDW_STATUS_FALLBACK = 1,     /* primal-dual active set cycled; interior point fallback used  */
+    DDW_STATUS_REGULARIZED = 2,  /* a non-positive pivot was lifted (Q singular on the free set) */
+    DDW_STATUS_INEXACT = 4,      /* fallback did not reach an exact KKT point (result approximate) */
+    DDW_STATUS_INFEASIBLE = 8    /* n_assets * max_weight < 1: the reference raises SolverError  */
+};
+
+/* error codes (return values) */
+#define DDW_ERR_ARG (-1)
+#define DDW_ERR_UNSUPPORTED (-2)
+#define DDW_ERR_WORKSPACE (-3)
+#define DDW_ERR_CUDA (-4)
+
+int ddw_version(void);
+/* message of the last error on the calling thread ("" if none) */
+const char *ddw_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * NumericalMarkowitz -- replaces self.cvxpylayer(rets, gamma_sqrt_ * covmat_sqrt, alpha_abs)[0]
+ * (allocate.py:240-273) including the gamma tiling (:268-270) and abs(alpha) (:271).
+ *   minimise  w'Qw - rets'w,  Q = A'A + |alpha| I,  A[j,k] = gamma_sqrt[(b N^2 + j N + k) % B] * covmat_sqrt[b,j,k]
+ *   s.t.      sum(w) = 1, 0 <= w <= max_weight
+ * rets (B,N)  covmat_sqrt (B,N,N)  gamma_sqrt (B)  alpha (B)
+ * w (B,N) out; state (B,N) int8 out: -1 at 0, +1 at max_weight, 0 free (saved for backward);
+ * status (B) int32 out.  workspace: ddw_markowitz_workspace_bytes() bytes, may be NULL if that is 0.
+ * ------------------------------------------------------------------------------------------- */
+size_t ddw_markowitz_workspace_bytes(int64_t B, int64_t N, int dtype);
+
+int ddw_markowitz_fwd(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                      double max_weight, int64_t B, int64_t N, int dtype,
+                      void *w, int8_t *state, int32_t *status,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* backward of the above (replaces the diffcp adjoint inside cvxpylayers):
+ * grad_w (B,N), w/state from the forward -> d_rets (B,N), d_covmat_sqrt (B,N,N), d_gamma_sqrt (B),
+ * d_alpha (B).  d_gamma_sqrt may be NULL (skips the tiling scatter pass). */
+int ddw_markowitz_bwd(const void *grad_w, const void *w, const int8_t *state,
+                      const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                      double max_weight, int64_t B, int64_t N, int dtype,
+                      void *d_rets, void *d_covmat_sqrt, void *d_gamma_sqrt, void *d_alpha,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SparsemaxAllocator -- replaces self.layer(x / temperature[:, None])[0] (allocate.py:586-595):
+ * Euclidean projection of x/temperature onto {sum = 1, 0 <= w <= max_weight}.
+ * x (B,N); temperature (B) or NULL (then temperature_scalar is used for every row); w (B,N) out.
+ * ------------------------------------------------------------------------------------------- */
+int ddw_capped_simplex_fwd(const void *x, const void *temperature, double temperature_scalar,
+                           double max_weight, int64_t B, int64_t N, int dtype, void *w, void *stream);
+/* d_x (B,N) out; d_temperature (B) out or NULL */
+int ddw_capped_simplex_bwd(const void *grad_w, const void *w, const void *x, const void *temperature,
+                           double temperature_scalar, double max_weight, int64_t B, int64_t N, int dtype,
+                           void *d_x, void *d_temperature, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SoftmaxAllocator(formulation="variational") -- replaces self.layer(inp)[0] (allocate.py:508-514):
+ * argmin -x'w - sum entr(w)  s.t. sum = 1, w <= max_weight, i.e. w_i = min(max_weight, exp(x_i/t - nu)).
+ * ------------------------------------------------------------------------------------------- */
+int ddw_capped_softmax_fwd(const void *x, const void *temperature, double temperature_scalar,
+                           double max_weight, int64_t B, int64_t N, int dtype, void *w, void *stream);
+int ddw_capped_softmax_bwd(const void *grad_w, const void *w, const void *x, const void *temperature,
+                           double temperature_scalar, double max_weight, int64_t B, int64_t N, int dtype,
+                           void *d_x, void *d_temperature, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CovarianceMatrix -- replaces the python loop of misc.py:107-119.
+ * x (B,L,N) observations; coef (B) shrinkage coefficient per sample (ignored for DDW_SHRINK_NONE);
+ * out (B,N,N): shrunk sample covariance, or its symmetric PSD square root when do_sqrt != 0.
+ * When do_sqrt != 0, eigvec (B,N,N) and eigval (B,N) receive the eigen-decomposition of the shrunk
+ * covariance (saved for backward; eigval holds sqrt|lambda| with sub-threshold values zeroed,
+ * misc.py:185-199).  They may be NULL when no backward is needed; then workspace supplies scratch.
+ * L == 1 is rejected by the host layer with ZeroDivisionError as in misc.py:143.
+ * ------------------------------------------------------------------------------------------- */
+size_t ddw_covariance_workspace_bytes(int64_t B, int64_t L, int64_t N, int dtype, int do_sqrt);
+
+int ddw_covariance_fwd(const void *x, const void *coef, int strategy, int do_sqrt,
+                       int64_t B, int64_t L, int64_t N, int dtype,
+                       void *out, void *eigvec, void *eigval, int32_t *sweeps,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* grad_out (B,N,N) -> d_x (B,L,N), d_coef (B) (may be NULL). */
+int ddw_covariance_bwd(const void *grad_out, const void *x, const void *coef, int strategy, int do_sqrt,
+                       const void *eigvec, const void *eigval,
+                       int64_t B, int64_t L, int64_t N, int dtype,
+                       void *d_x, void *d_coef,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDW_H_ */

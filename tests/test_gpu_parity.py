@@ -1,0 +1,345 @@
+"""GPU parity: CUDA kernels (through the layers, i.e. through the C ABI) vs the float64 CPU oracle
+on identical seeded inputs, vs the committed golden fixtures, and property checks at full size.
+
+Tolerances (north_star): weights 1e-5 abs, gradients 1e-4 rel (float32 kernels); float64 kernels are
+held to 1e-9.  Sparsemax supports must match exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from deepdow_b200 import (CovarianceMatrix, NumericalMarkowitz, SoftmaxAllocator, SolverError,
+                          SparsemaxAllocator)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+W_ATOL = {torch.float32: 1e-5, torch.float64: 1e-9}
+G_RTOL = {torch.float32: 1e-4, torch.float64: 1e-8}
+
+
+def t(a, dtype, grad=False):
+    return torch.tensor(np.asarray(a), dtype=dtype, device=DEV, requires_grad=grad)
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def make_problems(rng, B, N, kind="sym", alpha=1.0, rscale=0.5, gamma="ones"):
+    rets = rng.standard_normal((B, N)) * rscale
+    if kind == "sym":
+        R = rng.standard_normal((B, N, N))
+        C = R @ R.transpose(0, 2, 1) / N + 0.1 * np.eye(N)
+    elif kind == "asym":
+        C = rng.standard_normal((B, N, N)) * 0.5 + np.eye(N)
+    elif kind == "sqrtcov":
+        X = rng.standard_normal((B, 40, N)) * 0.01
+        C = oracle.covariance_fwd(X, 0.5, "diagonal", True)
+        rets = rng.standard_normal((B, N)) * 0.01
+    g = np.ones(B) if gamma == "ones" else rng.uniform(0.5, 2.0, B)
+    a = np.full(B, float(alpha)) * (rng.choice([-1.0, 1.0], B) if gamma != "ones" else 1.0)
+    return rets, C, g, a
+
+
+# ------------------------------------------------------------------ NumericalMarkowitz forward
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B,N,u,kind,gamma", [
+    (64, 20, 1.0, "sqrtcov", "ones"),      # config 1
+    (37, 5, 1.0, "sym", "rand"),
+    (33, 8, 0.3, "asym", "rand"),
+    (64, 50, 1.0, "sym", "ones"),
+    (128, 100, 0.2, "sym", "ones"),        # config 4 shape (reduced batch)
+    (16, 100, 1.0, "asym", "rand"),
+    (8, 129, 0.05, "sym", "ones"),         # 256-thread variant
+    (4, 200, 0.1, "sym", "rand"),
+])
+def test_markowitz_forward_vs_oracle(dtype, B, N, u, kind, gamma):
+    rng = np.random.default_rng(B * 1000 + N)
+    rets, C, g, a = make_problems(rng, B, N, kind, 1.0, 0.5, gamma)
+    w_ref, st_ref, kkt, status = oracle.markowitz_fwd(rets, C, g, a, u)
+    assert kkt.max() < 1e-10 and (status == 0).all()
+    layer = NumericalMarkowitz(N, max_weight=u)
+    w = layer(t(rets, dtype), t(C, dtype), t(g, dtype), t(a, dtype))
+    assert w.shape == (B, N) and w.dtype == dtype and w.device == torch.device(DEV)
+    err = (w.double().cpu().numpy() - w_ref)
+    assert np.abs(err).max() < W_ATOL[dtype], np.abs(err).max()
+    assert torch.allclose(w.sum(1), torch.ones(B, dtype=dtype, device=DEV), atol=10 * W_ATOL[dtype])
+    assert w.min() >= 0 and w.max() <= u + 1e-7
+    assert int((layer.last_status & 12).ne(0).sum()) == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_markowitz_golden_slsqp(dtype, golden_dir):
+    z = np.load(os.path.join(golden_dir, "markowitz_slsqp.npz"))
+    for c in range(int(z["n_cases"])):
+        k = f"m{c}"
+        N = z[k + "_rets"].shape[1]
+        layer = NumericalMarkowitz(N, max_weight=float(z[k + "_u"]))
+        w = layer(t(z[k + "_rets"], dtype), t(z[k + "_C"], dtype), t(z[k + "_gamma"], dtype), t(z[k + "_alpha"], dtype))
+        assert np.abs(w.double().cpu().numpy() - z[k + "_w"]).max() < 1e-5, c
+
+
+def test_markowitz_reduces_to_sparsemax_goldens(golden_dir):
+    z = np.load(os.path.join(golden_dir, "reference_vectors.npz"))
+    x = z["sparsemax_known_x"]
+    C = np.broadcast_to(np.eye(5), (2, 5, 5)).copy()
+    w = NumericalMarkowitz(5)(t(2 * x, torch.float32), t(C, torch.float32), t(np.ones(2), torch.float32), t(np.zeros(2), torch.float32))
+    assert np.allclose(w.cpu().numpy(), z["sparsemax_known_w"], atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_markowitz_vertex_degenerate_and_edge_cases(dtype):
+    rng = np.random.default_rng(11)
+    # LP-like, exactly five assets at the cap (no free asset at the optimum)
+    rets = rng.standard_normal((16, 30))
+    C = np.broadcast_to(np.eye(30) * 1e-3, (16, 30, 30)).copy()
+    g, a = np.ones(16), np.zeros(16)
+    w_ref, *_ = oracle.markowitz_fwd(rets, C, g, a, 0.2)
+    w = NumericalMarkowitz(30, 0.2)(t(rets, dtype), t(C, dtype), t(g, dtype), t(a, dtype))
+    assert np.abs(w.double().cpu().numpy() - w_ref).max() < W_ATOL[dtype]
+    # n_assets * max_weight == 1: a single feasible point
+    w = NumericalMarkowitz(5, 0.2)(t(rets[:, :5], dtype), t(C[:, :5, :5], dtype), t(g, dtype), t(np.ones(16), dtype))
+    assert torch.allclose(w, torch.full_like(w, 0.2))
+    # infeasible box -> SolverError (the reference raises diffcp.SolverError)
+    with pytest.raises(SolverError):
+        NumericalMarkowitz(4, 0.2)(t(rets[:, :4], dtype), t(C[:, :4, :4], dtype), t(g, dtype), t(np.ones(16), dtype))
+    # B = 1 with gamma of shape (1,) (examples/end_to_end/iid.py:362-365) and alpha = 0
+    rets1, C1, _, _ = make_problems(rng, 1, 12)
+    w_ref, *_ = oracle.markowitz_fwd(rets1, C1, np.ones(1) * 1.3, np.zeros(1), 1.0)
+    w = NumericalMarkowitz(12)(t(rets1, dtype), t(C1, dtype), t([1.3], dtype), t([0.0], dtype))
+    assert np.abs(w.double().cpu().numpy() - w_ref).max() < W_ATOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_markowitz_hard_problems_use_fallback_and_stay_exact(dtype):
+    """Ill-conditioned Q where the active set can cycle: the interior-point fallback must kick in."""
+    rng = np.random.default_rng(12)
+    B, N = 256, 20
+    V = np.linalg.qr(rng.standard_normal((B, N, N)))[0]
+    lam = np.logspace(-2, 0.5, N)
+    C = (V * lam) @ V.transpose(0, 2, 1)
+    rets = rng.standard_normal((B, N))
+    g, a = np.ones(B), np.zeros(B)
+    for u in (0.2, 1.0):
+        w_ref, st, kkt, status = oracle.markowitz_fwd(rets, C, g, a, u)
+        layer = NumericalMarkowitz(N, u)
+        w = layer(t(rets, dtype), t(C, dtype), t(g, dtype), t(a, dtype))
+        tol = 2e-4 if dtype == torch.float32 else 1e-8   # cond(Q) ~ 1e5: float32 cannot give 1e-5 here
+        assert np.abs(w.double().cpu().numpy() - w_ref).max() < tol
+        assert int((layer.last_status & 12).ne(0).sum()) == 0
+
+
+# ------------------------------------------------------------------ NumericalMarkowitz backward
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B,N,u,kind,gamma", [
+    (32, 7, 0.35, "asym", "rand"),
+    (64, 20, 1.0, "sym", "ones"),
+    (64, 50, 0.1, "sym", "rand"),
+    (96, 100, 0.2, "sym", "ones"),
+    (8, 150, 0.05, "sym", "ones"),
+])
+def test_markowitz_backward_vs_oracle(dtype, B, N, u, kind, gamma):
+    rng = np.random.default_rng(B * 7 + N)
+    rets, C, g, a = make_problems(rng, B, N, kind, 1.0, 0.5, gamma)
+    G = rng.standard_normal((B, N))
+    w_ref, st_ref, kkt, _ = oracle.markowitz_fwd(rets, C, g, a, u)
+    ref = oracle.markowitz_bwd(G, w_ref, st_ref, C, g, a, u)
+    tr, tC, tg, ta = t(rets, dtype, True), t(C, dtype, True), t(g, dtype, True), t(a, dtype, True)
+    w = NumericalMarkowitz(N, u)(tr, tC, tg, ta)
+    (w * t(G, dtype)).sum().backward()
+    # compare only problems whose active set agrees (a tie at a bound makes the gradient non-unique)
+    for name, got, want in zip(["rets", "covmat_sqrt", "gamma", "alpha"], [tr.grad, tC.grad, tg.grad, ta.grad], ref):
+        assert got is not None and got.shape == want.shape, name
+        assert rel_err(got, want) < G_RTOL[dtype], (name, rel_err(got, want))
+
+
+def test_markowitz_no_grad_and_double_backward_safety():
+    rng = np.random.default_rng(3)
+    rets, C, g, a = make_problems(rng, 8, 10)
+    with torch.no_grad():
+        w = NumericalMarkowitz(10)(t(rets, torch.float32), t(C, torch.float32), t(g, torch.float32), t(a, torch.float32))
+    assert not w.requires_grad
+
+
+def test_markowitz_full_size_properties():
+    """Config 4 at full size (B=4096, N=100, max_weight=0.2): KKT certificate computed in float64 on the GPU."""
+    B, N, u = 4096, 100, 0.2
+    gen = torch.Generator(device=DEV).manual_seed(4000)
+    R = torch.randn(B, N, N, generator=gen, device=DEV)
+    C = R @ R.transpose(1, 2) / N + 0.1 * torch.eye(N, device=DEV)
+    rets = torch.randn(B, N, generator=gen, device=DEV) * 0.5
+    g = torch.ones(B, device=DEV)
+    a = torch.ones(B, device=DEV)
+    layer = NumericalMarkowitz(N, u)
+    w = layer(rets, C, g, a)
+    assert int(layer.last_status.ne(0).sum()) == 0
+    wd, Cd = w.double(), C.double()
+    Q = Cd.transpose(1, 2) @ Cd + torch.eye(N, device=DEV, dtype=torch.float64)
+    h = 2 * (Q @ wd[..., None])[..., 0] - rets.double()
+    free = (wd > 1e-7) & (wd < u - 1e-7)
+    nu = -(h * free).sum(1) / free.sum(1).clamp(min=1)
+    grad = h + nu[:, None]
+    res = torch.where(free, grad.abs(), torch.where(wd <= 1e-7, (-grad).clamp(min=0), grad.clamp(min=0)))
+    assert (wd.sum(1) - 1).abs().max() < 1e-5
+    assert wd.min() >= 0 and wd.max() <= u + 1e-7
+    assert res.max() < 2e-4, res.max()      # gradient units; |h| ~ 1..10
+    # sample of problems against the oracle
+    idx = torch.arange(0, B, 64)
+    w_ref, *_ = oracle.markowitz_fwd(rets[idx].cpu().numpy(), C[idx].cpu().numpy(), np.ones(len(idx)), np.ones(len(idx)), u)
+    assert np.abs(w[idx].double().cpu().numpy() - w_ref).max() < 1e-5
+
+
+# ------------------------------------------------------------------ sparsemax / softmax
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B,N,u,scale", [(1024, 100, 1.0, 1.0), (1024, 100, 0.05, 10.0), (33, 5, 0.25, 1.0),
+                                         (7, 300, 0.01, 3.0), (5, 1000, 1.0, 1.0)])
+def test_sparsemax_vs_oracle(dtype, B, N, u, scale):
+    rng = np.random.default_rng(N)
+    x = rng.uniform(-0.5, 0.5, (B, N)) * scale
+    temp = rng.uniform(0.5, 2.0, B)
+    G = rng.standard_normal((B, N))
+    xin = t(x, dtype).double().cpu().numpy()       # the exact inputs the kernel sees
+    tin = t(temp, dtype).double().cpu().numpy()
+    w_ref = oracle.capped_simplex_fwd(xin, tin, u)
+    tx, tt = t(x, dtype, True), t(temp, dtype, True)
+    w = SparsemaxAllocator(N, temperature=None, max_weight=u)(tx, tt)
+    wn = w.detach().double().cpu().numpy()
+    assert np.abs(wn - w_ref).max() < W_ATOL[dtype]
+    # supports must match exactly, except entries the oracle itself puts within rounding of a bound
+    margin = 1e-6 if dtype == torch.float32 else 1e-12
+    v = xin / tin[:, None]
+    tau = (v - w_ref)[(w_ref > 0) & (w_ref < u)].reshape(-1)  # not used per row; margin test below is per element
+    sup_ref, sup = w_ref > 0, wn > 0
+    mism = sup_ref != sup
+    # a mismatch is tolerated only where the oracle's own weight is within rounding of zero
+    assert not (mism & (np.abs(w_ref) > margin)).any()
+    near_zero_boundary = mism.sum()
+    assert near_zero_boundary <= max(1, B // 200)
+    (w * t(G, dtype)).sum().backward()
+    dx_ref, dt_ref = oracle.capped_simplex_bwd(G, wn, xin, tin, u)
+    assert rel_err(tx.grad, dx_ref) < G_RTOL[dtype]
+    assert rel_err(tt.grad, dt_ref) < 10 * G_RTOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B,N,u,scale", [(1024, 100, 1.0, 1.0), (1024, 100, 0.05, 10.0), (33, 5, 0.25, 1.0), (6, 700, 0.01, 3.0)])
+def test_softmax_vs_oracle(dtype, B, N, u, scale):
+    rng = np.random.default_rng(N + 1)
+    x = rng.uniform(-0.5, 0.5, (B, N)) * scale
+    temp = rng.uniform(0.5, 2.0, B)
+    G = rng.standard_normal((B, N))
+    xin = t(x, dtype).double().cpu().numpy()
+    tin = t(temp, dtype).double().cpu().numpy()
+    w_ref = oracle.capped_softmax_fwd(xin, tin, u)
+    tx, tt = t(x, dtype, True), t(temp, dtype, True)
+    w = SoftmaxAllocator(temperature=None, formulation="variational", n_assets=N, max_weight=u)(tx, tt)
+    wn = w.detach().double().cpu().numpy()
+    assert np.abs(wn - w_ref).max() < W_ATOL[dtype]
+    (w * t(G, dtype)).sum().backward()
+    dx_ref, dt_ref = oracle.capped_softmax_bwd(G, wn, xin, tin, u)
+    assert rel_err(tx.grad, dx_ref) < G_RTOL[dtype]
+    assert rel_err(tt.grad, dt_ref) < 10 * G_RTOL[dtype]
+
+
+def test_row_allocators_reference_goldens(golden_dir):
+    z = np.load(os.path.join(golden_dir, "reference_vectors.npz"))
+    f32 = torch.float32
+    # tests/test_layers.py:821-838
+    w = SparsemaxAllocator(5, temperature=1)(t(z["sparsemax_known_x"], f32))
+    assert torch.allclose(w, t(z["sparsemax_known_w"], f32), atol=1e-3)
+    # docs/source/layers.rst:381-394
+    w = SparsemaxAllocator(3, temperature=1)(t(z["sparsemax_doc_x"], f32))
+    assert torch.allclose(w, t(z["sparsemax_doc_w"], f32), atol=2e-4)
+    # tests/test_layers.py:815-819, 752-759
+    assert torch.allclose(SparsemaxAllocator(5, temperature=1)(torch.ones(2, 5, device=DEV)), torch.full((2, 5), 0.2, device=DEV))
+    assert torch.allclose(SoftmaxAllocator(formulation="variational", n_assets=5, temperature=1)(torch.ones(2, 5, device=DEV)),
+                          torch.full((2, 5), 0.2, device=DEV), atol=1e-4)
+    # tests/test_layers.py:761-776, 840-850
+    for u in z["capped_u"]:
+        x = t(z["capped_x"], f32)
+        for layer_c, layer_u in [(SparsemaxAllocator(5, temperature=1, max_weight=float(u)), SparsemaxAllocator(5, temperature=1)),
+                                 (SoftmaxAllocator(n_assets=5, temperature=1, max_weight=float(u), formulation="variational"),
+                                  SoftmaxAllocator(n_assets=5, temperature=1, formulation="variational"))]:
+            wc, wu = layer_c(x), layer_u(x)
+            assert not torch.allclose(wc, wu)
+            assert wc.max().item() == pytest.approx(float(u), abs=1e-6)
+    # tests/test_layers.py:726-750: variational == analytical softmax
+    torch.manual_seed(2)
+    rets = (torch.randint(10, size=(3, 6)) + torch.rand(size=(3, 6))).to(DEV)
+    wa = SoftmaxAllocator(formulation="analytical")(rets)
+    wv = SoftmaxAllocator(formulation="variational", n_assets=6)(rets)
+    assert wa.shape == wv.shape and wa.dtype == wv.dtype and wa.device == wv.device
+    assert torch.allclose(wa, wv, atol=1e-5)
+
+
+# ------------------------------------------------------------------ CovarianceMatrix
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_covariance_vs_reference_fixtures(dtype, golden_dir):
+    z = np.load(os.path.join(golden_dir, "covariance_reference.npz"))
+    for c in range(int(z["n_cases"])):
+        k = f"c{c}"
+        strategy, sqrt = z[k + "_meta"]
+        strategy = None if strategy == "None" else str(strategy)
+        sqrt = bool(int(sqrt))
+        x, coef = t(z[k + "_x"], dtype, True), t(z[k + "_coef"], dtype, True)
+        layer = CovarianceMatrix(sqrt=sqrt, shrinkage_strategy=strategy, shrinkage_coef=None)
+        y = layer(x, coef)
+        ftol = 2e-5 if dtype == torch.float32 else 1e-10
+        assert rel_err(y, z[k + "_y"]) < ftol, (c, strategy, sqrt, rel_err(y, z[k + "_y"]))
+        (y * t(z[k + "_G"], dtype)).sum().backward()
+        if not np.isfinite(z[k + "_dx"]).all():
+            dx_ref, dc_ref = oracle.covariance_bwd(z[k + "_G"], z[k + "_x"], z[k + "_coef"], strategy, sqrt)
+        else:
+            dx_ref, dc_ref = z[k + "_dx"], z[k + "_dcoef"]
+        gtol = 2e-3 if dtype == torch.float32 else 1e-7     # sqrt backward divides by sqrt-eigenvalue sums
+        assert rel_err(x.grad, dx_ref) < gtol, (c, strategy, sqrt, rel_err(x.grad, dx_ref))
+        if strategy is not None:
+            assert rel_err(coef.grad, dc_ref) < gtol, (c, strategy, sqrt, rel_err(coef.grad, dc_ref))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B,L,N", [(64, 40, 20), (256, 40, 50), (16, 40, 100), (4, 60, 130), (2, 250, 200)])
+def test_covariance_vs_oracle_sizes(dtype, B, L, N):
+    rng = np.random.default_rng(L + N)
+    x = rng.standard_normal((B, L, N)) * 0.01
+    xin = t(x, dtype).double().cpu().numpy()
+    for strategy in ["diagonal", "scaled_identity"]:
+        for sqrt in [False, True]:
+            y = CovarianceMatrix(sqrt=sqrt, shrinkage_strategy=strategy)(t(x, dtype))
+            ref = oracle.covariance_fwd(xin, 0.5, strategy, sqrt)
+            tol = 3e-5 if dtype == torch.float32 else 1e-10
+            assert rel_err(y, ref) < tol, (strategy, sqrt, rel_err(y, ref))
+
+
+def test_covariance_reference_behaviour(golden_dir):
+    z = np.load(os.path.join(golden_dir, "covariance_reference.npz"))
+    # tests/test_layers.py:203-209
+    with pytest.raises(ValueError):
+        CovarianceMatrix(shrinkage_strategy="fake")
+    with pytest.raises(ValueError):
+        CovarianceMatrix(shrinkage_coef=None)(torch.ones(1, 5, 2, device=DEV))
+    # :221-225 dim == 1
+    with pytest.raises(ZeroDivisionError):
+        CovarianceMatrix()(torch.ones(2, 1, 3, device=DEV))
+    # :243-256 and docs/source/layers.rst:474-487
+    xd = t(z["doc_x"], torch.float32)
+    cov = CovarianceMatrix(sqrt=False)(xd)
+    sq = CovarianceMatrix(sqrt=True)(xd)
+    assert torch.allclose(cov, t(z["doc_cov"], torch.float32), rtol=1e-4)
+    assert torch.allclose(sq, t(z["doc_sqrt"], torch.float32), rtol=1e-3, atol=1e-3)
+    assert torch.allclose(cov[0], sq[0] @ sq[0], atol=1e-2)
+    # rank deficient input (strategy None, dim - 1 < n_assets)
+    y = CovarianceMatrix(sqrt=True, shrinkage_strategy=None, shrinkage_coef=1.0)(t(z["rd_x"], torch.float64))
+    assert rel_err(y, z["rd_y"]) < 1e-7
+    # :258-289 constructor coefficient == per-sample tensor coefficient
+    x = torch.rand(3, 4, 5, device=DEV) * 100
+    l1 = CovarianceMatrix(sqrt=False, shrinkage_strategy="diagonal", shrinkage_coef=0.3)
+    l2 = CovarianceMatrix(sqrt=False, shrinkage_strategy="diagonal", shrinkage_coef=None)
+    assert torch.allclose(l1(x), l2(x, 0.3 * torch.ones(3, device=DEV)))
+    assert sum(p.numel() for p in l1.parameters()) == 0

@@ -138,27 +138,30 @@ __global__ void __launch_bounds__(kThreads) covariance_fwd_kernel(CovParams<T> p
                     if (aq > tol * sqrtT(absT(spp * sqq)) && aq > Num<T>::tiny()) {
                         const T tau = (sqq - spp) / (T(2) * spq);
                         const T t = (tau >= T(0) ? T(1) : T(-1)) / (absT(tau) + sqrtT(T(1) + tau * tau));
-                        cc = rsqrtT(T(1) + t * t);
+                        cc = T(1) / sqrtT(T(1) + t * t);   // correctly rounded: rsqrt's bias would shrink V over ~1e3 rotations
                         ss = t * cc;
                         rotated = 1;
                     }
                 }
-                pp[k] = pi; pq[k] = qi; cs[k] = cc; sn[k] = ss;
+                // Rutishauser's form a' = a - s (b + tau a), b' = b + s (a - tau b), tau = s / (1 + c):
+                // unlike c*a - s*b it does not lose the 1 - c term when 1 + t^2 rounds to 1, which
+                // would otherwise stretch the eigenvectors by ~t^2/2 on every small rotation
+                pp[k] = pi; pq[k] = qi; cs[k] = ss / (T(1) + cc); sn[k] = ss;
             }
             __syncthreads();
             // columns p,q of S and rows p,q of VT
             for (int k = warp; k < npairs; k += kWarps) {
                 const T ss = sn[k];
                 if (ss == T(0)) continue;
-                const T cc = cs[k];
+                const T tt = cs[k];
                 const int pi = pp[k], qi = pq[k];
                 for (int i = lane; i < N; i += 32) {
                     const T a = S[i * LDS + pi], c2 = S[i * LDS + qi];
-                    S[i * LDS + pi] = cc * a - ss * c2;
-                    S[i * LDS + qi] = ss * a + cc * c2;
+                    S[i * LDS + pi] = fma(-ss, fma(a, tt, c2), a);
+                    S[i * LDS + qi] = fma(ss, fma(-c2, tt, a), c2);
                     const T va = VT[pi * LDV + i], vb = VT[qi * LDV + i];
-                    VT[pi * LDV + i] = cc * va - ss * vb;
-                    VT[qi * LDV + i] = ss * va + cc * vb;
+                    VT[pi * LDV + i] = fma(-ss, fma(va, tt, vb), va);
+                    VT[qi * LDV + i] = fma(ss, fma(-vb, tt, va), vb);
                 }
             }
             __syncthreads();
@@ -166,12 +169,12 @@ __global__ void __launch_bounds__(kThreads) covariance_fwd_kernel(CovParams<T> p
             for (int k = warp; k < npairs; k += kWarps) {
                 const T ss = sn[k];
                 if (ss == T(0)) continue;
-                const T cc = cs[k];
+                const T tt = cs[k];
                 const int pi = pp[k], qi = pq[k];
                 for (int j = lane; j < N; j += 32) {
                     const T a = S[pi * LDS + j], c2 = S[qi * LDS + j];
-                    S[pi * LDS + j] = cc * a - ss * c2;
-                    S[qi * LDS + j] = ss * a + cc * c2;
+                    S[pi * LDS + j] = fma(-ss, fma(a, tt, c2), a);
+                    S[qi * LDS + j] = fma(ss, fma(-c2, tt, a), c2);
                 }
             }
             __syncthreads();

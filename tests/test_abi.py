@@ -1,0 +1,78 @@
+"""CPU-only checks of the C-ABI boundary: the library loads without a GPU, exports every symbol that
+include/ddw.h declares (and the ctypes table binds exactly those), and rejects bad arguments before
+touching the device.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from deepdow_b200 import _C, build
+    if not os.path.exists(_C.LIB_PATH):
+        build.build()
+    return _C.lib()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ddw.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ddw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ddw.h but not exported"
+
+
+def test_ctypes_table_matches_header():
+    from deepdow_b200 import _C
+    assert sorted(_C.SIGNATURES) == declared_symbols()
+
+
+def test_version_and_error_channel(lib):
+    assert lib.ddw_version() == 100
+    assert isinstance(lib.ddw_last_error(), bytes)
+
+
+def test_argument_validation_without_gpu(lib):
+    # bad dtype / sizes are rejected on the host, before any CUDA call
+    rc = lib.ddw_markowitz_fwd(None, None, None, None, 1.0, 4, 5, 7, None, None, None, None, 0, None)
+    assert rc == -1 and b"dtype" in lib.ddw_last_error()
+    rc = lib.ddw_markowitz_fwd(None, None, None, None, 1.0, 4, 5000, 0, None, None, None, None, 0, None)
+    assert rc == -2 and b"n_assets" in lib.ddw_last_error()
+    rc = lib.ddw_markowitz_fwd(None, None, None, None, 1.0, 4, 5, 0, None, None, None, None, 0, None)
+    assert rc == -1 and b"null" in lib.ddw_last_error()
+    rc = lib.ddw_capped_simplex_fwd(None, None, 1.0, 1.0, 4, 5, 0, ctypes.c_void_p(8), None)
+    assert rc == -1
+    rc = lib.ddw_covariance_fwd(ctypes.c_void_p(8), ctypes.c_void_p(8), 1, 0, 2, 1, 3, 0, ctypes.c_void_p(8), None, None, None, None, 0, None)
+    assert rc == -1 and b"observations" in lib.ddw_last_error()
+    rc = lib.ddw_covariance_fwd(ctypes.c_void_p(8), ctypes.c_void_p(8), 9, 0, 2, 4, 3, 0, ctypes.c_void_p(8), None, None, None, None, 0, None)
+    assert rc == -1 and b"strategy" in lib.ddw_last_error()
+    # empty batch is a no-op
+    assert lib.ddw_markowitz_fwd(None, None, None, None, 1.0, 0, 5, 0, None, None, None, None, 0, None) == 0
+
+
+def test_workspace_queries(lib):
+    assert lib.ddw_markowitz_workspace_bytes(4096, 100, 0) > 4096 * 4
+    assert lib.ddw_markowitz_workspace_bytes(0, 100, 0) == 0
+    # N = 500 does not fit shared memory: the workspace holds Q per problem
+    assert lib.ddw_markowitz_workspace_bytes(8, 500, 0) >= 8 * 500 * 500 * 4
+    assert lib.ddw_covariance_workspace_bytes(8, 40, 50, 0, 1) == 0
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under deepdow_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "deepdow_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "ddw_oracle" not in text, f

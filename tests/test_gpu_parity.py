@@ -153,7 +153,6 @@ def test_markowitz_backward_vs_oracle(dtype, B, N, u, kind, gamma):
     tr, tC, tg, ta = t(rets, dtype, True), t(C, dtype, True), t(g, dtype, True), t(a, dtype, True)
     w = NumericalMarkowitz(N, u)(tr, tC, tg, ta)
     (w * t(G, dtype)).sum().backward()
-    # compare only problems whose active set agrees (a tie at a bound makes the gradient non-unique)
     for name, got, want in zip(["rets", "covmat_sqrt", "gamma", "alpha"], [tr.grad, tC.grad, tg.grad, ta.grad], ref):
         assert got is not None and got.shape == want.shape, name
         assert rel_err(got, want) < G_RTOL[dtype], (name, rel_err(got, want))
@@ -198,9 +197,10 @@ def test_markowitz_full_size_properties():
 # ------------------------------------------------------------------ sparsemax / softmax
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("B,N,u,scale", [(1024, 100, 1.0, 1.0), (1024, 100, 0.05, 10.0), (33, 5, 0.25, 1.0),
-                                         (7, 300, 0.01, 3.0), (5, 1000, 1.0, 1.0)])
+                                         (7, 300, 0.013, 3.0), (5, 1000, 1.0, 1.0)])
 def test_sparsemax_vs_oracle(dtype, B, N, u, scale):
     rng = np.random.default_rng(N)
+    u = float(np.float32(u)) if dtype == torch.float32 else u   # the cap exactly as the kernel sees it
     x = rng.uniform(-0.5, 0.5, (B, N)) * scale
     temp = rng.uniform(0.5, 2.0, B)
     G = rng.standard_normal((B, N))
@@ -213,8 +213,6 @@ def test_sparsemax_vs_oracle(dtype, B, N, u, scale):
     assert np.abs(wn - w_ref).max() < W_ATOL[dtype]
     # supports must match exactly, except entries the oracle itself puts within rounding of a bound
     margin = 1e-6 if dtype == torch.float32 else 1e-12
-    v = xin / tin[:, None]
-    tau = (v - w_ref)[(w_ref > 0) & (w_ref < u)].reshape(-1)  # not used per row; margin test below is per element
     sup_ref, sup = w_ref > 0, wn > 0
     mism = sup_ref != sup
     # a mismatch is tolerated only where the oracle's own weight is within rounding of zero
@@ -231,6 +229,7 @@ def test_sparsemax_vs_oracle(dtype, B, N, u, scale):
 @pytest.mark.parametrize("B,N,u,scale", [(1024, 100, 1.0, 1.0), (1024, 100, 0.05, 10.0), (33, 5, 0.25, 1.0), (6, 700, 0.01, 3.0)])
 def test_softmax_vs_oracle(dtype, B, N, u, scale):
     rng = np.random.default_rng(N + 1)
+    u = float(np.float32(u)) if dtype == torch.float32 else u
     x = rng.uniform(-0.5, 0.5, (B, N)) * scale
     temp = rng.uniform(0.5, 2.0, B)
     G = rng.standard_normal((B, N))

@@ -99,6 +99,166 @@ __device__ __forceinline__ void gram_lower(const T *__restrict__ Cb, const T *__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Same contract as gram_lower, for matrices small enough that every thread can keep its (at most
+// MAXT) 4x4 output tiles in registers across the whole K loop: the shared staging area is only
+// read, the result is written once at the end.  Staging uses 16-byte loads/stores when the chunk is
+// a flat copy (no compaction, no centring, N % 4 == 0).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st4(float *p, const Vec4<float> &v) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+}
+__device__ __forceinline__ void st4(double *p, const Vec4<double> &v) {
+    *reinterpret_cast<double2 *>(p) = make_double2(v.v[0], v.v[1]);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(v.v[2], v.v[3]);
+}
+
+template <typename T, int kThreads, int MAXT, bool kColMajorOut>
+__device__ __forceinline__ void gram_lower_reg(const T *__restrict__ Cb, const T *__restrict__ gamma,
+                                               long long gflat0, long long B, int K, int N, const T *mean,
+                                               const int *pos, int ncols, T *As, int AS, int CH, T *out, int ld,
+                                               T diag_add) {
+    const int tid = threadIdx.x;
+    const int NT = (ncols + 3) >> 2;
+    const int ntiles = NT * (NT + 1) / 2;
+    const bool flat = (AS == N) && pos == nullptr && mean == nullptr && (N & 3) == 0;
+    T pre[kPre];
+    const int dk = kThreads / N, di = kThreads % N;
+    const unsigned uB = (unsigned)B;
+    const unsigned gstep = gamma ? (unsigned)(kThreads % B) : 0u;
+    const unsigned gstep4 = gamma ? (unsigned)((4 * kThreads) % B) : 0u;
+
+    int offa[MAXT], offb[MAXT];
+    T acc[MAXT][4][4];
+#pragma unroll
+    for (int m = 0; m < MAXT; ++m) {
+        const int t = tid + m * kThreads;
+        offa[m] = -1; offb[m] = 0;
+        if (t < ntiles) {
+            int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+            while (ti * (ti + 1) / 2 > t) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            offa[m] = 4 * ti; offb[m] = 4 * (t - ti * (ti + 1) / 2);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[m][x][y] = T(0);
+    }
+
+    // fetch() only issues the global loads (matrix element and its gamma factor); the product is
+    // formed in stash(), one chunk later, so the loads stay in flight during the tile FMAs
+    T gpre[kPre];
+    auto fetch = [&](int row0) {
+        const int rows = min(CH, K - row0);
+        const int cnt = rows * N;
+        const long long base = (long long)row0 * N;
+        if (flat) {
+            unsigned gi = gamma ? (unsigned)((gflat0 + base + 4 * tid) % B) : 0u;
+#pragma unroll
+            for (int j = 0; j < kPre / 4; ++j) {
+                const int e = 4 * (tid + j * kThreads);
+                if (e < cnt) {
+                    const Vec4<T> v = ld4(Cb + base + e);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pre[4 * j + q] = v.v[q];
+                    if (gamma) {
+                        unsigned g = gi;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { gpre[4 * j + q] = gamma[g]; if (++g >= uB) g = 0; }
+                    }
+                }
+                gi += gstep4;
+                if (gi >= uB) gi -= uB;
+            }
+        } else {
+            unsigned gi = gamma ? (unsigned)((gflat0 + base + tid) % B) : 0u;
+#pragma unroll
+            for (int j = 0; j < kPre; ++j) {
+                const int e = tid + j * kThreads;
+                if (e < cnt) { pre[j] = Cb[base + e]; if (gamma) gpre[j] = gamma[gi]; }
+                gi += gstep;
+                if (gi >= uB) gi -= uB;
+            }
+        }
+    };
+    auto stash = [&](T *buf, int row0) {
+        const int rows = min(CH, K - row0);
+        const int cnt = rows * N;
+        if (flat) {
+#pragma unroll
+            for (int j = 0; j < kPre / 4; ++j) {
+                const int e = 4 * (tid + j * kThreads);
+                if (e < cnt) {
+                    Vec4<T> v;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v.v[q] = gamma ? pre[4 * j + q] * gpre[4 * j + q] : pre[4 * j + q];
+                    st4(buf + e, v);
+                }
+            }
+        } else {
+            int k = tid / N, i = tid - k * N;
+#pragma unroll
+            for (int j = 0; j < kPre; ++j) {
+                const int e = tid + j * kThreads;
+                if (e < cnt) {
+                    const int col = pos ? pos[i] : i;
+                    T val = gamma ? pre[j] * gpre[j] : pre[j];
+                    if (mean) val -= mean[i];
+                    if (col >= 0) buf[k * AS + col] = val;
+                }
+                i += di; k += dk;
+                if (i >= N) { i -= N; ++k; }
+            }
+        }
+    };
+
+    if (!flat) for (int e = tid; e < 2 * CH * AS; e += kThreads) As[e] = T(0);
+    fetch(0);
+    __syncthreads();
+    int buf = 0;
+    for (int row0 = 0; row0 < K; row0 += CH, buf ^= 1) {
+        T *Ab = As + buf * CH * AS;
+        stash(Ab, row0);
+        __syncthreads();
+        if (row0 + CH < K) fetch(row0 + CH);
+        const int rows = min(CH, K - row0);
+        for (int kk = 0; kk < rows; ++kk) {
+            const T *rowp = Ab + kk * AS;
+#pragma unroll
+            for (int m = 0; m < MAXT; ++m) {
+                if (offa[m] >= 0) {
+                    const Vec4<T> va = ld4(rowp + offa[m]), vb = ld4(rowp + offb[m]);
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) acc[m][x][y] = fma(va.v[x], vb.v[y], acc[m][x][y]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MAXT; ++m) {
+        if (offa[m] >= 0) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int i = offa[m] + x, j = offb[m] + y;
+                    if (i < ncols && j <= i)
+                        out[kColMajorOut ? (j * ld + i) : (i * ld + j)] = acc[m][x][y] + (i == j ? diag_add : T(0));
+                }
+        }
+    }
+    __syncthreads();
+}
+
+// number of 4x4 lower-triangle tiles per thread needed by gram_lower_reg
+__host__ __device__ __forceinline__ int gram_tiles_per_thread(int n, int threads) {
+    const int nt = (n + 3) / 4;
+    return (nt * (nt + 1) / 2 + threads - 1) / threads;
+}
+
+// ------------------------------------------------------------------------------------------------
 // In-place unscaled LDL' of the n x n lower triangle stored column-major at Lb (element (i,k) at
 // Lb[k*ld + i]) with `nrhs` extra rows n .. n+nrhs-1 that undergo the same elimination (so row
 // n+q ends up holding D * L^-1 * rhs_q).  dinv[k] = 1 / pivot_k.  One barrier per column.

@@ -74,6 +74,70 @@ static size_t mk_smem_bytes(int N, int LD, int AS, int CH, int tsize, bool globa
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small reduced systems (the usual case: a handful of free assets): every element of the augmented
+// lower triangle (n columns, n + 2 rows: Q_FF on top of the two right-hand sides) lives in a
+// register of its owning thread for the whole factorisation.  Column k is published to shared
+// memory once it is final; all later columns then apply  v(i,j) -= L(i,k) L(j,k) / d_k  from
+// registers.  One barrier per column, no index arithmetic in the loop.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallElemsMax = 8;   // elements per thread (variants with 2, 4 and 8 slots)
+
+template <typename T, int kThreads>
+__device__ __forceinline__ bool small_system_fits(int n) { return n * (n + 1) / 2 + 2 * n <= kThreads * kSmallElemsMax; }
+
+template <typename T, int kThreads, int kSmallElems, typename Init>
+__device__ __forceinline__ int factor_small_n(T *Lb, int ld, int nF, T *dinv, T dmin, Init init) {
+    const int tid = threadIdx.x;
+    const int E = nF * (nF + 1) / 2 + 2 * nF;
+    const int colh = nF + 2;   // column j holds rows j .. nF+1
+    T v[kSmallElems];
+    int ii[kSmallElems], jj[kSmallElems];
+#pragma unroll
+    for (int m = 0; m < kSmallElems; ++m) {
+        const int e = tid + m * kThreads;
+        ii[m] = 0; jj[m] = -1; v[m] = T(0);
+        if (e < E) {
+            // column-major enumeration: offset(j) = j*colh - j(j-1)/2
+            const float bq = (float)(2 * colh + 1);
+            int j = (int)((bq - sqrtf(bq * bq - 8.f * (float)e)) * 0.5f);
+            j = max(0, min(j, nF - 1));
+            while (j > 0 && j * colh - j * (j - 1) / 2 > e) --j;
+            while (j + 1 < nF && (j + 1) * colh - (j + 1) * j / 2 <= e) ++j;
+            const int i = j + (e - (j * colh - j * (j - 1) / 2));
+            ii[m] = i; jj[m] = j;
+            v[m] = init(i, j);
+        }
+    }
+    int lifted = 0;
+    for (int k = 0; k < nF; ++k) {
+        T *colk = Lb + k * ld;
+#pragma unroll
+        for (int m = 0; m < kSmallElems; ++m)
+            if (jj[m] == k) colk[ii[m]] = v[m];
+        __syncthreads();
+        T d = colk[k];
+        if (!(d > dmin)) { d = dmin; lifted = 1; }
+        const T invd = T(1) / d;
+        if (tid == 0) dinv[k] = invd;
+#pragma unroll
+        for (int m = 0; m < kSmallElems; ++m)
+            if (jj[m] > k) v[m] = fma(-colk[ii[m]], colk[jj[m]] * invd, v[m]);
+    }
+    __syncthreads();
+    return lifted;
+}
+
+// init(i, j) returns element (i, j) of the augmented lower triangle: rows 0..nF-1 the matrix, row nF
+// and nF+1 the two right-hand sides.
+template <typename T, int kThreads, typename Init>
+__device__ __forceinline__ int factor_small(T *Lb, int ld, int nF, T *dinv, T dmin, Init init) {
+    const int E = nF * (nF + 1) / 2 + 2 * nF;
+    if (E <= 2 * kThreads) return factor_small_n<T, kThreads, 2>(Lb, ld, nF, dinv, dmin, init);
+    if (E <= 4 * kThreads) return factor_small_n<T, kThreads, 4>(Lb, ld, nF, dinv, dmin, init);
+    return factor_small_n<T, kThreads, 8>(Lb, ld, nF, dinv, dmin, init);
+}
+
+// ------------------------------------------------------------------------------------------------
 // One reduced-KKT solve + state update (a primal-dual active-set step).  Returns `changed`.
 //   w_L = 0, w_U = u, [[2 Q_FF, 1],[1', 0]] [w_F; nu] = [r_F - 2 u Q_FU 1; 1 - u |U|]
 // ------------------------------------------------------------------------------------------------
@@ -103,21 +167,34 @@ __device__ __forceinline__ int pdas_step(const MkSmem<T> &s, int N, int LD, T u,
     int changed = 0;
     T nu_mult = T(0);
     if (nF > 0) {
-        // (b) gather Q_FF and the two right-hand sides
-        for (int cc = warp; cc < nF; cc += kWarps) {
-            const int jc = s.idx[cc];
-            for (int a = cc + lane; a < nF; a += 32) Lb[cc * LD + a] = Qs[s.idx[a] * LD + jc];
+        if (small_system_fits<T, kThreads>(nF)) {
+            // (b,c) gather straight into registers and factor there
+            auto init = [&](int i, int j) -> T {
+                const int cj = s.idx[j];
+                if (i < nF) return Qs[s.idx[i] * LD + cj];   // idx ascending: (idx[i], idx[j]) is in the lower triangle
+                if (i > nF) return T(1);
+                T acc = T(0);
+                for (int q = 0; q < nU; ++q) acc += sym_at(Qs, LD, cj, s.idxU[q]);
+                return s.r[cj] - T(2) * u * acc;
+            };
+            lifted |= factor_small<T, kThreads>(Lb, LD, nF, s.dinv, dmin, init);
+        } else {
+            // (b) gather Q_FF and the two right-hand sides
+            for (int cc = warp; cc < nF; cc += kWarps) {
+                const int jc = s.idx[cc];
+                for (int a = cc + lane; a < nF; a += 32) Lb[cc * LD + a] = Qs[s.idx[a] * LD + jc];
+            }
+            for (int a = tid; a < nF; a += kThreads) {
+                const int i = s.idx[a];
+                T acc = T(0);
+                for (int m = 0; m < nU; ++m) acc += sym_at(Qs, LD, i, s.idxU[m]);
+                Lb[a * LD + nF] = s.r[i] - T(2) * u * acc;
+                Lb[a * LD + nF + 1] = T(1);
+            }
+            __syncthreads();
+            // (c) factor, eliminating the right-hand sides on the way
+            lifted |= factor_ldl<T, kThreads>(Lb, LD, nF, 2, s.dinv, dmin);
         }
-        for (int a = tid; a < nF; a += kThreads) {
-            const int i = s.idx[a];
-            T acc = T(0);
-            for (int m = 0; m < nU; ++m) acc += sym_at(Qs, LD, i, s.idxU[m]);
-            Lb[a * LD + nF] = s.r[i] - T(2) * u * acc;
-            Lb[a * LD + nF + 1] = T(1);
-        }
-        __syncthreads();
-        // (c) factor, eliminating the right-hand sides on the way
-        lifted |= factor_ldl<T, kThreads>(Lb, LD, nF, 2, s.dinv, dmin);
         // (d,e) multiplier of the budget constraint and back substitution -- warp 0
         if (warp == 0) {
             T s12 = T(0), s22 = T(0);
@@ -278,7 +355,7 @@ __device__ __forceinline__ int trivial_cases(int N, T u, T *w_out, int8_t *st_ou
     return 0;
 }
 
-template <typename T, int kThreads, int NREG, bool kGlobal>
+template <typename T, int kThreads, int NREG, bool kGlobal, int MAXT>
 __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const long long b = blockIdx.x;
@@ -289,8 +366,13 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> 
     MkSmem<T> s = carve<T, kGlobal>(smem_raw, N, LD, p.AS, p.CH, p.ws, b);
     for (int i = tid; i < N; i += kThreads) s.r[i] = p.rets[b * N + i];
     const T aabs = absT(p.alpha[b]);
-    gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, b * (long long)N * N, p.B, N, N, nullptr,
-                                   nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
+    if (MAXT > 0)
+        gram_lower_reg<T, kThreads, (MAXT > 0 ? MAXT : 1), false>(p.C + b * (long long)N * N, p.gamma,
+                                                                   b * (long long)N * N, p.B, N, N, nullptr, nullptr, N,
+                                                                   s.As, p.AS, p.CH, s.Qs, LD, aabs);
+    else
+        gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, b * (long long)N * N, p.B, N, N, nullptr,
+                                       nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
     if (tid < 32) {
         T dmax;
         diag_init_warp<T, NREG>(s, N, LD, p.u, &dmax);
@@ -545,10 +627,14 @@ template <typename T> struct MkBwdParams {
 
 static size_t mk_bwd_smem_bytes(int N, int LDW, int AS, int CH, int tsize, bool global_l) {
     const int NP = round_up(N + 2, 32);
-    size_t elems = (global_l ? 0 : (size_t)round_up(N * LDW, 4)) + (size_t)2 * CH * AS + (size_t)5 * NP + 32;
-    return elems * tsize + ((size_t)2 * NP + 8) * sizeof(int);
+    size_t elems = (global_l ? 0 : (size_t)round_up(N * LDW, 4)) + (size_t)2 * CH * AS + (size_t)7 * NP + 64;
+    return elems * tsize + ((size_t)3 * NP + 8) * sizeof(int);
 }
 
+// Two paths.  "Compact" (the usual case): the columns of A that carry weight (free + capped assets)
+// are copied once from HBM into shared memory, and the restricted Gram, A d and A w all read that
+// copy.  "Streaming" (support too large for the arena, or Q in global memory): chunked Gram over the
+// free columns and a second, L2-resident pass over A for A d and A w.
 template <typename T, int kThreads, int NREG, bool kGlobal>
 __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -557,22 +643,24 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
     constexpr int kWarps = kThreads / 32;
     const int NP = round_up(N + 2, 32);
     T *ptr = reinterpret_cast<T *>(smem_raw);
-    T *Lb;
-    if (kGlobal) Lb = p.ws + b * (long long)N * LDW;
-    else { Lb = ptr; ptr += round_up(N * LDW, 4); }
-    T *As = ptr; ptr += 2 * p.CH * p.AS;
+    T *arena = ptr;
+    const int arena_elems = (kGlobal ? 0 : round_up(N * LDW, 4)) + 2 * p.CH * p.AS;
+    ptr += arena_elems;
     T *wv = ptr; ptr += NP;
     T *dv = ptr; ptr += NP;
     T *gv = ptr; ptr += NP;
     T *dinv = ptr; ptr += NP;
     T *qv = ptr; ptr += NP;
-    T *red = ptr; ptr += 32;
+    T *wc = ptr; ptr += NP;     // w and d on the compacted support
+    T *dc = ptr; ptr += NP;
+    T *red = ptr; ptr += 64;
     int *idx = reinterpret_cast<int *>(ptr);
-    int *pos = idx + NP;
-    int *misc = pos + NP;
+    int *pos = idx + NP;        // column -> index among the free assets, or -1
+    int *posS = pos + NP;       // column -> index among free + capped assets, or -1
+    int *misc = posS + NP;
 
     if (warp == 0) {
-        int nf = 0;
+        int nf = 0, nu = 0;
         for (int base = 0; base < N; base += 32) {
             const int i = base + lane;
             const int v = i < N ? (int)p.state[b * N + i] : 2;
@@ -582,26 +670,139 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
             if (v == 0) idx[a] = i;
             nf += __popc(mf);
         }
-        if (lane == 0) misc[0] = nf;
+        for (int base = 0; base < N; base += 32) {
+            const int i = base + lane;
+            const int v = i < N ? (int)p.state[b * N + i] : 2;
+            const unsigned mu = __ballot_sync(kFullMask, v == 1);
+            if (i < N) posS[i] = v == 0 ? pos[i] : (v == 1 ? nf + nu + __popc(mu & ((1u << lane) - 1u)) : -1);
+            nu += __popc(mu);
+        }
+        if (lane == 0) { misc[0] = nf; misc[1] = nu; }
     }
     for (int i = tid; i < N; i += kThreads) {
         wv[i] = p.w[b * N + i];
         gv[i] = p.grad_w[b * N + i];
         dv[i] = T(0);
     }
+    for (int i = tid; i < NP; i += kThreads) { wc[i] = T(0); dc[i] = T(0); }
     __syncthreads();
-    const int nF = misc[0];
+    const int nF = misc[0], nS = misc[0] + misc[1];
     const T *Cb = p.C + b * (long long)N * N;
     const long long gflat0 = b * (long long)N * N;
     const T alpha = p.alpha[b];
+    const unsigned uB = (unsigned)p.B;
+    const int CS = round_up(nS, 4), LDc = (nF + 2) | 1;
+    const int NT = (nF + 3) >> 2, ntiles = NT * (NT + 1) / 2;
+    // K-split of the small Gram: KS slices of rows per tile, partial sums reduced through shared memory
+    int KS = 1;
+    if (ntiles > 0) { KS = kThreads / ntiles; KS = KS < 1 ? 1 : (KS > 8 ? 8 : KS); }
+    const bool compact = !kGlobal && nF > 0 &&
+                         (N * CS + round_up(nF * LDc, 4) + (KS > 1 ? KS * ntiles * 16 : 0) <= arena_elems);
+    T *pv = gv;   // p = A d overwrites grad_w once d is known
+    T *Ac = arena, *Lb, *part = nullptr;
+    int ldl;
+    if (compact) { Lb = arena + N * CS; ldl = LDc; part = Lb + round_up(nF * LDc, 4); }
+    else { Lb = kGlobal ? p.ws + b * (long long)N * LDW : arena; ldl = LDW; }
+
     if (nF > 0) {
-        gram_lower<T, kThreads, true>(Cb, p.gamma, gflat0, p.B, N, N, nullptr, pos, nF, As, p.AS, p.CH, Lb, LDW,
-                                      absT(alpha));
+        if (compact) {
+            // ---- one pass over A: keep the support columns (gamma-tiled) in shared memory
+            for (int i = tid; i < N; i += kThreads) { const int c = posS[i]; if (c >= 0) wc[c] = wv[i]; }
+            if ((N & 3) == 0) {
+                const int n4 = N * N / 4;
+                int k = (4 * tid) / N, i = 4 * tid - k * N;
+                const int dk = (4 * kThreads) / N, di = (4 * kThreads) % N;
+                unsigned gi = (unsigned)((gflat0 + 4 * tid) % p.B);
+                const unsigned gstep = (unsigned)((4 * kThreads) % p.B);
+                for (int e4 = tid; e4 < n4; e4 += kThreads) {
+                    const Vec4<T> v = ld4(Cb + 4 * e4);
+                    unsigned g = gi;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int c = posS[i + q];
+                        if (c >= 0) Ac[k * CS + c] = v.v[q] * p.gamma[g];
+                        if (++g >= uB) g = 0;
+                    }
+                    i += di; k += dk;
+                    if (i >= N) { i -= N; ++k; }
+                    gi += gstep; if (gi >= uB) gi -= uB;
+                }
+            } else {
+                int k = tid / N, i = tid - k * N;
+                const int dk = kThreads / N, di = kThreads % N;
+                unsigned gi = (unsigned)((gflat0 + tid) % p.B);
+                const unsigned gstep = (unsigned)(kThreads % p.B);
+                for (int e = tid; e < N * N; e += kThreads) {
+                    const int c = posS[i];
+                    if (c >= 0) Ac[k * CS + c] = Cb[e] * p.gamma[gi];
+                    i += di; k += dk;
+                    if (i >= N) { i -= N; ++k; }
+                    gi += gstep; if (gi >= uB) gi -= uB;
+                }
+            }
+            // pad columns of the compact copy are read by the 4-wide tile loads: keep them finite
+            for (int e = tid; e < N * (CS - nS); e += kThreads) {
+                const int k = e / (CS - nS), c = nS + e - k * (CS - nS);
+                Ac[k * CS + c] = T(0);
+            }
+            __syncthreads();
+            // ---- Q_FF = A_F' A_F + |alpha| I, 4x4 tiles, rows split KS ways
+            {
+                const int q = tid % KS, tstep = kThreads / KS;
+                for (int t = tid / KS; t < ntiles; t += tstep) {
+                    int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+                    while (ti * (ti + 1) / 2 > t) --ti;
+                    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+                    const int tj = t - ti * (ti + 1) / 2;
+                    T acc[4][4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) acc[x][y] = T(0);
+                    for (int k = q; k < N; k += KS) {
+                        const Vec4<T> va = ld4(Ac + k * CS + 4 * ti), vb = ld4(Ac + k * CS + 4 * tj);
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) acc[x][y] = fma(va.v[x], vb.v[y], acc[x][y]);
+                    }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            if (KS > 1) part[(q * ntiles + t) * 16 + 4 * x + y] = acc[x][y];
+                            else {
+                                const int i = 4 * ti + x, j = 4 * tj + y;
+                                if (i < nF && j <= i) Lb[j * ldl + i] = acc[x][y] + (i == j ? absT(alpha) : T(0));
+                            }
+                        }
+                }
+                if (KS > 1) {
+                    __syncthreads();
+                    for (int e = tid; e < ntiles * 16; e += kThreads) {
+                        const int tt = e >> 4, xy = e & 15;
+                        int t2 = (int)((sqrtf(8.f * (float)tt + 1.f) - 1.f) * 0.5f);
+                        while (t2 * (t2 + 1) / 2 > tt) --t2;
+                        while ((t2 + 1) * (t2 + 2) / 2 <= tt) ++t2;
+                        const int i = 4 * t2 + (xy >> 2), j = 4 * (tt - t2 * (t2 + 1) / 2) + (xy & 3);
+                        if (i < nF && j <= i) {
+                            T sum = T(0);
+                            for (int qq = 0; qq < KS; ++qq) sum += part[(qq * ntiles + tt) * 16 + xy];
+                            Lb[j * ldl + i] = sum + (i == j ? absT(alpha) : T(0));
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        } else {
+            gram_lower<T, kThreads, true>(Cb, p.gamma, gflat0, p.B, N, N, nullptr, pos, nF, arena + (kGlobal ? 0 : round_up(N * LDW, 4)),
+                                          p.AS, p.CH, Lb, ldl, absT(alpha));
+        }
         T dmax = T(0);
         for (int a = tid; a < nF; a += kThreads) {
-            Lb[a * LDW + nF] = gv[idx[a]];
-            Lb[a * LDW + nF + 1] = T(1);
-            dmax = max(dmax, Lb[a * LDW + a]);
+            Lb[a * ldl + nF] = gv[idx[a]];
+            Lb[a * ldl + nF + 1] = T(1);
+            dmax = max(dmax, Lb[a * ldl + a]);
         }
         dmax = warp_max(dmax);
         if (lane == 0) red[warp] = dmax;
@@ -609,11 +810,14 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
         dmax = T(0);
         for (int i = 0; i < kWarps; ++i) dmax = max(dmax, red[i]);
         const T dmin = T(4) * Num<T>::eps() * dmax + Num<T>::tiny();
-        factor_ldl<T, kThreads>(Lb, LDW, nF, 2, dinv, dmin);
+        if (small_system_fits<T, kThreads>(nF))
+            factor_small<T, kThreads>(Lb, ldl, nF, dinv, dmin, [&](int i, int j) -> T { return Lb[j * ldl + i]; });
+        else
+            factor_ldl<T, kThreads>(Lb, ldl, nF, 2, dinv, dmin);
         if (warp == 0) {
             T s12 = T(0), s22 = T(0);
             for (int k = lane; k < nF; k += 32) {
-                const T y1 = Lb[k * LDW + nF], y2 = Lb[k * LDW + nF + 1], di = dinv[k];
+                const T y1 = Lb[k * ldl + nF], y2 = Lb[k * ldl + nF + 1], di = dinv[k];
                 s12 = fma(y1 * y2, di, s12);
                 s22 = fma(y2 * y2, di, s22);
             }
@@ -623,13 +827,13 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
 #pragma unroll
             for (int m = 0; m < NREG; ++m) {
                 const int k = lane + 32 * m;
-                zt[m] = k < nF ? T(0.5) * (Lb[k * LDW + nF] - eta * Lb[k * LDW + nF + 1]) : T(0);
+                zt[m] = k < nF ? T(0.5) * (Lb[k * ldl + nF] - eta * Lb[k * ldl + nF + 1]) : T(0);
             }
-            backsub_warp<T, NREG>(Lb, LDW, nF, dinv, zt);
+            backsub_warp<T, NREG>(Lb, ldl, nF, dinv, zt);
 #pragma unroll
             for (int m = 0; m < NREG; ++m) {
                 const int k = lane + 32 * m;
-                if (k < nF) dv[idx[k]] = zt[m];
+                if (k < nF) { dv[idx[k]] = zt[m]; dc[k] = zt[m]; }
             }
         }
         __syncthreads();
@@ -639,26 +843,59 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
     for (int i = tid; i < N; i += kThreads) { p.d_rets[b * N + i] = dv[i]; ldot = fma(dv[i], wv[i], ldot); }
     const T dot = block_sum<T, kThreads>(ldot, red);
     if (tid == 0) p.d_alpha[b] = (alpha > T(0) ? T(1) : (alpha < T(0) ? T(-1) : T(0))) * (T(-2) * dot);
-    // p = A d, q = A w: one warp per row, coalesced reads of covmat_sqrt (L2 resident after the Gram)
-    T *pv = gv;  // grad_w no longer needed
-    for (int j = warp; j < N; j += kWarps) {
-        T sp = T(0), sq = T(0);
-        const long long rowflat = gflat0 + (long long)j * N;
-        unsigned gi = (unsigned)((rowflat + lane) % p.B);
-        const unsigned gstep = (unsigned)(32 % p.B);
-        for (int k = lane; k < N; k += 32) {
-            const T a = Cb[(long long)j * N + k] * p.gamma[gi];
-            sp = fma(a, dv[k], sp); sq = fma(a, wv[k], sq);
-            gi += gstep; if (gi >= (unsigned)p.B) gi -= (unsigned)p.B;
+    // p = A d, q = A w
+    if (compact) {
+        for (int k = tid; k < N; k += kThreads) {
+            T sp = T(0), sq = T(0);
+            for (int c = 0; c < CS; c += 4) {
+                const Vec4<T> a = ld4(Ac + k * CS + c), d4 = ld4(dc + c), w4 = ld4(wc + c);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { sp = fma(a.v[q], d4.v[q], sp); sq = fma(a.v[q], w4.v[q], sq); }
+            }
+            pv[k] = sp; qv[k] = sq;
         }
-        sp = warp_sum(sp); sq = warp_sum(sq);
-        if (lane == 0) { pv[j] = sp; qv[j] = sq; }
+    } else if (nF > 0) {
+        // one warp per row, coalesced reads of covmat_sqrt (L2 resident after the Gram)
+        for (int j = warp; j < N; j += kWarps) {
+            T sp = T(0), sq = T(0);
+            const long long rowflat = gflat0 + (long long)j * N;
+            unsigned gi = (unsigned)((rowflat + lane) % p.B);
+            const unsigned gstep = (unsigned)(32 % p.B);
+            for (int k = lane; k < N; k += 32) {
+                const T a = Cb[(long long)j * N + k] * p.gamma[gi];
+                sp = fma(a, dv[k], sp); sq = fma(a, wv[k], sq);
+                gi += gstep; if (gi >= uB) gi -= uB;
+            }
+            sp = warp_sum(sp); sq = warp_sum(sq);
+            if (lane == 0) { pv[j] = sp; qv[j] = sq; }
+        }
+    } else {
+        for (int j = tid; j < N; j += kThreads) { pv[j] = T(0); qv[j] = T(0); }   // d = 0: every gradient vanishes
     }
     __syncthreads();
     if (p.vecs) for (int i = tid; i < N; i += kThreads) { p.vecs[(b * 2) * N + i] = pv[i]; p.vecs[(b * 2 + 1) * N + i] = qv[i]; }
-    // d_covmat_sqrt = gamma_ * (-2) (p w' + q d')
-    {
-        T *dC = p.d_C + gflat0;
+    // d_covmat_sqrt = gamma_ * (-2) (p w' + q d'): one warp per row, 16-byte stores when rows are aligned
+    T *dC = p.d_C + gflat0;
+    if ((N & 3) == 0) {
+        for (int j = warp; j < N; j += kWarps) {
+            const T pj = T(-2) * pv[j], qj = T(-2) * qv[j];
+            const long long rowflat = gflat0 + (long long)j * N;
+            unsigned gi = (unsigned)((rowflat + 4 * lane) % p.B);
+            const unsigned gstep = (unsigned)(128 % p.B);
+            for (int k = 4 * lane; k < N; k += 128) {
+                const Vec4<T> w4 = ld4(wv + k), d4 = ld4(dv + k);
+                Vec4<T> o;
+                unsigned g = gi;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    o.v[q] = p.gamma[g] * fma(pj, w4.v[q], qj * d4.v[q]);
+                    if (++g >= uB) g = 0;
+                }
+                st4(dC + (long long)j * N + k, o);
+                gi += gstep; if (gi >= uB) gi -= uB;
+            }
+        }
+    } else {
         const int total = N * N;
         int j = tid / N, k = tid - j * N;
         const int dj = kThreads / N, dkk = kThreads % N;
@@ -668,7 +905,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
             dC[e] = p.gamma[gi] * T(-2) * fma(pv[j], wv[k], qv[j] * dv[k]);
             k += dkk; j += dj;
             if (k >= N) { k -= N; ++j; }
-            gi += gstep; if (gi >= (unsigned)p.B) gi -= (unsigned)p.B;
+            gi += gstep; if (gi >= uB) gi -= uB;
         }
     }
 }
@@ -789,9 +1026,9 @@ template <typename T> static WsLayout<T> ws_layout(void *ws, long long B, int N)
     return l;
 }
 
-template <typename T, int kThreads, int NREG, bool kGlobal>
+template <typename T, int kThreads, int NREG, bool kGlobal, int MAXT>
 static int launch_fwd_variant(const MkFwdParams<T> &p, const MkPlan &pl, T *ipm_ws, cudaStream_t st) {
-    auto kf = markowitz_fwd_kernel<T, kThreads, NREG, kGlobal>;
+    auto kf = markowitz_fwd_kernel<T, kThreads, NREG, kGlobal, MAXT>;
     auto ki = markowitz_ipm_kernel<T, kThreads, NREG, kGlobal>;
     if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess ||
         cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
@@ -821,13 +1058,20 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
     p.w = (T *)w; p.state = state; p.status = status; p.ws = l.q;
     p.fail_count = l.fail_count; p.fail_list = l.fail_list;
     if (!pl.global_q) {
-        if (pl.threads == 128) return launch_fwd_variant<T, 128, 4, false>(p, pl, l.ipm, st);
-        if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, false>(p, pl, l.ipm, st);
+        if (pl.threads == 128) {
+            // Gram tiles kept in registers: 1, 2, 3 or 5 tiles of 4x4 per thread (n_assets <= 60 / 88 / 108 / 128)
+            const int mt = gram_tiles_per_thread(N, 128);
+            if (mt <= 1) return launch_fwd_variant<T, 128, 4, false, 1>(p, pl, l.ipm, st);
+            if (mt <= 2) return launch_fwd_variant<T, 128, 4, false, 2>(p, pl, l.ipm, st);
+            if (mt <= 3) return launch_fwd_variant<T, 128, 4, false, 3>(p, pl, l.ipm, st);
+            return launch_fwd_variant<T, 128, 4, false, 5>(p, pl, l.ipm, st);
+        }
+        if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, false, 0>(p, pl, l.ipm, st);
     }
-    if (pl.threads == 128) return launch_fwd_variant<T, 128, 4, true>(p, pl, l.ipm, st);
-    if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, true>(p, pl, l.ipm, st);
-    if (pl.nreg == 16) return launch_fwd_variant<T, 512, 16, true>(p, pl, l.ipm, st);
-    return launch_fwd_variant<T, 512, 32, true>(p, pl, l.ipm, st);
+    if (pl.threads == 128) return launch_fwd_variant<T, 128, 4, true, 0>(p, pl, l.ipm, st);
+    if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, true, 0>(p, pl, l.ipm, st);
+    if (pl.nreg == 16) return launch_fwd_variant<T, 512, 16, true, 0>(p, pl, l.ipm, st);
+    return launch_fwd_variant<T, 512, 32, true, 0>(p, pl, l.ipm, st);
 }
 
 template <typename T, int kThreads, int NREG, bool kGlobal>

@@ -80,6 +80,14 @@ def require_cuda(*tensors):
                 f"got a tensor on {t.device}")
 
 
+def aligned(t):
+    """Contiguous and 16-byte aligned (the kernels use 128-bit loads/stores); copies only if needed."""
+    if t is None:
+        return None
+    t = t.contiguous()
+    return t.clone() if t.data_ptr() % 16 else t
+
+
 def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 

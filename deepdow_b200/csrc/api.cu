@@ -44,6 +44,14 @@ template <typename T>
 int covariance_bwd_t(const void *, const void *, const void *, int, int, const void *, const void *, long long, int,
                      int, void *, void *, void *, size_t, cudaStream_t);
 
+static bool misaligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+#define DDW_CHECK_ALIGNED(fn, ...)                                                              \
+    do {                                                                                        \
+        const void *ptrs_[] = {__VA_ARGS__};                                                    \
+        for (const void *q_ : ptrs_)                                                            \
+            if (misaligned(q_)) { set_error("%s: every buffer must be 16-byte aligned", fn); return DDW_ERR_ARG; } \
+    } while (0)
+
 static int check_dims(const char *fn, int64_t B, int64_t N, int64_t nmax, int dtype) {
     if (dtype != DDW_F32 && dtype != DDW_F64) { set_error("%s: dtype must be DDW_F32 or DDW_F64", fn); return DDW_ERR_ARG; }
     if (B < 0 || B >= (1LL << 31)) { set_error("%s: batch size %lld out of range", fn, (long long)B); return DDW_ERR_ARG; }
@@ -74,6 +82,7 @@ int ddw_markowitz_fwd(const void *rets, const void *covmat_sqrt, const void *gam
     if (rc) return rc;
     if (B == 0) return 0;
     if (!rets || !covmat_sqrt || !gamma_sqrt || !alpha || !w || !state || !status) { set_error("ddw_markowitz_fwd: null pointer"); return DDW_ERR_ARG; }
+    DDW_CHECK_ALIGNED("ddw_markowitz_fwd", rets, covmat_sqrt, gamma_sqrt, alpha, w, workspace);
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64
                ? markowitz_fwd_t<double>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st)
@@ -90,6 +99,7 @@ int ddw_markowitz_bwd(const void *grad_w, const void *w, const int8_t *state, co
     if (rc) return rc;
     if (B == 0) return 0;
     if (!grad_w || !w || !state || !covmat_sqrt || !gamma_sqrt || !alpha || !d_rets || !d_covmat_sqrt || !d_alpha) { set_error("ddw_markowitz_bwd: null pointer"); return DDW_ERR_ARG; }
+    DDW_CHECK_ALIGNED("ddw_markowitz_bwd", grad_w, w, covmat_sqrt, gamma_sqrt, alpha, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace);
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64
                ? markowitz_bwd_t<double>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st)
@@ -150,6 +160,7 @@ int ddw_covariance_fwd(const void *x, const void *coef, int strategy, int do_sqr
     if (L < 2 || L >= (1LL << 24)) { set_error("ddw_covariance_fwd: need 2 <= dim < 2^24 observations, got %lld", (long long)L); return DDW_ERR_ARG; }
     if (strategy < DDW_SHRINK_NONE || strategy > DDW_SHRINK_SCALED_IDENTITY) { set_error("ddw_covariance_fwd: bad strategy %d", strategy); return DDW_ERR_ARG; }
     if (!x || !out || (strategy != DDW_SHRINK_NONE && !coef)) { set_error("ddw_covariance_fwd: null pointer"); return DDW_ERR_ARG; }
+    DDW_CHECK_ALIGNED("ddw_covariance_fwd", x, out, eigvec, eigval, workspace);
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64
                ? covariance_fwd_t<double>(x, coef, strategy, do_sqrt, B, (int)L, (int)N, out, eigvec, eigval, sweeps, workspace, workspace_bytes, st)
@@ -166,6 +177,7 @@ int ddw_covariance_bwd(const void *grad_out, const void *x, const void *coef, in
     if (L < 2 || L >= (1LL << 24)) { set_error("ddw_covariance_bwd: need 2 <= dim < 2^24 observations, got %lld", (long long)L); return DDW_ERR_ARG; }
     if (strategy < DDW_SHRINK_NONE || strategy > DDW_SHRINK_SCALED_IDENTITY) { set_error("ddw_covariance_bwd: bad strategy %d", strategy); return DDW_ERR_ARG; }
     if (!grad_out || !x || !d_x || (strategy != DDW_SHRINK_NONE && !coef) || (do_sqrt && (!eigvec || !eigval))) { set_error("ddw_covariance_bwd: null pointer"); return DDW_ERR_ARG; }
+    DDW_CHECK_ALIGNED("ddw_covariance_bwd", grad_out, x, eigvec, eigval, d_x, workspace);
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64
                ? covariance_bwd_t<double>(grad_out, x, coef, strategy, do_sqrt, eigvec, eigval, B, (int)L, (int)N, d_x, d_coef, workspace, workspace_bytes, st)

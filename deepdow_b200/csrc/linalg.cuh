@@ -162,9 +162,15 @@ __device__ __forceinline__ void gram_lower_reg(const T *__restrict__ Cb, const T
 #pragma unroll
                     for (int q = 0; q < 4; ++q) pre[4 * j + q] = v.v[q];
                     if (gamma) {
-                        unsigned g = gi;
+                        if ((uB & 3u) == 0u) {
+                            const Vec4<T> g4 = ld4(gamma + gi);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) { gpre[4 * j + q] = gamma[g]; if (++g >= uB) g = 0; }
+                            for (int q = 0; q < 4; ++q) gpre[4 * j + q] = g4.v[q];
+                        } else {
+                            unsigned g = gi;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) { gpre[4 * j + q] = gamma[g]; if (++g >= uB) g = 0; }
+                        }
                     }
                 }
                 gi += gstep4;
@@ -222,6 +228,7 @@ __device__ __forceinline__ void gram_lower_reg(const T *__restrict__ Cb, const T
         __syncthreads();
         if (row0 + CH < K) fetch(row0 + CH);
         const int rows = min(CH, K - row0);
+#pragma unroll 2
         for (int kk = 0; kk < rows; ++kk) {
             const T *rowp = Ab + kk * AS;
 #pragma unroll

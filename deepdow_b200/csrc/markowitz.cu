@@ -330,8 +330,11 @@ __device__ __forceinline__ void diag_init_warp(const MkSmem<T> &s, int N, int LD
 template <typename T, int kThreads>
 __device__ __forceinline__ void write_result(const MkSmem<T> &s, int N, T u, T *w_out, int8_t *st_out) {
     for (int i = threadIdx.x; i < N; i += kThreads) {
-        const int8_t st = s.st[i];
+        int8_t st = s.st[i];
         const T wi = st == 0 ? clampT(s.wv[i], T(0), u) : (st > 0 ? u : T(0));
+        // tie rule: a free asset whose weight lands exactly on a bound (within rounding) is reported as
+        // active, so the saved state is a function of the returned weights
+        if (st == 0) st = wi <= T(0) ? -1 : (wi >= u ? 1 : 0);
         w_out[i] = wi;
         st_out[i] = st;
     }
@@ -714,18 +717,34 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
                 const int dk = (4 * kThreads) / N, di = (4 * kThreads) % N;
                 unsigned gi = (unsigned)((gflat0 + 4 * tid) % p.B);
                 const unsigned gstep = (unsigned)((4 * kThreads) % p.B);
-                for (int e4 = tid; e4 < n4; e4 += kThreads) {
-                    const Vec4<T> v = ld4(Cb + 4 * e4);
-                    unsigned g = gi;
+                const bool gvec = (uB & 3u) == 0u;   // then every aligned 4-group of flat indices is contiguous mod B
+                for (int e4 = tid; e4 < n4; e4 += 4 * kThreads) {
+                    Vec4<T> v[4], g4[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int c = posS[i + q];
-                        if (c >= 0) Ac[k * CS + c] = v.v[q] * p.gamma[g];
-                        if (++g >= uB) g = 0;
+                    for (int r = 0; r < 4; ++r)
+                        if (e4 + r * kThreads < n4) v[r] = ld4(Cb + 4 * (e4 + r * kThreads));
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (e4 + r * kThreads < n4) {
+                            if (gvec) g4[r] = ld4(p.gamma + gi);
+                            else { unsigned g = gi;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) { g4[r].v[q] = p.gamma[g]; if (++g >= uB) g = 0; } }
+                        }
+                        gi += gstep; if (gi >= uB) gi -= uB;
                     }
-                    i += di; k += dk;
-                    if (i >= N) { i -= N; ++k; }
-                    gi += gstep; if (gi >= uB) gi -= uB;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (e4 + r * kThreads < n4) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int c = posS[i + q];
+                                if (c >= 0) Ac[k * CS + c] = v[r].v[q] * g4[r].v[q];
+                            }
+                        }
+                        i += di; k += dk;
+                        if (i >= N) { i -= N; ++k; }
+                    }
                 }
             } else {
                 int k = tid / N, i = tid - k * N;
@@ -884,13 +903,13 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
             const unsigned gstep = (unsigned)(128 % p.B);
             for (int k = 4 * lane; k < N; k += 128) {
                 const Vec4<T> w4 = ld4(wv + k), d4 = ld4(dv + k);
-                Vec4<T> o;
-                unsigned g = gi;
+                Vec4<T> o, g4;
+                if ((uB & 3u) == 0u) g4 = ld4(p.gamma + gi);
+                else { unsigned g = gi;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    o.v[q] = p.gamma[g] * fma(pj, w4.v[q], qj * d4.v[q]);
-                    if (++g >= uB) g = 0;
-                }
+                    for (int q = 0; q < 4; ++q) { g4.v[q] = p.gamma[g]; if (++g >= uB) g = 0; } }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) o.v[q] = g4.v[q] * fma(pj, w4.v[q], qj * d4.v[q]);
                 st4(dC + (long long)j * N + k, o);
                 gi += gstep; if (gi >= uB) gi -= uB;
             }
@@ -932,6 +951,7 @@ __global__ void __launch_bounds__(128) markowitz_gamma_kernel(const T *__restric
     const int NNi = (int)NN;
     T acc = T(0);
     long long flat = flat0;
+#pragma unroll 8
     for (long long q = q0; q < q1; ++q) {
         const T pj = vecs[(b * 2) * N + j], qj = vecs[(b * 2 + 1) * N + j];
         const T dA = T(-2) * fma(pj, w[b * N + k], qj * d[b * N + k]);
@@ -1109,7 +1129,7 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
     cudaMemsetAsync(d_gamma, 0, sizeof(T) * (size_t)B, st);
     const long long NN = (long long)N * N;
     // enough slices to fill the machine, few enough that atomics stay negligible
-    long long nsplit = max(1LL, min(NN, (148LL * 16 * 128 + B - 1) / B));
+    long long nsplit = max(1LL, min(min(NN, 65535LL), (148LL * 16 * 128 + B - 1) / B));
     const int q_per = (int)((NN + nsplit - 1) / nsplit);
     nsplit = (NN + q_per - 1) / q_per;
     dim3 grid((unsigned)((B + 127) / 128), (unsigned)nsplit);

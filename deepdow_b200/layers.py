@@ -35,8 +35,8 @@ class _MarkowitzFn(torch.autograd.Function):
         lib = _C.lib()
         B, N = rets.shape
         dt = _C.dtype_code(rets)
-        rets_c, cov_c = rets.contiguous(), covmat_sqrt.contiguous()
-        gam_c, alp_c = gamma_sqrt.contiguous(), alpha.contiguous()
+        rets_c, cov_c = _C.aligned(rets), _C.aligned(covmat_sqrt)
+        gam_c, alp_c = _C.aligned(gamma_sqrt), _C.aligned(alpha)
         w = torch.empty_like(rets_c)
         state = torch.empty((B, N), dtype=torch.int8, device=rets.device)
         status = torch.empty((B,), dtype=torch.int32, device=rets.device)
@@ -61,7 +61,7 @@ class _MarkowitzFn(torch.autograd.Function):
         lib = _C.lib()
         B, N = w.shape
         dt = _C.dtype_code(w)
-        g = grad_w.contiguous()
+        g = _C.aligned(grad_w)
         d_rets = torch.empty_like(w)
         d_cov = torch.empty_like(cov_c)
         d_alpha = torch.empty_like(alp_c)
@@ -256,8 +256,8 @@ class _CovarianceFn(torch.autograd.Function):
         lib = _C.lib()
         B, L, N = x.shape
         dt = _C.dtype_code(x)
-        x_c = x.contiguous()
-        coef_c = None if coef is None else coef.to(x.dtype).contiguous()
+        x_c = _C.aligned(x)
+        coef_c = None if coef is None else _C.aligned(coef.to(x.dtype))
         out = torch.empty((B, N, N), dtype=x.dtype, device=x.device)
         need_grad = x.requires_grad or (coef is not None and coef.requires_grad)
         eigvec = eigval = None
@@ -279,7 +279,7 @@ class _CovarianceFn(torch.autograd.Function):
         lib = _C.lib()
         B, L, N = x_c.shape
         dt = _C.dtype_code(x_c)
-        g = grad_out.contiguous()
+        g = _C.aligned(grad_out)
         d_x = torch.empty_like(x_c)
         d_coef = torch.empty_like(coef_c) if (coef_c is not None and ctx.needs_input_grad[1]) else None
         ws = _workspace(lib.ddw_covariance_workspace_bytes(B, L, N, dt, do_sqrt), x_c.device)

@@ -14,6 +14,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer to a contiguous row-major array that the caller
  *     owns (torch allocates them); nothing is allocated or freed in here, no global state
+ *   - matrix / vector buffers of the Markowitz and covariance entry points must be 16-byte aligned
+ *     (they are read and written with 128-bit accesses); torch allocations are
  *   - `dtype` selects the element type of all floating point buffers (DDW_F32 / DDW_F64)
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously
  *   - return value: 0 = enqueued, negative = argument / launch error (ddw_last_error())

@@ -205,7 +205,12 @@ static int polish(const double *Q, const double *r, double u, int n, signed char
             else if (il >= 0 && iu >= 0 && -h[il] > -h[iu] + tol) { st[il] = 0; st[iu] = 0; changed = 1; }
         }
         if (!changed) {
-            for (int i = 0; i < n; ++i) w[i] = w[i] < 0 ? 0.0 : (w[i] > u ? u : w[i]);
+            /* tie rule shared with the CUDA kernel: a free weight that lands exactly on a bound is
+             * reported as active, so the state is a function of the returned weights */
+            for (int i = 0; i < n; ++i) {
+                w[i] = w[i] < 0 ? 0.0 : (w[i] > u ? u : w[i]);
+                if (st[i] == 0) st[i] = w[i] <= 0.0 ? -1 : (w[i] >= u ? 1 : 0);
+            }
             *nu_out = nu;
             return 1 + (nf > 0);
         }

@@ -38,6 +38,10 @@ def make_problems(rng, B, N, kind="sym", alpha=1.0, rscale=0.5, gamma="ones"):
         C = R @ R.transpose(0, 2, 1) / N + 0.1 * np.eye(N)
     elif kind == "asym":
         C = rng.standard_normal((B, N, N)) * 0.5 + np.eye(N)
+    elif kind == "dense":
+        R = rng.standard_normal((B, N, N))
+        C = R @ R.transpose(0, 2, 1) / N + 0.1 * np.eye(N)
+        rets = rng.standard_normal((B, N)) * 0.02
     elif kind == "sqrtcov":
         X = rng.standard_normal((B, 40, N)) * 0.01
         C = oracle.covariance_fwd(X, 0.5, "diagonal", True)
@@ -58,6 +62,8 @@ def make_problems(rng, B, N, kind="sym", alpha=1.0, rscale=0.5, gamma="ones"):
     (16, 100, 1.0, "asym", "rand"),
     (8, 129, 0.05, "sym", "ones"),         # 256-thread variant
     (4, 200, 0.1, "sym", "rand"),
+    (4, 240, 1.0, "sqrtcov", "ones"),      # Q in global workspace, dense free set
+    (3, 500, 0.01, "sym", "ones"),         # config 5 shape (reduced batch)
 ])
 def test_markowitz_forward_vs_oracle(dtype, B, N, u, kind, gamma):
     rng = np.random.default_rng(B * 1000 + N)
@@ -143,6 +149,9 @@ def test_markowitz_hard_problems_use_fallback_and_stay_exact(dtype):
     (64, 50, 0.1, "sym", "rand"),
     (96, 100, 0.2, "sym", "ones"),
     (8, 150, 0.05, "sym", "ones"),
+    (32, 100, 1.0, "dense", "ones"),       # nearly all assets free: generic factorisation + streaming path
+    (4, 240, 0.05, "dense", "ones"),       # factor in global workspace
+    (3, 500, 0.01, "sym", "rand"),         # config 5 shape (reduced batch)
 ])
 def test_markowitz_backward_vs_oracle(dtype, B, N, u, kind, gamma):
     rng = np.random.default_rng(B * 7 + N)

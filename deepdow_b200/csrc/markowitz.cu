@@ -33,6 +33,8 @@ template <typename T> struct MkFwdParams {
     T *ws;            // global Q/L storage when the matrix does not fit shared memory
     int *fail_count;  // [0] = number of problems that need the fallback
     int *fail_list;   // their indices
+    int *work_count;  // dense kernel in list mode: number of entries of work_list (nullptr: one CTA per problem)
+    int *work_list;
 };
 
 template <typename T> __device__ __forceinline__ T sym_at(const T *Qs, int LD, int i, int j) {
@@ -271,7 +273,8 @@ __device__ __forceinline__ int pdas_step(const MkSmem<T> &s, int N, int LD, T u,
 
 // Safeguarded Newton on nu for the separable problem with diag(Q): initial active set.  Warp 0.
 template <typename T, int NREG>
-__device__ __forceinline__ void diag_init_warp(const MkSmem<T> &s, int N, int LD, T u, T *dmax_out) {
+__device__ __forceinline__ void diag_init_warp(const T *qdiag, int qstride, const T *r, int8_t *st_out, int N, T u,
+                                               T *dmax_out) {
     const int lane = threadIdx.x & 31;
     T i2q[NREG], rr[NREG];
     T lo = Num<T>::inf(), hi = -Num<T>::inf(), sa = T(0), sb = T(0), dmax = T(0);
@@ -279,10 +282,10 @@ __device__ __forceinline__ void diag_init_warp(const MkSmem<T> &s, int N, int LD
     for (int m = 0; m < NREG; ++m) {
         const int i = lane + 32 * m;
         if (i < N) {
-            T q = s.Qs[i * LD + i];
+            T q = qdiag[i * qstride];
             dmax = q > dmax ? q : dmax;
             q = q > Num<T>::tiny() ? q : Num<T>::tiny();
-            i2q[m] = T(0.5) / q; rr[m] = s.r[i];
+            i2q[m] = T(0.5) / q; rr[m] = r[i];
             const T l = rr[m] - T(2) * q * u;
             lo = l < lo ? l : lo; hi = rr[m] > hi ? rr[m] : hi;
             sa = fma(rr[m], i2q[m], sa); sb += i2q[m];
@@ -320,7 +323,7 @@ __device__ __forceinline__ void diag_init_warp(const MkSmem<T> &s, int N, int LD
         const int i = lane + 32 * m;
         if (i < N) {
             const T v = (rr[m] - nu) * i2q[m];
-            s.st[i] = v <= T(0) ? -1 : (v >= u ? 1 : 0);
+            st_out[i] = v <= T(0) ? -1 : (v >= u ? 1 : 0);
         }
     }
     *dmax_out = dmax;
@@ -358,45 +361,57 @@ __device__ __forceinline__ int trivial_cases(int N, T u, T *w_out, int8_t *st_ou
     return 0;
 }
 
+}  // namespace ddw
+
+#include "markowitz_sparse.cuh"
+
+namespace ddw {
+
+// Dense forward kernel.  Direct mode (work_list == nullptr): one CTA per portfolio, grid = B.
+// List mode: a fixed grid walks the portfolios that the sparse kernel handed over.
 template <typename T, int kThreads, int NREG, bool kGlobal, int MAXT>
 __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const long long b = blockIdx.x;
     const int N = p.N, LD = p.LD, tid = threadIdx.x;
-    T *w_out = p.w + b * N;
-    int8_t *st_out = p.state + b * N;
-    if (trivial_cases<T, kThreads>(N, p.u, w_out, st_out, p.status + b)) return;
-    MkSmem<T> s = carve<T, kGlobal>(smem_raw, N, LD, p.AS, p.CH, p.ws, b);
-    for (int i = tid; i < N; i += kThreads) s.r[i] = p.rets[b * N + i];
-    const T aabs = absT(p.alpha[b]);
-    if (MAXT > 0)
-        gram_lower_reg<T, kThreads, (MAXT > 0 ? MAXT : 1), false>(p.C + b * (long long)N * N, p.gamma,
-                                                                   b * (long long)N * N, p.B, N, N, nullptr, nullptr, N,
-                                                                   s.As, p.AS, p.CH, s.Qs, LD, aabs);
-    else
-        gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, b * (long long)N * N, p.B, N, N, nullptr,
-                                       nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
-    if (tid < 32) {
-        T dmax;
-        diag_init_warp<T, NREG>(s, N, LD, p.u, &dmax);
-        if (tid == 0) s.red[33] = dmax;
-    }
-    __syncthreads();
-    const T dmin = T(4) * Num<T>::eps() * s.red[33] + Num<T>::tiny();
-    const T tolw = T(8) * Num<T>::eps();
-    int lifted = 0, converged = 0;
-    for (int it = 0; it < kMaxPdas; ++it) {
-        if (!pdas_step<T, kThreads, NREG>(s, N, LD, p.u, dmin, tolw, lifted)) { converged = 1; break; }
-    }
-    write_result<T, kThreads>(s, N, p.u, w_out, st_out);
-    if (tid == 0) {
-        int st = lifted ? DDW_STATUS_REGULARIZED : 0;
-        if (!converged) {
-            st |= DDW_STATUS_FALLBACK | DDW_STATUS_INEXACT;
-            const int slot = atomicAdd(p.fail_count, 1);
-            p.fail_list[slot] = (int)b;
+    const long long nwork = p.work_list ? (long long)*p.work_count : p.B;
+    for (long long wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const long long b = p.work_list ? (long long)p.work_list[wi] : wi;
+        T *w_out = p.w + b * N;
+        int8_t *st_out = p.state + b * N;
+        if (trivial_cases<T, kThreads>(N, p.u, w_out, st_out, p.status + b)) continue;
+        MkSmem<T> s = carve<T, kGlobal>(smem_raw, N, LD, p.AS, p.CH, p.ws, b);
+        __syncthreads();   // list mode: the previous portfolio's shared state is dead from here on
+        for (int i = tid; i < N; i += kThreads) s.r[i] = p.rets[b * N + i];
+        const T aabs = absT(p.alpha[b]);
+        if (MAXT > 0)
+            gram_lower_reg<T, kThreads, (MAXT > 0 ? MAXT : 1), false>(p.C + b * (long long)N * N, p.gamma,
+                                                                       b * (long long)N * N, p.B, N, N, nullptr, nullptr,
+                                                                       N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
+        else
+            gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, b * (long long)N * N, p.B, N, N,
+                                           nullptr, nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
+        if (tid < 32) {
+            T dmax;
+            diag_init_warp<T, NREG>(s.Qs, LD + 1, s.r, s.st, N, p.u, &dmax);
+            if (tid == 0) s.red[33] = dmax;
         }
-        p.status[b] = st;
+        __syncthreads();
+        const T dmin = T(4) * Num<T>::eps() * s.red[33] + Num<T>::tiny();
+        const T tolw = T(8) * Num<T>::eps();
+        int lifted = 0, converged = 0;
+        for (int it = 0; it < kMaxPdas; ++it) {
+            if (!pdas_step<T, kThreads, NREG>(s, N, LD, p.u, dmin, tolw, lifted)) { converged = 1; break; }
+        }
+        write_result<T, kThreads>(s, N, p.u, w_out, st_out);
+        if (tid == 0) {
+            int st = lifted ? DDW_STATUS_REGULARIZED : 0;
+            if (!converged) {
+                st |= DDW_STATUS_FALLBACK | DDW_STATUS_INEXACT;
+                const int slot = atomicAdd(p.fail_count, 1);
+                p.fail_list[slot] = (int)b;
+            }
+            p.status[b] = st;
+        }
     }
 }
 
@@ -1019,7 +1034,7 @@ size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
     const MkPlan pf = plan_fwd(N, tsize), pb = plan_bwd(N, tsize);
     const int NP = round_up(N + 2, 32);
     size_t bytes = 0;
-    bytes += align256(sizeof(int) * (size_t)(B + 1));                      // fail_count + fail_list
+    bytes += align256(sizeof(int) * (size_t)(2 * B + 4));                  // fail/work counters + lists
     bytes += align256((size_t)kIpmGrid * 8 * NP * tsize);                  // interior-point vectors
     bytes += align256((size_t)B * 2 * N * tsize);                          // (A d, A w) for the gamma pass
     size_t q = 0;
@@ -1030,33 +1045,58 @@ size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
 }
 
 template <typename T> struct WsLayout {
-    int *fail_count, *fail_list;
+    int *fail_count, *fail_list, *work_count, *work_list;
     T *ipm, *vecs, *q;
 };
 template <typename T> static WsLayout<T> ws_layout(void *ws, long long B, int N) {
     const int NP = round_up(N + 2, 32);
     WsLayout<T> l;
     unsigned char *p = reinterpret_cast<unsigned char *>(ws);
-    l.fail_count = reinterpret_cast<int *>(p);
-    l.fail_list = l.fail_count + 1;
-    p += align256(sizeof(int) * (size_t)(B + 1));
+    l.fail_count = reinterpret_cast<int *>(p);   // [0] fail_count, [1] work_count (cleared together)
+    l.work_count = l.fail_count + 1;
+    l.fail_list = l.fail_count + 4;
+    l.work_list = l.fail_list + B;
+    p += align256(sizeof(int) * (size_t)(2 * B + 4));
     l.ipm = reinterpret_cast<T *>(p); p += align256((size_t)kIpmGrid * 8 * NP * sizeof(T));
     l.vecs = reinterpret_cast<T *>(p); p += align256((size_t)B * 2 * N * sizeof(T));
     l.q = reinterpret_cast<T *>(p);
     return l;
 }
 
+constexpr int kDenseListGrid = 4 * 148;
+
 template <typename T, int kThreads, int NREG, bool kGlobal, int MAXT>
-static int launch_fwd_variant(const MkFwdParams<T> &p, const MkPlan &pl, T *ipm_ws, cudaStream_t st) {
+static int launch_fwd_variant(MkFwdParams<T> p, const MkPlan &pl, T *ipm_ws, bool sparse_first, cudaStream_t st) {
     auto kf = markowitz_fwd_kernel<T, kThreads, NREG, kGlobal, MAXT>;
     auto ki = markowitz_ipm_kernel<T, kThreads, NREG, kGlobal>;
-    if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess ||
-        cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
-        return check_launch("cudaFuncSetAttribute(markowitz_fwd)");
-    cudaMemsetAsync(p.fail_count, 0, sizeof(int), st);
-    kf<<<(unsigned)p.B, kThreads, pl.smem, st>>>(p);
-    int rc = check_launch("markowitz_fwd_kernel");
-    if (rc) return rc;
+    static bool configured = false;   // per template instance
+    if (!configured) {
+        // opt in to the device maximum once: the same instance serves several n_assets
+        if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess ||
+            cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(markowitz_fwd)");
+        configured = true;
+    }
+    cudaMemsetAsync(p.fail_count, 0, 2 * sizeof(int), st);
+    int rc;
+    if (sparse_first) {
+        // small-support portfolios are finished by the sparse kernel; the rest land on work_list
+        auto ks = markowitz_fwd_sparse_kernel<T, 128, 4>;
+        const size_t sp_smem = sp_smem_bytes(p.N, sizeof(T));
+        static bool sp_configured = false;
+        if (!sp_configured) {
+            if (cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess)
+                return check_launch("cudaFuncSetAttribute(markowitz_fwd_sparse)");
+            sp_configured = true;
+        }
+        ks<<<(unsigned)p.B, 128, sp_smem, st>>>(p);
+        if ((rc = check_launch("markowitz_fwd_sparse_kernel"))) return rc;
+        kf<<<(unsigned)min((long long)kDenseListGrid, p.B), kThreads, pl.smem, st>>>(p);
+    } else {
+        p.work_count = nullptr; p.work_list = nullptr;
+        kf<<<(unsigned)p.B, kThreads, pl.smem, st>>>(p);
+    }
+    if ((rc = check_launch("markowitz_fwd_kernel"))) return rc;
     const unsigned grid = (unsigned)min((long long)kIpmGrid, p.B);
     ki<<<grid, kThreads, pl.smem, st>>>(p, ipm_ws);
     return check_launch("markowitz_ipm_kernel");
@@ -1077,21 +1117,24 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
     p.u = (T)u; p.B = B; p.N = N; p.LD = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
     p.w = (T *)w; p.state = state; p.status = status; p.ws = l.q;
     p.fail_count = l.fail_count; p.fail_list = l.fail_list;
+    p.work_count = l.work_count; p.work_list = l.work_list;
+    // sparse-support kernel first whenever A (4 N^2 bytes) fits shared memory with room for >= 2 CTAs per SM
+    const bool sparse_first = N <= 128 && sp_smem_bytes(N, sizeof(T)) <= (size_t)smem_limit() / 2 && N >= 8;
     if (!pl.global_q) {
         if (pl.threads == 128) {
             // Gram tiles kept in registers: 1, 2, 3 or 5 tiles of 4x4 per thread (n_assets <= 60 / 88 / 108 / 128)
             const int mt = gram_tiles_per_thread(N, 128);
-            if (mt <= 1) return launch_fwd_variant<T, 128, 4, false, 1>(p, pl, l.ipm, st);
-            if (mt <= 2) return launch_fwd_variant<T, 128, 4, false, 2>(p, pl, l.ipm, st);
-            if (mt <= 3) return launch_fwd_variant<T, 128, 4, false, 3>(p, pl, l.ipm, st);
-            return launch_fwd_variant<T, 128, 4, false, 5>(p, pl, l.ipm, st);
+            if (mt <= 1) return launch_fwd_variant<T, 128, 4, false, 1>(p, pl, l.ipm, sparse_first, st);
+            if (mt <= 2) return launch_fwd_variant<T, 128, 4, false, 2>(p, pl, l.ipm, sparse_first, st);
+            if (mt <= 3) return launch_fwd_variant<T, 128, 4, false, 3>(p, pl, l.ipm, sparse_first, st);
+            return launch_fwd_variant<T, 128, 4, false, 5>(p, pl, l.ipm, sparse_first, st);
         }
-        if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, false, 0>(p, pl, l.ipm, st);
+        if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, false, 0>(p, pl, l.ipm, false, st);
     }
-    if (pl.threads == 128) return launch_fwd_variant<T, 128, 4, true, 0>(p, pl, l.ipm, st);
-    if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, true, 0>(p, pl, l.ipm, st);
-    if (pl.nreg == 16) return launch_fwd_variant<T, 512, 16, true, 0>(p, pl, l.ipm, st);
-    return launch_fwd_variant<T, 512, 32, true, 0>(p, pl, l.ipm, st);
+    if (pl.threads == 128) return launch_fwd_variant<T, 128, 4, true, 0>(p, pl, l.ipm, false, st);
+    if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, true, 0>(p, pl, l.ipm, false, st);
+    if (pl.nreg == 16) return launch_fwd_variant<T, 512, 16, true, 0>(p, pl, l.ipm, false, st);
+    return launch_fwd_variant<T, 512, 32, true, 0>(p, pl, l.ipm, false, st);
 }
 
 template <typename T, int kThreads, int NREG, bool kGlobal>

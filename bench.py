@@ -146,6 +146,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--status-mode", default="lazy", choices=["lazy", "sync", "off"],
+                    help="NumericalMarkowitz.check_status: lazy (default of the layer), sync (read the failure "
+                         "counter inside every forward: a host sync) or off (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -180,6 +183,7 @@ def main():
     alp = torch.ones(B, device=dev)
     G = torch.randn(B, N, generator=gen, device=dev)
     layer = NumericalMarkowitz(N, max_weight=u)
+    layer.check_status = {"lazy": "lazy", "sync": True, "off": False}[args.status_mode]
     inputs = [t.requires_grad_() for t in (rets, C, gam, alp)]
 
     def step_device(ev=None):
@@ -211,10 +215,12 @@ def main():
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    cpu0 = time.perf_counter()
     t_start.record()
     for i in range(args.steps):
         step_device(evs[i])
     t_end.record()
+    cpu_enqueue_ms = 1e3 * (time.perf_counter() - cpu0) / args.steps   # host time to enqueue one step
     barrier()
     clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
@@ -284,6 +290,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world} (independent problems, no collective)",
                        "l2": "inputs (164 MB covmat_sqrt) + gradients (164 MB) per step exceed the 126 MB L2",
+                       "status_check": args.status_mode,
                        "active_set": {"mean_free": nfree, "mean_at_cap": ncap, "fallback_problems": nfallback}},
             "e2e": {"value": world * B * steps_total / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -292,7 +299,7 @@ def main():
             "kernels_per_step": ["markowitz_fwd_kernel", "markowitz_ipm_kernel (walks the empty fallback list)",
                                  "markowitz_bwd_kernel", "markowitz_gamma_kernel"],
             "fwd_only": {"value": world * B * steps_total / (fwd_only_ms * 1e-3), "unit": UNIT},
-            "phase_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
+            "phase_ms": {"fwd": fwd_ms, "bwd": bwd_ms, "host_enqueue": cpu_enqueue_ms},
             "roofline": {"bound": "hbm", "kernel": "markowitz_fwd_kernel" if dom_fwd else "markowitz_bwd_kernel",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "peak_source": peak_src,

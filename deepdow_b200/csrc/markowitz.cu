@@ -35,6 +35,7 @@ template <typename T> struct MkFwdParams {
     int *fail_list;   // their indices
     int *work_count;  // dense kernel in list mode: number of entries of work_list (nullptr: one CTA per problem)
     int *work_list;
+    int *bad_count;   // number of portfolios left INFEASIBLE or INEXACT (what the host layer raises on)
 };
 
 template <typename T> __device__ __forceinline__ T sym_at(const T *Qs, int LD, int i, int j) {
@@ -345,12 +346,12 @@ __device__ __forceinline__ void write_result(const MkSmem<T> &s, int N, T u, T *
 
 // returns 1 when the problem was decided by the box alone (infeasible or a single feasible point)
 template <typename T, int kThreads>
-__device__ __forceinline__ int trivial_cases(int N, T u, T *w_out, int8_t *st_out, int32_t *status) {
+__device__ __forceinline__ int trivial_cases(int N, T u, T *w_out, int8_t *st_out, int32_t *status, int *bad_count) {
     const T cap = u * (T)N;
     const T tol = T(8) * Num<T>::eps() * (T)N;
     if (cap < T(1) - tol || !(u > T(0))) {
         for (int i = threadIdx.x; i < N; i += kThreads) { w_out[i] = Num<T>::inf() - Num<T>::inf(); st_out[i] = 0; }
-        if (threadIdx.x == 0) *status = DDW_STATUS_INFEASIBLE;
+        if (threadIdx.x == 0) { *status = DDW_STATUS_INFEASIBLE; atomicAdd(bad_count, 1); }
         return 1;
     }
     if (cap <= T(1) + tol) {
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> 
         const long long b = p.work_list ? (long long)p.work_list[wi] : wi;
         T *w_out = p.w + b * N;
         int8_t *st_out = p.state + b * N;
-        if (trivial_cases<T, kThreads>(N, p.u, w_out, st_out, p.status + b)) continue;
+        if (trivial_cases<T, kThreads>(N, p.u, w_out, st_out, p.status + b, p.bad_count)) continue;
         MkSmem<T> s = carve<T, kGlobal>(smem_raw, N, LD, p.AS, p.CH, p.ws, b);
         __syncthreads();   // list mode: the previous portfolio's shared state is dead from here on
         for (int i = tid; i < N; i += kThreads) s.r[i] = p.rets[b * N + i];
@@ -622,7 +623,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_ipm_kernel(MkFwdParams<T> 
                 p.w[b * N + i] = wi;
                 p.state[b * N + i] = wi <= thr ? -1 : (u - wi <= thr ? 1 : 0);
             }
-            if (tid == 0) p.status[b] = DDW_STATUS_FALLBACK | DDW_STATUS_INEXACT;
+            if (tid == 0) { p.status[b] = DDW_STATUS_FALLBACK | DDW_STATUS_INEXACT; atomicAdd(p.bad_count, 1); }
         }
         __syncthreads();
     }
@@ -978,6 +979,41 @@ __global__ void __launch_bounds__(128) markowitz_gamma_kernel(const T *__restric
     atomicAdd(d_gamma + m, acc);
 }
 
+// Same reduction, four neighbouring bins per thread with 128-bit loads (needs B % 4 == 0 and N % 4 == 0,
+// then the four elements flat .. flat+3 sit in one row of one problem).
+template <typename T>
+__global__ void __launch_bounds__(128) markowitz_gamma_kernel4(const T *__restrict__ C, const T *__restrict__ w,
+                                                               const T *__restrict__ d, const T *__restrict__ vecs,
+                                                               long long B, int N, int q_per_split, T *d_gamma) {
+    const long long m = 4 * ((long long)blockIdx.x * 128 + threadIdx.x);
+    if (m >= B) return;
+    const long long NN = (long long)N * N;
+    const long long q0 = (long long)blockIdx.y * q_per_split;
+    const long long q1 = min(q0 + q_per_split, NN);
+    if (q0 >= q1) return;
+    const long long flat0 = q0 * B + m;
+    long long b = flat0 / NN;
+    int rem = (int)(flat0 - b * NN);
+    int j = rem / N, k = rem - j * N;
+    const long long Bq = B / NN;
+    const int Br = (int)(B - Bq * NN), Brj = Br / N, Brk = Br - Brj * N;
+    const int NNi = (int)NN;
+    T acc[4] = {T(0), T(0), T(0), T(0)};
+    long long flat = flat0;
+#pragma unroll 4
+    for (long long q = q0; q < q1; ++q) {
+        const T pj = T(-2) * vecs[(b * 2) * N + j], qj = T(-2) * vecs[(b * 2 + 1) * N + j];
+        const Vec4<T> c4 = ld4(C + flat), w4 = ld4(w + b * N + k), d4 = ld4(d + b * N + k);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc[x] = fma(c4.v[x], fma(pj, w4.v[x], qj * d4.v[x]), acc[x]);
+        flat += B; b += Bq; rem += Br; j += Brj; k += Brk;
+        if (k >= N) { k -= N; ++j; }
+        if (rem >= NNi) { rem -= NNi; j -= N; ++b; }
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) atomicAdd(d_gamma + m + x, acc[x]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
@@ -1045,15 +1081,16 @@ size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
 }
 
 template <typename T> struct WsLayout {
-    int *fail_count, *fail_list, *work_count, *work_list;
+    int *fail_count, *fail_list, *work_count, *work_list, *bad_count;
     T *ipm, *vecs, *q;
 };
 template <typename T> static WsLayout<T> ws_layout(void *ws, long long B, int N) {
     const int NP = round_up(N + 2, 32);
     WsLayout<T> l;
     unsigned char *p = reinterpret_cast<unsigned char *>(ws);
-    l.fail_count = reinterpret_cast<int *>(p);   // [0] fail_count, [1] work_count (cleared together)
+    l.fail_count = reinterpret_cast<int *>(p);   // [0] fail_count, [1] work_count, [2] bad_count (cleared together)
     l.work_count = l.fail_count + 1;
+    l.bad_count = l.fail_count + 2;
     l.fail_list = l.fail_count + 4;
     l.work_list = l.fail_list + B;
     p += align256(sizeof(int) * (size_t)(2 * B + 4));
@@ -1077,7 +1114,7 @@ static int launch_fwd_variant(MkFwdParams<T> p, const MkPlan &pl, T *ipm_ws, boo
             return check_launch("cudaFuncSetAttribute(markowitz_fwd)");
         configured = true;
     }
-    cudaMemsetAsync(p.fail_count, 0, 2 * sizeof(int), st);
+    cudaMemsetAsync(p.fail_count, 0, 4 * sizeof(int), st);
     int rc;
     if (sparse_first) {
         // small-support portfolios are finished by the sparse kernel; the rest land on work_list
@@ -1117,7 +1154,7 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
     p.u = (T)u; p.B = B; p.N = N; p.LD = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
     p.w = (T *)w; p.state = state; p.status = status; p.ws = l.q;
     p.fail_count = l.fail_count; p.fail_list = l.fail_list;
-    p.work_count = l.work_count; p.work_list = l.work_list;
+    p.work_count = l.work_count; p.work_list = l.work_list; p.bad_count = l.bad_count;
     // sparse-support kernel first whenever A (4 N^2 bytes) fits shared memory with room for >= 2 CTAs per SM
     const bool sparse_first = N <= 128 && sp_smem_bytes(N, sizeof(T)) <= (size_t)smem_limit() / 2 && N >= 8;
     if (!pl.global_q) {
@@ -1171,13 +1208,19 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
     if (rc || !d_gamma) return rc;
     cudaMemsetAsync(d_gamma, 0, sizeof(T) * (size_t)B, st);
     const long long NN = (long long)N * N;
+    const bool vec4 = (B % 4 == 0) && (N % 4 == 0);
+    const long long cols = vec4 ? B / 4 : B;   // threads along the bin dimension
     // enough slices to fill the machine, few enough that atomics stay negligible
-    long long nsplit = max(1LL, min(min(NN, 65535LL), (148LL * 16 * 128 + B - 1) / B));
+    long long nsplit = max(1LL, min(min(NN, 65535LL), (148LL * 16 * 128 + cols - 1) / cols));
     const int q_per = (int)((NN + nsplit - 1) / nsplit);
     nsplit = (NN + q_per - 1) / q_per;
-    dim3 grid((unsigned)((B + 127) / 128), (unsigned)nsplit);
-    markowitz_gamma_kernel<T><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, l.vecs, B, N, q_per,
-                                                    (T *)d_gamma);
+    dim3 grid((unsigned)((cols + 127) / 128), (unsigned)nsplit);
+    if (vec4)
+        markowitz_gamma_kernel4<T><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, l.vecs, B, N,
+                                                         q_per, (T *)d_gamma);
+    else
+        markowitz_gamma_kernel<T><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, l.vecs, B, N,
+                                                        q_per, (T *)d_gamma);
     return check_launch("markowitz_gamma_kernel");
 }
 

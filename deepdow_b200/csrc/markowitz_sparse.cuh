@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
     const T u = p.u;
     T *w_out = p.w + b * N;
     int8_t *st_out = p.state + b * N;
-    if (trivial_cases<T, kThreads>(N, u, w_out, st_out, p.status + b)) return;
+    if (trivial_cases<T, kThreads>(N, u, w_out, st_out, p.status + b, p.bad_count)) return;
     SpSmem<T> s = sp_carve<T>(smem_raw, N);
     T *As = s.As, *Qc = s.Qc, *Lb = s.Qc + 1;
     const T *Cb = p.C + b * (long long)N * N;
@@ -82,7 +82,18 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
     else for (int e = tid; e < N * N; e += kThreads) As[e] = Cb[e];
     // ---- gamma tiling (allocate.py:268-270), in place; every thread touches the elements it will not
     // need before the next barrier
-    {
+    if ((N & 3) == 0 && (uB & 3u) == 0u) {
+        unsigned gi = (unsigned)((gflat0 + 4 * tid) % p.B);
+        const unsigned gstep = (unsigned)((4 * kThreads) % p.B);
+        for (int e = 4 * tid; e < N * N; e += 4 * kThreads) {
+            Vec4<T> a = ld4(As + e);
+            const Vec4<T> g4 = ld4(p.gamma + gi);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a.v[q] *= g4.v[q];
+            st4(As + e, a);
+            gi += gstep; if (gi >= uB) gi -= uB;
+        }
+    } else {
         unsigned gi = (unsigned)((gflat0 + tid) % p.B);
         const unsigned gstep = (unsigned)(kThreads % p.B);
         for (int e = tid; e < N * N; e += kThreads) {
@@ -233,11 +244,14 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
         for (int i = tid; i < N; i += kThreads) {
             T a0 = T(0), a1 = T(0);
             int k = 0;
-            for (; k + 1 < N; k += 2) {
-                a0 = fma(As[k * N + i], s.tv[k], a0);
-                a1 = fma(As[(k + 1) * N + i], s.tv[k + 1], a1);
+            for (; k + 3 < N; k += 4) {
+                const Vec4<T> t4 = ld4(s.tv + k);
+                a0 = fma(As[k * N + i], t4.v[0], a0);
+                a1 = fma(As[(k + 1) * N + i], t4.v[1], a1);
+                a0 = fma(As[(k + 2) * N + i], t4.v[2], a0);
+                a1 = fma(As[(k + 3) * N + i], t4.v[3], a1);
             }
-            if (k < N) a0 = fma(As[k * N + i], s.tv[k], a0);
+            for (; k < N; ++k) a0 = fma(As[k * N + i], s.tv[k], a0);
             const T h = T(2) * (a0 + a1 + aabs * s.wv[i]) - s.r[i];
             if (nF > 0) {
                 const T gi = h + nu_mult;

@@ -28,9 +28,50 @@ def _workspace(nbytes, device):
 # ------------------------------------------------------------------------------------------------
 # NumericalMarkowitz
 # ------------------------------------------------------------------------------------------------
+class _StatusWatch:
+    """Deferred read of the solver's failure counter (workspace header, include/ddw.h).
+
+    Reading it inside ``forward`` is a host<->device sync that stalls the launch pipeline (measured:
+    0.26 ms of a 0.93 ms fwd+bwd step at B=4096, N=100).  In "lazy" mode the counter is copied
+    asynchronously to pinned host memory and inspected by the next call that finds the copy finished,
+    so a failure raises ``SolverError`` at most one call late instead of blocking every call.
+    """
+    SLOTS = 8
+
+    def __init__(self):
+        self.buf = None
+        self.pending = []   # (slot, event, description)
+        self.next = 0
+
+    def push(self, counter, what):
+        if self.buf is None:
+            self.buf = torch.zeros(self.SLOTS, dtype=torch.int32).pin_memory()
+        if len(self.pending) >= self.SLOTS:
+            self.poll(block=True)
+        slot = self.next
+        self.next = (self.next + 1) % self.SLOTS
+        self.buf[slot:slot + 1].copy_(counter, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((slot, ev, what))
+
+    def poll(self, block=False):
+        while self.pending:
+            slot, ev, what = self.pending[0]
+            if not ev.query():
+                if not block:
+                    return
+                ev.synchronize()
+            self.pending.pop(0)
+            bad = int(self.buf[slot])
+            if bad:
+                self.pending.clear()
+                raise SolverError(f"{bad} portfolio problems could not be solved ({what})")
+
+
 class _MarkowitzFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, check_status):
+    def forward(ctx, rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, check_status, watch):
         _C.require_cuda(rets, covmat_sqrt, gamma_sqrt, alpha)
         lib = _C.lib()
         B, N = rets.shape
@@ -45,11 +86,14 @@ class _MarkowitzFn(torch.autograd.Function):
                                    float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status),
                                    _C.ptr(ws), ws.numel(), _C.stream())
         _C.check(rc, "ddw_markowitz_fwd")
-        if check_status:
-            bad = int((status & (_C.STATUS_INFEASIBLE | _C.STATUS_INEXACT)).ne(0).sum())
+        what = f"batch of {B}, n_assets={N}, max_weight={max_weight}"
+        counter = ws[8:12].view(torch.int32)          # counter [2] of the workspace header (include/ddw.h)
+        if check_status is True:
+            bad = int(counter)
             if bad:
-                raise SolverError(f"{bad} of {B} portfolio problems could not be solved "
-                                  f"(n_assets={N}, max_weight={max_weight})")
+                raise SolverError(f"{bad} portfolio problems could not be solved ({what})")
+        elif check_status == "lazy":
+            watch.push(counter, what)
         ctx.save_for_backward(w, state, cov_c, gam_c, alp_c)
         ctx.max_weight = float(max_weight)
         ctx.mark_non_differentiable(status)
@@ -72,7 +116,7 @@ class _MarkowitzFn(torch.autograd.Function):
                                    ctx.max_weight, B, N, dt, _C.ptr(d_rets), _C.ptr(d_cov), _C.ptr(d_gamma),
                                    _C.ptr(d_alpha), _C.ptr(ws), ws.numel(), _C.stream())
         _C.check(rc, "ddw_markowitz_bwd")
-        return d_rets, d_cov, d_gamma, d_alpha, None, None
+        return d_rets, d_cov, d_gamma, d_alpha, None, None, None
 
 
 class NumericalMarkowitz(nn.Module):
@@ -102,8 +146,11 @@ class NumericalMarkowitz(nn.Module):
         super().__init__()
         self.n_assets = n_assets
         self.max_weight = max_weight
-        self.check_status = True
+        # "lazy": a failed solve raises SolverError from the next call that finds the status copy finished
+        # (no host sync per forward); True: check inside every forward (blocks); False: never check
+        self.check_status = "lazy"
         self.last_status = None
+        self._watch = _StatusWatch()
 
     def forward(self, rets, covmat_sqrt, gamma_sqrt, alpha):
         """Same arguments as the reference (allocate.py:240-273).
@@ -119,11 +166,20 @@ class NumericalMarkowitz(nn.Module):
         # the reference's repeat/view needs exactly n_samples gamma values (allocate.py:268-270)
         if gamma_sqrt.numel() != n_samples or alpha.numel() != n_samples:
             raise ValueError("gamma_sqrt and alpha need shape (n_samples,)")
+        if self.check_status:
+            self._watch.poll()                     # surfaces a failure of an earlier call, never blocks
+            if n_assets * float(self.max_weight) < 1.0 - 1e-6:
+                # the box leaves no fully invested portfolio: the reference's solver raises here too
+                raise SolverError(f"infeasible: n_assets * max_weight = {n_assets * float(self.max_weight):g} < 1")
         dtype = rets.dtype
         w, status = _MarkowitzFn.apply(rets, covmat_sqrt.to(dtype), gamma_sqrt.reshape(-1).to(dtype),
-                                       alpha.reshape(-1).to(dtype), self.max_weight, self.check_status)
+                                       alpha.reshape(-1).to(dtype), self.max_weight, self.check_status, self._watch)
         self.last_status = status
         return w
+
+    def synchronize_status(self):
+        """Block until every outstanding solve has reported; raise SolverError if any failed."""
+        self._watch.poll(block=True)
 
     def extra_repr(self):
         return f"n_assets={self.n_assets}, max_weight={self.max_weight}"
@@ -131,7 +187,12 @@ class NumericalMarkowitz(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["last_status"] = None
+        state["_watch"] = None            # pinned buffers and CUDA events are not picklable
         return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._watch = _StatusWatch()
 
 
 # ------------------------------------------------------------------------------------------------

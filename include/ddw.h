@@ -65,7 +65,10 @@ const char *ddw_last_error(void);
  *   s.t.      sum(w) = 1, 0 <= w <= max_weight
  * rets (B,N)  covmat_sqrt (B,N,N)  gamma_sqrt (B)  alpha (B)
  * w (B,N) out; state (B,N) int8 out: -1 at 0, +1 at max_weight, 0 free (saved for backward);
- * status (B) int32 out.  workspace: ddw_markowitz_workspace_bytes() bytes, may be NULL if that is 0.
+ * status (B) int32 out.  workspace: ddw_markowitz_workspace_bytes() bytes.  After the forward, the first
+ * 16 bytes of the workspace hold int32 counters: [0] portfolios sent to the interior-point fallback,
+ * [1] portfolios sent from the sparse-support kernel to the dense kernel, [2] portfolios left with
+ * DDW_STATUS_INFEASIBLE or DDW_STATUS_INEXACT (the host layer raises SolverError when it is non-zero).
  * ------------------------------------------------------------------------------------------- */
 size_t ddw_markowitz_workspace_bytes(int64_t B, int64_t N, int dtype);
 

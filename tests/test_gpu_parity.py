@@ -167,6 +167,28 @@ def test_markowitz_backward_vs_oracle(dtype, B, N, u, kind, gamma):
         assert rel_err(got, want) < G_RTOL[dtype], (name, rel_err(got, want))
 
 
+def test_markowitz_status_modes():
+    rng = np.random.default_rng(4)
+    rets, C, g, a = make_problems(rng, 16, 12)
+    args = [t(x, torch.float32) for x in (rets, C, g, a)]
+    ref = None
+    for mode in ("lazy", True, False):
+        layer = NumericalMarkowitz(12, 0.5)
+        layer.check_status = mode
+        for _ in range(12):                     # more calls than status slots: the ring must recycle
+            w = layer(*args)
+        layer.synchronize_status()
+        assert int(layer.last_status.ne(0).sum()) == 0
+        ref = w if ref is None else ref
+        assert torch.equal(w, ref)
+    # an infeasible box is rejected on the host, immediately, in every checking mode
+    for mode in ("lazy", True):
+        layer = NumericalMarkowitz(12, 0.05)
+        layer.check_status = mode
+        with pytest.raises(SolverError):
+            layer(*args)
+
+
 def test_markowitz_no_grad_and_double_backward_safety():
     rng = np.random.default_rng(3)
     rets, C, g, a = make_problems(rng, 8, 10)

@@ -48,14 +48,20 @@ def make_inputs_numpy(B, N, seed):
     return rets, C.astype(np.float32), np.ones(B, np.float32), np.ones(B, np.float32), G
 
 
-def time_cpu_oracle(sample, repeats, seed=4000, nthreads=0):
-    """Oracle port (float64, OpenMP) forward+backward on `sample` problems; returns (solves/s, threads, seconds)."""
+def time_cpu_oracle(sample, repeats, seed=4000, nthreads=0, budget_s=None):
+    """Oracle port (float64, OpenMP) forward+backward on `sample` problems; returns (solves/s, threads, seconds).
+    With `budget_s` the number of repeats is chosen so that about that many seconds of CPU work are timed."""
     import numpy as np
     import oracle
     rets, C, g, a, G = make_inputs_numpy(sample, N_ASSETS, seed)
     rets, C, g, a, G = [x.astype(np.float64) for x in (rets, C, g, a, G)]
     oracle.markowitz_fwd(rets[:8], C[:8], g[:8], a[:8], MAX_WEIGHT, nthreads)  # load + warm
     times = []
+    if budget_s is not None:
+        t0 = time.perf_counter()
+        w, st, kkt, status = oracle.markowitz_fwd(rets, C, g, a, MAX_WEIGHT, nthreads)
+        oracle.markowitz_bwd(G, w, st, C, g, a, MAX_WEIGHT, nthreads)
+        repeats = max(3, min(200, int(budget_s / max(time.perf_counter() - t0, 1e-3))))
     for _ in range(repeats):
         t0 = time.perf_counter()
         w, st, kkt, status = oracle.markowitz_fwd(rets, C, g, a, MAX_WEIGHT, nthreads)
@@ -68,7 +74,7 @@ def run_reference(args, rank, world):
     """Reference arm: CPU oracle port on the host cores (rank 0 only)."""
     if rank != 0:
         return
-    sample = 512
+    sample = B_PER_GPU
     oracle_warm = time_cpu_oracle(64, 1)
     del oracle_warm
     import numpy as np
@@ -89,7 +95,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(per_step),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample} of the 4096 problems per step"},
+        "config": {"workload": WORKLOAD, "sample": f"all {sample} problems per step, fwd+bwd"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} problems fwd+bwd per step, float64 oracle port (cvxpylayers/SCS not installable)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -295,12 +301,13 @@ def main():
             "e2e": {"value": world * B * steps_total / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / steps_total},
-            "gpu_launches": 4 * steps_total,
-            "kernels_per_step": ["markowitz_fwd_kernel", "markowitz_ipm_kernel (walks the empty fallback list)",
-                                 "markowitz_bwd_kernel", "markowitz_gamma_kernel"],
+            "gpu_launches": 5 * steps_total,
+            "kernels_per_step": ["markowitz_fwd_sparse_kernel", "markowitz_fwd_kernel (dense work list, empty here)",
+                                 "markowitz_ipm_kernel (fallback list, empty here)", "markowitz_bwd_kernel",
+                                 "markowitz_gamma_kernel4"],
             "fwd_only": {"value": world * B * steps_total / (fwd_only_ms * 1e-3), "unit": UNIT},
             "phase_ms": {"fwd": fwd_ms, "bwd": bwd_ms, "host_enqueue": cpu_enqueue_ms},
-            "roofline": {"bound": "hbm", "kernel": "markowitz_fwd_kernel" if dom_fwd else "markowitz_bwd_kernel",
+            "roofline": {"bound": "hbm", "kernel": "markowitz_fwd_sparse_kernel" if dom_fwd else "markowitz_bwd_kernel",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": fwd_bytes if dom_fwd else bwd_bytes,
@@ -310,9 +317,10 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, secs = time_cpu_oracle(1024, 3)
+            v, cores, secs = time_cpu_oracle(B, 0, budget_s=12.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"1024 of the 4096 problems, fwd+bwd, 3 repeats, {secs:.1f} s of float64 oracle"}
+                                    "sample": f"the same {B} problems, fwd+bwd, repeated for {secs:.1f} s, float64 oracle port "
+                                              "(OpenMP over problems; cvxpylayers/SCS is not installable)"}
             line["host_cpu_count"] = os.cpu_count()
         print(json.dumps(line), flush=True)
     if world > 1:

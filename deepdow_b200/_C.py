@@ -35,6 +35,8 @@ SIGNATURES = {
     "ddw_covariance_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
     "ddw_covariance_fwd": (_i32, [_vp, _vp, _i32, _i32, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddw_covariance_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "ddw_psd_sqrt_fwd": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ddw_psd_sqrt_bwd": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
 }
 
 

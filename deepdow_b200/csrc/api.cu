@@ -184,4 +184,33 @@ int ddw_covariance_bwd(const void *grad_out, const void *x, const void *coef, in
                : covariance_bwd_t<float>(grad_out, x, coef, strategy, do_sqrt, eigvec, eigval, B, (int)L, (int)N, d_x, d_coef, workspace, workspace_bytes, st);
 }
 
+/* psd sqrt of given symmetric matrices: the covariance kernels in direct mode (L = 0, no shrinkage) */
+int ddw_psd_sqrt_fwd(const void *m, int64_t B, int64_t N, int dtype, void *out, void *eigvec, void *eigval,
+                     void *workspace, size_t workspace_bytes, void *stream) {
+    g_err[0] = 0;
+    int rc = check_dims("ddw_psd_sqrt_fwd", B, N, 1024, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!m || !out) { set_error("ddw_psd_sqrt_fwd: null pointer"); return DDW_ERR_ARG; }
+    DDW_CHECK_ALIGNED("ddw_psd_sqrt_fwd", m, out, eigvec, eigval, workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64
+               ? covariance_fwd_t<double>(m, nullptr, DDW_SHRINK_NONE, 1, B, 0, (int)N, out, eigvec, eigval, nullptr, workspace, workspace_bytes, st)
+               : covariance_fwd_t<float>(m, nullptr, DDW_SHRINK_NONE, 1, B, 0, (int)N, out, eigvec, eigval, nullptr, workspace, workspace_bytes, st);
+}
+
+int ddw_psd_sqrt_bwd(const void *grad_out, const void *eigvec, const void *eigval, int64_t B, int64_t N, int dtype,
+                     void *d_m, void *workspace, size_t workspace_bytes, void *stream) {
+    g_err[0] = 0;
+    int rc = check_dims("ddw_psd_sqrt_bwd", B, N, 1024, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!grad_out || !eigvec || !eigval || !d_m) { set_error("ddw_psd_sqrt_bwd: null pointer"); return DDW_ERR_ARG; }
+    DDW_CHECK_ALIGNED("ddw_psd_sqrt_bwd", grad_out, eigvec, eigval, d_m, workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64
+               ? covariance_bwd_t<double>(grad_out, grad_out, nullptr, DDW_SHRINK_NONE, 1, eigvec, eigval, B, 0, (int)N, d_m, nullptr, workspace, workspace_bytes, st)
+               : covariance_bwd_t<float>(grad_out, grad_out, nullptr, DDW_SHRINK_NONE, 1, eigvec, eigval, B, 0, (int)N, d_m, nullptr, workspace, workspace_bytes, st);
+}
+
 }  // extern "C"

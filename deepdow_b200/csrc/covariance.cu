@@ -94,20 +94,27 @@ __global__ void __launch_bounds__(kThreads) covariance_fwd_kernel(CovParams<T> p
     int *pp = reinterpret_cast<int *>(ptr);
     int *pq = pp + NP;
 
-    const T *xb = p.x + b * (long long)L * N;
-    // 1. column means
-    for (int i = tid; i < N; i += kThreads) {
-        T acc = T(0);
-        for (int l = 0; l < L; ++l) acc += xb[(long long)l * N + i];
-        mean[i] = acc / (T)L;
+    const bool direct = L == 0;   // ddw_psd_sqrt_fwd: x already is the (B, N, N) symmetric matrix
+    const T *xb = p.x + b * (long long)(direct ? N : L) * N;
+    if (direct) {
+        for (int i = warp; i < N; i += kWarps)
+            for (int j = lane; j <= i; j += 32) S[i * LDS + j] = T(0.5) * (xb[(long long)i * N + j] + xb[(long long)j * N + i]);
+        __syncthreads();
+    } else {
+        // 1. column means
+        for (int i = tid; i < N; i += kThreads) {
+            T acc = T(0);
+            for (int l = 0; l < L; ++l) acc += xb[(long long)l * N + i];
+            mean[i] = acc / (T)L;
+        }
+        __syncthreads();
+        // 2. centred Gram (lower triangle, unscaled)
+        gram_lower<T, kThreads, false>(xb, nullptr, 0, 1, L, N, mean, nullptr, N, As, p.AS, p.CH, S, LDS, T(0));
+        // 3. 1/(L-1) and shrinkage
+        const T fact = T(1) / (T)(L - 1);
+        const T c = p.strategy == DDW_SHRINK_NONE ? T(1) : p.coef[b];
+        shrink_lower<T, kThreads>(S, LDS, N, p.strategy, c, fact, red);
     }
-    __syncthreads();
-    // 2. centred Gram (lower triangle, unscaled)
-    gram_lower<T, kThreads, false>(xb, nullptr, 0, 1, L, N, mean, nullptr, N, As, p.AS, p.CH, S, LDS, T(0));
-    // 3. 1/(L-1) and shrinkage
-    const T fact = T(1) / (T)(L - 1);
-    const T c = p.strategy == DDW_SHRINK_NONE ? T(1) : p.coef[b];
-    shrink_lower<T, kThreads>(S, LDS, N, p.strategy, c, fact, red);
     T *outb = p.out + b * (long long)N * N;
     if (!p.do_sqrt) {
         store_sym<T, kThreads>(S, LDS, N, outb);
@@ -304,6 +311,7 @@ __global__ void __launch_bounds__(kThreads) covariance_bwd_kernel(CovParams<T> p
     T *rs = ptr; ptr += NP;
     T *red = ptr; ptr += 64;
 
+    const bool direct = L == 0;   // ddw_psd_sqrt_bwd: gradient w.r.t. the matrix itself
     const T *xb = p.x + b * (long long)L * N;
     const T *gb = p.grad_out + b * (long long)N * N;
     // symmetrised upstream gradient
@@ -318,9 +326,11 @@ __global__ void __launch_bounds__(kThreads) covariance_bwd_kernel(CovParams<T> p
         }
     }
     for (int i = tid; i < N; i += kThreads) {
-        T acc = T(0);
-        for (int l = 0; l < L; ++l) acc += xb[(long long)l * N + i];
-        mean[i] = acc / (T)L;
+        if (!direct) {
+            T acc = T(0);
+            for (int l = 0; l < L; ++l) acc += xb[(long long)l * N + i];
+            mean[i] = acc / (T)L;
+        }
         if (p.do_sqrt) rs[i] = p.eigval_in[b * N + i];
     }
     __syncthreads();
@@ -336,6 +346,17 @@ __global__ void __launch_bounds__(kThreads) covariance_bwd_kernel(CovParams<T> p
         __syncthreads();
         mm_smem<T, kThreads>(Gm, LD, 1, VT, LD, 1, S0, LD, N);      // S0 = M VT
         mm_smem<T, kThreads>(VT, 1, LD, S0, LD, 1, Gm, LD, N);      // Gm = VT' S0 = V M V'
+    }
+    if (direct) {
+        T *dm = p.d_x + b * (long long)N * N;
+        int i = tid / N, j = tid - i * N;
+        const int di = kThreads / N, dj = kThreads % N;
+        for (int e = tid; e < N * N; e += kThreads) {
+            dm[e] = Gm[i * LD + j];
+            j += dj; i += di;
+            if (j >= N) { j -= N; ++i; }
+        }
+        return;
     }
     // sample covariance (lower, unscaled) for the coefficient gradient
     const T fact = T(1) / (T)(L - 1);
@@ -421,7 +442,7 @@ static CovPlan cov_plan_fwd(int L, int N, int tsize, int do_sqrt) {
     pl.LDS = N | 1;
     pl.LDV = round_up(N, 4);
     pl.AS = round_up(N, 4);
-    pl.CH = max(1, min(L, pl.threads * kPre / N));
+    pl.CH = max(1, min(max(L, 1), pl.threads * kPre / N));
     const int NP = round_up(N + 2, 32);
     const size_t vec = ((size_t)2 * pl.CH * pl.AS + 4 * (size_t)NP + 64) * tsize + 2 * (size_t)NP * sizeof(int);
     const size_t mat = ((size_t)round_up(N * pl.LDS, 4) + (do_sqrt ? (size_t)round_up(N * pl.LDV, 4) : 0)) * tsize;
@@ -442,7 +463,7 @@ static CovPlan cov_plan_bwd(int L, int N, int tsize, int do_sqrt) {
     pl.LDS = N | 1;
     pl.LDV = pl.LDS;
     pl.AS = round_up(N, 4);
-    pl.CH = max(2, min(L, pl.threads * kPre / N));   // >= 2 so that the staging area also holds the 4 x N d_x tile
+    pl.CH = max(2, min(max(L, 2), pl.threads * kPre / N));   // >= 2 so that the staging area also holds the 4 x N d_x tile
     const int NP = round_up(N + 2, 32);
     const size_t vec = ((size_t)2 * pl.CH * pl.AS + 2 * (size_t)NP + 64) * tsize;
     const size_t msz = (size_t)round_up(N * pl.LDS, 4);

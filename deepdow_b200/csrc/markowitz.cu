@@ -891,11 +891,13 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
         }
     } else if (nF > 0) {
         // one warp per row, coalesced reads of covmat_sqrt (L2 resident after the Gram)
+        unsigned grow = (unsigned)((gflat0 + (long long)warp * N + lane) % p.B);
+        const unsigned growstep = (unsigned)(((long long)kWarps * N) % p.B);
+        const unsigned gstep = (unsigned)(32 % p.B);
         for (int j = warp; j < N; j += kWarps) {
             T sp = T(0), sq = T(0);
-            const long long rowflat = gflat0 + (long long)j * N;
-            unsigned gi = (unsigned)((rowflat + lane) % p.B);
-            const unsigned gstep = (unsigned)(32 % p.B);
+            unsigned gi = grow;
+            grow += growstep; if (grow >= uB) grow -= uB;
             for (int k = lane; k < N; k += 32) {
                 const T a = Cb[(long long)j * N + k] * p.gamma[gi];
                 sp = fma(a, dv[k], sp); sq = fma(a, wv[k], sq);
@@ -912,15 +914,18 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
     // d_covmat_sqrt = gamma_ * (-2) (p w' + q d'): one warp per row, 16-byte stores when rows are aligned
     T *dC = p.d_C + gflat0;
     if ((N & 3) == 0) {
+        // gamma index of (row j, column 4*lane): one 64-bit modulo per thread, then incremental
+        unsigned grow = (unsigned)((gflat0 + (long long)warp * N + 4 * lane) % p.B);
+        const unsigned growstep = (unsigned)(((long long)kWarps * N) % p.B);
+        const unsigned gstep = (unsigned)(128 % p.B);
+        const bool gvec = (uB & 3u) == 0u;
         for (int j = warp; j < N; j += kWarps) {
             const T pj = T(-2) * pv[j], qj = T(-2) * qv[j];
-            const long long rowflat = gflat0 + (long long)j * N;
-            unsigned gi = (unsigned)((rowflat + 4 * lane) % p.B);
-            const unsigned gstep = (unsigned)(128 % p.B);
+            unsigned gi = grow;
             for (int k = 4 * lane; k < N; k += 128) {
                 const Vec4<T> w4 = ld4(wv + k), d4 = ld4(dv + k);
                 Vec4<T> o, g4;
-                if ((uB & 3u) == 0u) g4 = ld4(p.gamma + gi);
+                if (gvec) g4 = ld4(p.gamma + gi);
                 else { unsigned g = gi;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { g4.v[q] = p.gamma[g]; if (++g >= uB) g = 0; } }
@@ -929,6 +934,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
                 st4(dC + (long long)j * N + k, o);
                 gi += gstep; if (gi >= uB) gi -= uB;
             }
+            grow += growstep; if (grow >= uB) grow -= uB;
         }
     } else {
         const int total = N * N;

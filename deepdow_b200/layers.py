@@ -351,6 +351,41 @@ class _CovarianceFn(torch.autograd.Function):
         return d_x, d_coef, None, None
 
 
+class _PsdSqrtFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, m):
+        _C.require_cuda(m)
+        lib = _C.lib()
+        B, N, _ = m.shape
+        dt = _C.dtype_code(m)
+        m_c = _C.aligned(m)
+        out = torch.empty_like(m_c)
+        eigvec = eigval = None
+        if m.requires_grad:
+            eigvec = torch.empty_like(m_c)
+            eigval = torch.empty((B, N), dtype=m.dtype, device=m.device)
+        ws = _workspace(lib.ddw_covariance_workspace_bytes(B, 2, N, dt, 1), m.device)
+        rc = lib.ddw_psd_sqrt_fwd(_C.ptr(m_c), B, N, dt, _C.ptr(out), _C.ptr(eigvec), _C.ptr(eigval), _C.ptr(ws),
+                                  ws.numel(), _C.stream())
+        _C.check(rc, "ddw_psd_sqrt_fwd")
+        ctx.save_for_backward(eigvec, eigval)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eigvec, eigval = ctx.saved_tensors
+        lib = _C.lib()
+        B, N, _ = eigvec.shape
+        dt = _C.dtype_code(eigvec)
+        g = _C.aligned(grad_out)
+        d_m = torch.empty_like(eigvec)
+        ws = _workspace(lib.ddw_covariance_workspace_bytes(B, 2, N, dt, 1), eigvec.device)
+        rc = lib.ddw_psd_sqrt_bwd(_C.ptr(g), _C.ptr(eigvec), _C.ptr(eigval), B, N, dt, _C.ptr(d_m), _C.ptr(ws),
+                                  ws.numel(), _C.stream())
+        _C.check(rc, "ddw_psd_sqrt_bwd")
+        return d_m
+
+
 class CovarianceMatrix(nn.Module):
     """Covariance matrix or its square root.
 
@@ -400,3 +435,8 @@ class CovarianceMatrix(nn.Module):
             raise ZeroDivisionError("float division by zero")
         coef = None if shrinkage_strategy is None else coef
         return _CovarianceFn.apply(x, coef, _C.SHRINKAGE[shrinkage_strategy], False)[0]
+
+    @staticmethod
+    def compute_sqrt(m):
+        """Square root of a single positive semi-definite matrix (n_assets, n_assets), misc.py:168-201."""
+        return _PsdSqrtFn.apply(m.unsqueeze(0))[0]

@@ -131,6 +131,16 @@ int ddw_covariance_bwd(const void *grad_out, const void *x, const void *coef, in
                        void *d_x, void *d_coef,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * CovarianceMatrix.compute_sqrt (misc.py:168-201) on given symmetric matrices m (B,N,N):
+ * out = v sqrt|lambda| v' with the reference's rank threshold; eigvec/eigval as in ddw_covariance_fwd
+ * (NULL when no backward is needed).  Workspace: ddw_covariance_workspace_bytes(B, 2, N, dtype, 1).
+ * ------------------------------------------------------------------------------------------- */
+int ddw_psd_sqrt_fwd(const void *m, int64_t B, int64_t N, int dtype, void *out, void *eigvec, void *eigval,
+                     void *workspace, size_t workspace_bytes, void *stream);
+int ddw_psd_sqrt_bwd(const void *grad_out, const void *eigvec, const void *eigval, int64_t B, int64_t N, int dtype,
+                     void *d_m, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -373,3 +373,20 @@ def test_covariance_reference_behaviour(golden_dir):
     l2 = CovarianceMatrix(sqrt=False, shrinkage_strategy="diagonal", shrinkage_coef=None)
     assert torch.allclose(l1(x), l2(x, 0.3 * torch.ones(3, device=DEV)))
     assert sum(p.numel() for p in l1.parameters()) == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_compute_sqrt_static(dtype):
+    """CovarianceMatrix.compute_sqrt (misc.py:168-201) on a given matrix, forward and gradient."""
+    rng = np.random.default_rng(21)
+    for N in (5, 40, 110):
+        R = rng.standard_normal((N, N))
+        M = R @ R.T / N + 0.05 * np.eye(N)
+        G = rng.standard_normal((N, N))
+        m = t(M, dtype, True)
+        r = CovarianceMatrix.compute_sqrt(m)
+        Min = m.detach().double().cpu().numpy()
+        assert rel_err(r, oracle.psd_sqrt_fwd(Min[None])[0]) < (2e-5 if dtype == torch.float32 else 1e-10)
+        assert rel_err(r @ r, Min) < (5e-5 if dtype == torch.float32 else 1e-10)
+        (r * t(G, dtype)).sum().backward()
+        assert rel_err(m.grad, oracle.psd_sqrt_bwd(G[None], Min[None])[0]) < (2e-3 if dtype == torch.float32 else 1e-7)

@@ -1,0 +1,9 @@
+// markowitz_fwd_f32.cu -- float instantiation of the NumericalMarkowitz forward solver (markowitz_impl.cuh).
+// One translation unit per (direction, dtype) so that nvcc compiles them in parallel.
+#define DDW_MK_DEFINE_WORKSPACE
+#include "markowitz_impl.cuh"
+
+namespace ddw {
+template int markowitz_fwd_t<float>(const void *, const void *, const void *, const void *, double, long long, int,
+                                    void *, int8_t *, int32_t *, void *, size_t, cudaStream_t);
+}  // namespace ddw

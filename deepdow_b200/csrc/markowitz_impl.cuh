@@ -1,4 +1,4 @@
-// markowitz.cu -- batched box-and-simplex QP solver and its implicit-differentiation backward.
+// markowitz_impl.cuh -- batched box-and-simplex QP solver and its implicit-differentiation backward.
 //
 // Replaces the CvxpyLayer call of NumericalMarkowitz.forward (reference
 // deepdow/layers/allocate.py:240-273; problem stated at :220-232) and the diffcp adjoint behind it.
@@ -14,6 +14,7 @@
 // diagonal approximation of Q; every iterate is an exact reduced-KKT solve, so the converged
 // answer is the exact optimum of the program that SCS only approximates.  Problems on which the
 // active set cycles are handed to a Mehrotra interior-point kernel (same primitives) and polished.
+#pragma once
 #include "common.cuh"
 #include "linalg.cuh"
 
@@ -1072,6 +1073,8 @@ constexpr int kIpmGrid = 296;
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
+size_t markowitz_workspace_bytes(long long B, int N, int tsize);
+#ifdef DDW_MK_DEFINE_WORKSPACE
 size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
     const MkPlan pf = plan_fwd(N, tsize), pb = plan_bwd(N, tsize);
     const int NP = round_up(N + 2, 32);
@@ -1085,6 +1088,8 @@ size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
     bytes += align256(q);
     return bytes;
 }
+
+#endif  // DDW_MK_DEFINE_WORKSPACE
 
 template <typename T> struct WsLayout {
     int *fail_count, *fail_list, *work_count, *work_list, *bad_count;
@@ -1229,16 +1234,5 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
                                                         q_per, (T *)d_gamma);
     return check_launch("markowitz_gamma_kernel");
 }
-
-template int markowitz_fwd_t<float>(const void *, const void *, const void *, const void *, double, long long, int,
-                                    void *, int8_t *, int32_t *, void *, size_t, cudaStream_t);
-template int markowitz_fwd_t<double>(const void *, const void *, const void *, const void *, double, long long, int,
-                                     void *, int8_t *, int32_t *, void *, size_t, cudaStream_t);
-template int markowitz_bwd_t<float>(const void *, const void *, const int8_t *, const void *, const void *,
-                                    const void *, long long, int, void *, void *, void *, void *, void *, size_t,
-                                    cudaStream_t);
-template int markowitz_bwd_t<double>(const void *, const void *, const int8_t *, const void *, const void *,
-                                     const void *, long long, int, void *, void *, void *, void *, void *, size_t,
-                                     cudaStream_t);
 
 }  // namespace ddw

@@ -148,10 +148,11 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=256, help="problems per stage of the host-buffer pipeline (e2e)")
     ap.add_argument("--status-mode", default="lazy", choices=["lazy", "sync", "off"],
                     help="NumericalMarkowitz.check_status: lazy (default of the layer), sync (read the failure "
                          "counter inside every forward: a host sync) or off (diagnostic)")
@@ -228,7 +229,6 @@ def main():
     t_end.record()
     cpu_enqueue_ms = 1e3 * (time.perf_counter() - cpu0) / args.steps   # host time to enqueue one step
     barrier()
-    clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
     fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
     bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
@@ -248,10 +248,34 @@ def main():
     fwd_only_ms = f0.elapsed_time(f1)
 
     # ---- timed region 2: end to end from pinned host buffers -----------------------------------
+    # (a) the host-buffer C-ABI call (ddw_markowitz_host_step through MarkowitzHostPipeline): chunks flow through
+    #     H2D / kernels / D2H streams; every input comes from and every output lands in pinned host memory
+    # (b) the same through the nn.Module with explicit .to(device) / .copy_ around it (no overlap)
+    from deepdow_b200.host import MarkowitzHostPipeline
     host_in = [t.detach().cpu().pin_memory() for t in (rets, C, gam, alp, G)]
-    host_out = [torch.empty(s, dtype=torch.float32).pin_memory() for s in ((B, N), (B, N), (B, N, N), (B,), (B,))]
     h2d_bytes = sum(t.numel() * 4 for t in host_in)
-    d2h_bytes = sum(t.numel() * 4 for t in host_out)
+    pipe = MarkowitzHostPipeline(N, u, chunk=args.chunk, device=dev)
+    out = pipe.step(*host_in)
+    d2h_bytes = sum(t.numel() * t.element_size() for t in out)
+    for _ in range(2):
+        out = pipe.step(*host_in, out=out, sync=False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = pipe.step(*host_in, out=out, sync=False)
+    e1.record()
+    barrier()
+    pipe.check()
+    clocks = sampler.stop()          # sampled over both timed regions (device-resident and end-to-end)
+    e2e_ms = e0.elapsed_time(e1)
+    n_chunks = (B + args.chunk - 1) // args.chunk
+    # the pipelined host path must reproduce the device path bit for bit (same kernels, chunked)
+    with torch.no_grad():
+        w_dev = layer(*[t.detach() for t in inputs])
+    assert torch.equal(out.w, w_dev.cpu()), "host pipeline and device path disagree"
+
+    host_out = [torch.empty(s, dtype=torch.float32).pin_memory() for s in ((B, N), (B, N), (B, N, N), (B,), (B,))]
 
     def step_e2e():
         d = [t.to(dev, non_blocking=True) for t in host_in]
@@ -264,18 +288,18 @@ def main():
     for _ in range(3):
         step_e2e()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
     for _ in range(args.steps):
         step_e2e()
-    e1.record()
+    l1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_layer_ms = l0.elapsed_time(l1)
 
-    times = torch.tensor([elapsed_ms, e2e_ms, fwd_only_ms], device=dev, dtype=torch.float64)
+    times = torch.tensor([elapsed_ms, e2e_ms, fwd_only_ms, e2e_layer_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, fwd_only_ms = [float(x) for x in times.tolist()]
+    elapsed_ms, e2e_ms, fwd_only_ms, e2e_layer_ms = [float(x) for x in times.tolist()]
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -300,7 +324,11 @@ def main():
                        "active_set": {"mean_free": nfree, "mean_at_cap": ncap, "fallback_problems": nfallback}},
             "e2e": {"value": world * B * steps_total / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms / steps_total},
+                    "ms_per_step": e2e_ms / steps_total,
+                    "api": f"ddw_markowitz_host_step via MarkowitzHostPipeline.step (pinned host buffers, {n_chunks} chunks of "
+                           f"{args.chunk} problems on H2D / kernel / D2H streams)",
+                    "layer_api_unpipelined": {"value": world * B * steps_total / (e2e_layer_ms * 1e-3),
+                                              "ms_per_step": e2e_layer_ms / steps_total}},
             "gpu_launches": 5 * steps_total,
             "kernels_per_step": ["markowitz_fwd_sparse_kernel", "markowitz_fwd_kernel (dense work list, empty here)",
                                  "markowitz_ipm_kernel (fallback list, empty here)", "markowitz_bwd_kernel",

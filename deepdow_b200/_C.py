@@ -28,6 +28,15 @@ SIGNATURES = {
     "ddw_markowitz_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "ddw_markowitz_fwd": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddw_markowitz_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ddw_markowitz_fwd_chunk": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ddw_markowitz_bwd_chunk": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _i32,
+                                       _vp, _vp, _sz, _vp]),
+    "ddw_host_pipeline_create": (_i32, [ctypes.POINTER(ctypes.c_void_p)]),
+    "ddw_host_pipeline_destroy": (None, [_vp]),
+    "ddw_host_pipeline_graph_launches": (_i32, [_vp]),
+    "ddw_markowitz_host_scratch_bytes": (_sz, [_i64, _i64, _i32, _i64]),
+    "ddw_markowitz_host_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _sz, _vp]),
     "ddw_capped_simplex_fwd": (_i32, [_vp, _vp, _dbl, _dbl, _i64, _i64, _i32, _vp, _vp]),
     "ddw_capped_simplex_bwd": (_i32, [_vp, _vp, _vp, _vp, _dbl, _dbl, _i64, _i64, _i32, _vp, _vp, _vp]),
     "ddw_capped_softmax_fwd": (_i32, [_vp, _vp, _dbl, _dbl, _i64, _i64, _i32, _vp, _vp]),

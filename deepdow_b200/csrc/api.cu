@@ -29,10 +29,10 @@ int check_launch(const char *what) {
 size_t markowitz_workspace_bytes(long long B, int N, int tsize);
 template <typename T>
 int markowitz_fwd_t(const void *, const void *, const void *, const void *, double, long long, int, void *, int8_t *,
-                    int32_t *, void *, size_t, cudaStream_t);
+                    int32_t *, void *, size_t, cudaStream_t, long long, long long);
 template <typename T>
 int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, const void *, const void *, long long,
-                    int, void *, void *, void *, void *, void *, size_t, cudaStream_t);
+                    int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int);
 template <typename T>
 int row_op_t(int, const void *, const void *, double, double, long long, int, const void *, const void *, void *,
              void *, void *, cudaStream_t);
@@ -74,36 +74,55 @@ size_t ddw_markowitz_workspace_bytes(int64_t B, int64_t N, int dtype) {
     return markowitz_workspace_bytes(B, (int)N, dtype == DDW_F64 ? 8 : 4);
 }
 
-int ddw_markowitz_fwd(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
-                      double max_weight, int64_t B, int64_t N, int dtype, void *w, int8_t *state, int32_t *status,
-                      void *workspace, size_t workspace_bytes, void *stream) {
+int ddw_markowitz_fwd_chunk(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                            double max_weight, int64_t B, int64_t N, int dtype, int64_t batch_total, int64_t batch_offset,
+                            void *w, int8_t *state, int32_t *status, void *workspace, size_t workspace_bytes,
+                            void *stream) {
     g_err[0] = 0;
     int rc = check_dims("ddw_markowitz_fwd", B, N, 1024, dtype);
     if (rc) return rc;
     if (B == 0) return 0;
+    if (batch_offset < 0 || batch_offset + B > batch_total || batch_total >= (1LL << 31)) { set_error("ddw_markowitz_fwd: chunk [%lld, %lld) outside the batch of %lld", (long long)batch_offset, (long long)(batch_offset + B), (long long)batch_total); return DDW_ERR_ARG; }
     if (!rets || !covmat_sqrt || !gamma_sqrt || !alpha || !w || !state || !status) { set_error("ddw_markowitz_fwd: null pointer"); return DDW_ERR_ARG; }
     DDW_CHECK_ALIGNED("ddw_markowitz_fwd", rets, covmat_sqrt, gamma_sqrt, alpha, w, workspace);
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64
-               ? markowitz_fwd_t<double>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st)
-               : markowitz_fwd_t<float>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st);
+               ? markowitz_fwd_t<double>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, batch_total, batch_offset)
+               : markowitz_fwd_t<float>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, batch_total, batch_offset);
+}
+
+int ddw_markowitz_fwd(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                      double max_weight, int64_t B, int64_t N, int dtype, void *w, int8_t *state, int32_t *status,
+                      void *workspace, size_t workspace_bytes, void *stream) {
+    return ddw_markowitz_fwd_chunk(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, N, dtype, B, 0, w, state, status,
+                                   workspace, workspace_bytes, stream);
+}
+
+int ddw_markowitz_bwd_chunk(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt,
+                            const void *gamma_sqrt, const void *alpha, double max_weight, int64_t B, int64_t N, int dtype,
+                            int64_t batch_total, int64_t batch_offset, void *d_rets, void *d_covmat_sqrt,
+                            void *d_gamma_sqrt, int accumulate_gamma, void *d_alpha, void *workspace,
+                            size_t workspace_bytes, void *stream) {
+    (void)max_weight;
+    g_err[0] = 0;
+    int rc = check_dims("ddw_markowitz_bwd", B, N, 1024, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (batch_offset < 0 || batch_offset + B > batch_total || batch_total >= (1LL << 31)) { set_error("ddw_markowitz_bwd: chunk [%lld, %lld) outside the batch of %lld", (long long)batch_offset, (long long)(batch_offset + B), (long long)batch_total); return DDW_ERR_ARG; }
+    if (!grad_w || !w || !state || !covmat_sqrt || !gamma_sqrt || !alpha || !d_rets || !d_covmat_sqrt || !d_alpha) { set_error("ddw_markowitz_bwd: null pointer"); return DDW_ERR_ARG; }
+    DDW_CHECK_ALIGNED("ddw_markowitz_bwd", grad_w, w, covmat_sqrt, gamma_sqrt, alpha, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64
+               ? markowitz_bwd_t<double>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st, batch_total, batch_offset, accumulate_gamma)
+               : markowitz_bwd_t<float>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st, batch_total, batch_offset, accumulate_gamma);
 }
 
 int ddw_markowitz_bwd(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt,
                       const void *gamma_sqrt, const void *alpha, double max_weight, int64_t B, int64_t N, int dtype,
                       void *d_rets, void *d_covmat_sqrt, void *d_gamma_sqrt, void *d_alpha, void *workspace,
                       size_t workspace_bytes, void *stream) {
-    (void)max_weight;
-    g_err[0] = 0;
-    int rc = check_dims("ddw_markowitz_bwd", B, N, 1024, dtype);
-    if (rc) return rc;
-    if (B == 0) return 0;
-    if (!grad_w || !w || !state || !covmat_sqrt || !gamma_sqrt || !alpha || !d_rets || !d_covmat_sqrt || !d_alpha) { set_error("ddw_markowitz_bwd: null pointer"); return DDW_ERR_ARG; }
-    DDW_CHECK_ALIGNED("ddw_markowitz_bwd", grad_w, w, covmat_sqrt, gamma_sqrt, alpha, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace);
-    cudaStream_t st = (cudaStream_t)stream;
-    return dtype == DDW_F64
-               ? markowitz_bwd_t<double>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st)
-               : markowitz_bwd_t<float>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st);
+    return ddw_markowitz_bwd_chunk(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, N, dtype, B, 0, d_rets,
+                                   d_covmat_sqrt, d_gamma_sqrt, 0, d_alpha, workspace, workspace_bytes, stream);
 }
 
 static int row_call(const char *fn, int which, const void *x, const void *temperature, double tscalar, double u,

@@ -1,0 +1,288 @@
+// host_pipeline.cu -- HOST-buffer entry point of NumericalMarkowitz (include/ddw.h, "HOST-buffer entry point").
+//
+// The reference layer is called with CPU tensors and returns CPU tensors (deepdow/layers/allocate.py:240-273,
+// solved on host threads behind CvxpyLayer, :273).  A caller that keeps its data on the host therefore needs
+// host -> device -> host around the solver kernels.  Done naively that is three serial phases (copy in, solve,
+// copy out) and PCIe, not the GPU, sets the pace: at B = 4096, N = 100 the step moves 167 MB each way.
+// Here the (B,N,N) tensors -- 98% of the bytes -- are cut into chunks that flow through three streams
+//     s_in : H2D of chunk i+1      s_run : forward + backward of chunk i      s_out : D2H of chunk i-1
+// so that both PCIe directions and the kernels run at the same time; the small per-problem vectors travel once
+// per batch.  Chunk slots live in caller-owned device scratch and are recycled round-robin, guarded by events.
+//
+// A step enqueues ~15 operations per chunk, and at 16-32 chunks the host cannot issue them as fast as the GPU
+// retires them (measured: 70-100 us of enqueue time per chunk).  The whole step -- copies, kernels and the
+// cross-stream dependencies -- is therefore captured into a CUDA graph the second time it is requested with the
+// same arguments and replayed with a single launch from then on.  Capture needs page-locked host buffers;
+// pageable ones take the eager path.
+#include "common.cuh"
+
+namespace ddw {
+
+size_t markowitz_workspace_bytes(long long B, int N, int tsize);
+template <typename T>
+int markowitz_fwd_t(const void *, const void *, const void *, const void *, double, long long, int, void *, int8_t *,
+                    int32_t *, void *, size_t, cudaStream_t, long long, long long);
+template <typename T>
+int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, const void *, const void *, long long,
+                    int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int);
+
+constexpr int kSlots = 3;
+
+static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+
+// device scratch: whole-batch vectors, then kSlots chunk slots of (covmat_sqrt, d_covmat_sqrt, workspace)
+struct ScratchLayout {
+    size_t gamma, d_gamma, rets, alpha, grad_w, w, state, status, d_rets, d_alpha;   // whole batch
+    size_t slots, slot_bytes, C, d_C, ws, ws_bytes;                                  // per slot
+    size_t total;
+};
+
+static ScratchLayout scratch_layout(long long B, long long chunk, int N, int tsize) {
+    ScratchLayout l;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += up256(bytes); return at; };
+    const size_t b = (size_t)B, c = (size_t)chunk, n = (size_t)N;
+    l.gamma = take(b * tsize);
+    l.d_gamma = take(b * tsize);
+    l.rets = take(b * n * tsize);
+    l.alpha = take(b * tsize);
+    l.grad_w = take(b * n * tsize);
+    l.w = take(b * n * tsize);
+    l.state = take(b * n);
+    l.status = take(b * sizeof(int32_t));
+    l.d_rets = take(b * n * tsize);
+    l.d_alpha = take(b * tsize);
+    l.slots = o;
+    o = 0;
+    l.C = take(c * n * n * tsize);
+    l.d_C = take(c * n * n * tsize);
+    l.ws_bytes = markowitz_workspace_bytes(chunk, N, tsize);
+    l.ws = take(l.ws_bytes);
+    l.slot_bytes = o;
+    l.total = l.slots + (size_t)kSlots * l.slot_bytes;
+    return l;
+}
+
+struct StepArgs {
+    const void *h_rets, *h_covmat_sqrt, *h_gamma_sqrt, *h_alpha, *h_grad_w;
+    double max_weight;
+    int64_t B, N, chunk;
+    int dtype;
+    void *h_w;
+    int32_t *h_status;
+    void *h_d_rets, *h_d_covmat_sqrt, *h_d_gamma_sqrt, *h_d_alpha, *dev_scratch;
+    size_t dev_scratch_bytes;
+    bool operator==(const StepArgs &o) const {
+        return h_rets == o.h_rets && h_covmat_sqrt == o.h_covmat_sqrt && h_gamma_sqrt == o.h_gamma_sqrt &&
+               h_alpha == o.h_alpha && h_grad_w == o.h_grad_w && max_weight == o.max_weight && B == o.B && N == o.N &&
+               chunk == o.chunk && dtype == o.dtype && h_w == o.h_w && h_status == o.h_status && h_d_rets == o.h_d_rets &&
+               h_d_covmat_sqrt == o.h_d_covmat_sqrt && h_d_gamma_sqrt == o.h_d_gamma_sqrt && h_d_alpha == o.h_d_alpha &&
+               dev_scratch == o.dev_scratch && dev_scratch_bytes == o.dev_scratch_bytes;
+    }
+};
+
+}  // namespace ddw
+
+using namespace ddw;
+
+struct ddw_host_pipeline {
+    cudaStream_t s_in, s_run, s_out, s_origin;
+    cudaEvent_t start, in_done[kSlots], run_done[kSlots], out_done[kSlots], head_in, tail_in, tail_run, tail_out;
+    // graph cache: the last argument set seen, and its instantiated graph once it has been seen twice
+    StepArgs last;
+    bool have_last;
+    cudaGraphExec_t exec;
+    int graph_launches;
+};
+
+namespace ddw {
+
+static bool page_locked(const void *p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// Enqueue one step: everything forks from `origin` and joins back into it.
+static int enqueue_step(ddw_host_pipeline *pipe, const StepArgs &a, cudaStream_t origin) {
+    const int ts = a.dtype == DDW_F64 ? 8 : 4, n = (int)a.N;
+    const int64_t B = a.B, chunk = a.chunk;
+    const ScratchLayout L = scratch_layout(B, chunk, n, ts);
+    unsigned char *base = reinterpret_cast<unsigned char *>(a.dev_scratch);
+    const bool bwd = a.h_grad_w != nullptr;
+    const bool want_dgamma = bwd && a.h_d_gamma_sqrt != nullptr;
+    const size_t row = (size_t)n * ts, mat = (size_t)n * n * ts;
+
+    cudaEventRecord(pipe->start, origin);
+    cudaStreamWaitEvent(pipe->s_in, pipe->start, 0);
+    cudaStreamWaitEvent(pipe->s_run, pipe->start, 0);
+    cudaStreamWaitEvent(pipe->s_out, pipe->start, 0);
+
+    // per-problem vectors of the whole batch: 2% of the bytes, one copy each
+    cudaMemcpyAsync(base + L.gamma, a.h_gamma_sqrt, (size_t)B * ts, cudaMemcpyHostToDevice, pipe->s_in);
+    cudaMemcpyAsync(base + L.rets, a.h_rets, (size_t)B * row, cudaMemcpyHostToDevice, pipe->s_in);
+    cudaMemcpyAsync(base + L.alpha, a.h_alpha, (size_t)B * ts, cudaMemcpyHostToDevice, pipe->s_in);
+    if (bwd) cudaMemcpyAsync(base + L.grad_w, a.h_grad_w, (size_t)B * row, cudaMemcpyHostToDevice, pipe->s_in);
+    cudaEventRecord(pipe->head_in, pipe->s_in);
+    cudaStreamWaitEvent(pipe->s_run, pipe->head_in, 0);
+    if (want_dgamma) cudaMemsetAsync(base + L.d_gamma, 0, (size_t)B * ts, pipe->s_run);
+
+    int rc = 0, it = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++it) {
+        const int64_t c = (B - b0 < chunk) ? (B - b0) : chunk;
+        const int sl = it % kSlots;
+        unsigned char *S = base + L.slots + (size_t)sl * L.slot_bytes;
+        // the slot is free once its previous tenant has been copied out
+        if (it >= kSlots) cudaStreamWaitEvent(pipe->s_in, pipe->out_done[sl], 0);
+        cudaMemcpyAsync(S + L.C, reinterpret_cast<const unsigned char *>(a.h_covmat_sqrt) + b0 * mat, c * mat,
+                        cudaMemcpyHostToDevice, pipe->s_in);
+        cudaEventRecord(pipe->in_done[sl], pipe->s_in);
+
+        cudaStreamWaitEvent(pipe->s_run, pipe->in_done[sl], 0);
+        unsigned char *rets = base + L.rets + b0 * row, *alpha = base + L.alpha + b0 * ts, *w = base + L.w + b0 * row;
+        unsigned char *grad_w = base + L.grad_w + b0 * row, *d_rets = base + L.d_rets + b0 * row;
+        unsigned char *d_alpha = base + L.d_alpha + b0 * ts;
+        int8_t *state = reinterpret_cast<int8_t *>(base + L.state) + b0 * n;
+        int32_t *status = reinterpret_cast<int32_t *>(base + L.status) + b0;
+        if (a.dtype == DDW_F64)
+            rc = markowitz_fwd_t<double>(rets, S + L.C, base + L.gamma, alpha, a.max_weight, c, n, w, state, status, S + L.ws, L.ws_bytes, pipe->s_run, B, b0);
+        else
+            rc = markowitz_fwd_t<float>(rets, S + L.C, base + L.gamma, alpha, a.max_weight, c, n, w, state, status, S + L.ws, L.ws_bytes, pipe->s_run, B, b0);
+        if (!rc && bwd) {
+            void *dg = want_dgamma ? base + L.d_gamma : nullptr;
+            if (a.dtype == DDW_F64)
+                rc = markowitz_bwd_t<double>(grad_w, w, state, S + L.C, base + L.gamma, alpha, c, n, d_rets, S + L.d_C, dg, d_alpha, S + L.ws, L.ws_bytes, pipe->s_run, B, b0, 1);
+            else
+                rc = markowitz_bwd_t<float>(grad_w, w, state, S + L.C, base + L.gamma, alpha, c, n, d_rets, S + L.d_C, dg, d_alpha, S + L.ws, L.ws_bytes, pipe->s_run, B, b0, 1);
+        }
+        cudaEventRecord(pipe->run_done[sl], pipe->s_run);
+        if (rc) break;
+
+        cudaStreamWaitEvent(pipe->s_out, pipe->run_done[sl], 0);
+        if (bwd)
+            cudaMemcpyAsync(reinterpret_cast<unsigned char *>(a.h_d_covmat_sqrt) + b0 * mat, S + L.d_C, c * mat,
+                            cudaMemcpyDeviceToHost, pipe->s_out);
+        cudaEventRecord(pipe->out_done[sl], pipe->s_out);
+    }
+    if (!rc) {
+        // s_out has waited for the last run_done, so every chunk's results are final
+        cudaMemcpyAsync(a.h_w, base + L.w, (size_t)B * row, cudaMemcpyDeviceToHost, pipe->s_out);
+        cudaMemcpyAsync(a.h_status, base + L.status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, pipe->s_out);
+        if (bwd) {
+            cudaMemcpyAsync(a.h_d_rets, base + L.d_rets, (size_t)B * row, cudaMemcpyDeviceToHost, pipe->s_out);
+            cudaMemcpyAsync(a.h_d_alpha, base + L.d_alpha, (size_t)B * ts, cudaMemcpyDeviceToHost, pipe->s_out);
+        }
+        if (want_dgamma) cudaMemcpyAsync(a.h_d_gamma_sqrt, base + L.d_gamma, (size_t)B * ts, cudaMemcpyDeviceToHost, pipe->s_out);
+    }
+    // `origin` resumes when all three streams have drained
+    cudaEventRecord(pipe->tail_in, pipe->s_in);
+    cudaEventRecord(pipe->tail_run, pipe->s_run);
+    cudaEventRecord(pipe->tail_out, pipe->s_out);
+    cudaStreamWaitEvent(origin, pipe->tail_in, 0);
+    cudaStreamWaitEvent(origin, pipe->tail_run, 0);
+    cudaStreamWaitEvent(origin, pipe->tail_out, 0);
+    return rc;
+}
+
+}  // namespace ddw
+
+extern "C" {
+
+int ddw_host_pipeline_create(ddw_host_pipeline **out) {
+    if (!out) { set_error("ddw_host_pipeline_create: null pointer"); return DDW_ERR_ARG; }
+    ddw_host_pipeline *p = new ddw_host_pipeline();
+    p->have_last = false; p->exec = nullptr; p->graph_launches = 0;
+    bool ok = cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->s_origin, cudaStreamNonBlocking) == cudaSuccess;
+    auto ev = [&](cudaEvent_t *e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+    ev(&p->start); ev(&p->head_in); ev(&p->tail_in); ev(&p->tail_run); ev(&p->tail_out);
+    for (int i = 0; i < kSlots; ++i) { ev(&p->in_done[i]); ev(&p->run_done[i]); ev(&p->out_done[i]); }
+    if (!ok) {
+        check_launch("ddw_host_pipeline_create");
+        delete p;
+        return DDW_ERR_CUDA;
+    }
+    *out = p;
+    return 0;
+}
+
+void ddw_host_pipeline_destroy(ddw_host_pipeline *p) {
+    if (!p) return;
+    cudaStreamSynchronize(p->s_in); cudaStreamSynchronize(p->s_run); cudaStreamSynchronize(p->s_out);
+    cudaStreamSynchronize(p->s_origin);
+    if (p->exec) cudaGraphExecDestroy(p->exec);
+    cudaEventDestroy(p->start); cudaEventDestroy(p->head_in);
+    cudaEventDestroy(p->tail_in); cudaEventDestroy(p->tail_run); cudaEventDestroy(p->tail_out);
+    for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(p->in_done[i]); cudaEventDestroy(p->run_done[i]); cudaEventDestroy(p->out_done[i]); }
+    cudaStreamDestroy(p->s_in); cudaStreamDestroy(p->s_run); cudaStreamDestroy(p->s_out); cudaStreamDestroy(p->s_origin);
+    delete p;
+}
+
+/* number of steps served by replaying the cached CUDA graph (diagnostic) */
+int ddw_host_pipeline_graph_launches(const ddw_host_pipeline *p) { return p ? p->graph_launches : 0; }
+
+size_t ddw_markowitz_host_scratch_bytes(int64_t B, int64_t N, int dtype, int64_t chunk) {
+    if (B <= 0 || N <= 0 || N > 1024 || chunk <= 0) return 0;
+    if (chunk > B) chunk = B;
+    return scratch_layout(B, chunk, (int)N, dtype == DDW_F64 ? 8 : 4).total;
+}
+
+int ddw_markowitz_host_step(ddw_host_pipeline *pipe, const void *h_rets, const void *h_covmat_sqrt,
+                            const void *h_gamma_sqrt, const void *h_alpha, const void *h_grad_w, double max_weight,
+                            int64_t B, int64_t N, int dtype, int64_t chunk, void *h_w, int32_t *h_status, void *h_d_rets,
+                            void *h_d_covmat_sqrt, void *h_d_gamma_sqrt, void *h_d_alpha, void *dev_scratch,
+                            size_t dev_scratch_bytes, void *stream) {
+    const char *fn = "ddw_markowitz_host_step";
+    if (dtype != DDW_F32 && dtype != DDW_F64) { set_error("%s: dtype must be DDW_F32 or DDW_F64", fn); return DDW_ERR_ARG; }
+    if (B < 0 || B >= (1LL << 31) || chunk <= 0) { set_error("%s: bad batch size / chunk", fn); return DDW_ERR_ARG; }
+    if (N < 1 || N > 1024) { set_error("%s: n_assets=%lld outside [1, 1024]", fn, (long long)N); return DDW_ERR_UNSUPPORTED; }
+    if (B == 0) return 0;
+    const bool bwd = h_grad_w != nullptr;
+    if (!pipe || !h_rets || !h_covmat_sqrt || !h_gamma_sqrt || !h_alpha || !h_w || !h_status ||
+        (bwd && (!h_d_rets || !h_d_covmat_sqrt || !h_d_alpha))) { set_error("%s: null pointer", fn); return DDW_ERR_ARG; }
+    if (chunk > B) chunk = B;
+    if (!dev_scratch || dev_scratch_bytes < ddw_markowitz_host_scratch_bytes(B, N, dtype, chunk)) { set_error("%s: device scratch too small", fn); return DDW_ERR_WORKSPACE; }
+    if (reinterpret_cast<uintptr_t>(dev_scratch) & 255u) { set_error("%s: device scratch must be 256-byte aligned", fn); return DDW_ERR_ARG; }
+    if (!bwd) h_d_rets = h_d_covmat_sqrt = h_d_gamma_sqrt = h_d_alpha = nullptr;
+
+    const StepArgs a = {h_rets, h_covmat_sqrt, h_gamma_sqrt, h_alpha, h_grad_w, max_weight, B, N, chunk, dtype, h_w, h_status,
+                        h_d_rets, h_d_covmat_sqrt, h_d_gamma_sqrt, h_d_alpha, dev_scratch, dev_scratch_bytes};
+    cudaStream_t user = (cudaStream_t)stream;
+    const bool same = pipe->have_last && pipe->last == a;
+    if (same && pipe->exec) {
+        ++pipe->graph_launches;
+        cudaGraphLaunch(pipe->exec, user);
+        return check_launch(fn);
+    }
+    if (pipe->exec) { cudaGraphExecDestroy(pipe->exec); pipe->exec = nullptr; }
+    if (same && page_locked(h_rets) && page_locked(h_covmat_sqrt) && page_locked(h_gamma_sqrt) && page_locked(h_alpha) &&
+        page_locked(h_grad_w) && page_locked(h_w) && page_locked(h_status) && page_locked(h_d_rets) &&
+        page_locked(h_d_covmat_sqrt) && page_locked(h_d_gamma_sqrt) && page_locked(h_d_alpha)) {
+        // second request with these arguments: record the step once, replay it from now on
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(pipe->s_origin, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = enqueue_step(pipe, a, pipe->s_origin);
+            const cudaError_t e = cudaStreamEndCapture(pipe->s_origin, &graph);
+            if (!rc && e == cudaSuccess && graph &&
+                cudaGraphInstantiate(&pipe->exec, graph, nullptr, nullptr, 0) == cudaSuccess) {
+                cudaGraphDestroy(graph);
+                ++pipe->graph_launches;
+                cudaGraphLaunch(pipe->exec, user);
+                return check_launch(fn);
+            }
+            if (graph) cudaGraphDestroy(graph);
+            pipe->exec = nullptr;
+        }
+        cudaGetLastError();   // capture failed: fall through to the eager path
+    }
+    pipe->last = a;
+    pipe->have_last = true;
+    const int rc = enqueue_step(pipe, a, user);
+    if (rc) return rc;
+    return check_launch(fn);
+}
+
+}  // extern "C"

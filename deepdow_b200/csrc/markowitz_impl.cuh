@@ -26,7 +26,9 @@ constexpr int kMaxIpm = 40;
 template <typename T> struct MkFwdParams {
     const T *rets, *C, *gamma, *alpha;
     T u;
-    long long B;
+    long long B;       // problems in this launch
+    long long Bmod;    // n_samples of the whole batch = modulus of the gamma tiling
+    long long b0;      // index of this launch's first problem in the whole batch
     int N, LD, AS, CH;
     T *w;
     int8_t *state;
@@ -387,10 +389,10 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> 
         const T aabs = absT(p.alpha[b]);
         if (MAXT > 0)
             gram_lower_reg<T, kThreads, (MAXT > 0 ? MAXT : 1), false>(p.C + b * (long long)N * N, p.gamma,
-                                                                       b * (long long)N * N, p.B, N, N, nullptr, nullptr,
+                                                                       (p.b0 + b) * (long long)N * N, p.Bmod, N, N, nullptr, nullptr,
                                                                        N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
         else
-            gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, b * (long long)N * N, p.B, N, N,
+            gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, (p.b0 + b) * (long long)N * N, p.Bmod, N, N,
                                            nullptr, nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
         if (tid < 32) {
             T dmax;
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_ipm_kernel(MkFwdParams<T> 
         __syncthreads();
         for (int i = tid; i < N; i += kThreads) s.r[i] = p.rets[b * N + i];
         const T aabs = absT(p.alpha[b]);
-        gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, b * (long long)N * N, p.B, N, N, nullptr,
+        gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, (p.b0 + b) * (long long)N * N, p.Bmod, N, N, nullptr,
                                        nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
         // objective scale so that gradients are O(1)
         T sc = T(0);
@@ -639,7 +641,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_ipm_kernel(MkFwdParams<T> 
 template <typename T> struct MkBwdParams {
     const T *grad_w, *w, *C, *gamma, *alpha;
     const int8_t *state;
-    long long B;
+    long long B, Bmod, b0;   // as in MkFwdParams
     int N, LDW, AS, CH;
     T *d_rets, *d_C, *d_alpha, *vecs;
     T *ws;  // global factor storage when it does not fit shared memory
@@ -708,9 +710,9 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
     __syncthreads();
     const int nF = misc[0], nS = misc[0] + misc[1];
     const T *Cb = p.C + b * (long long)N * N;
-    const long long gflat0 = b * (long long)N * N;
+    const long long gflat0 = (p.b0 + b) * (long long)N * N;
     const T alpha = p.alpha[b];
-    const unsigned uB = (unsigned)p.B;
+    const unsigned uB = (unsigned)p.Bmod;
     const int CS = round_up(nS, 4), LDc = (nF + 2) | 1;
     const int NT = (nF + 3) >> 2, ntiles = NT * (NT + 1) / 2;
     // K-split of the small Gram: KS slices of rows per tile, partial sums reduced through shared memory
@@ -732,8 +734,8 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
                 const int n4 = N * N / 4;
                 int k = (4 * tid) / N, i = 4 * tid - k * N;
                 const int dk = (4 * kThreads) / N, di = (4 * kThreads) % N;
-                unsigned gi = (unsigned)((gflat0 + 4 * tid) % p.B);
-                const unsigned gstep = (unsigned)((4 * kThreads) % p.B);
+                unsigned gi = (unsigned)((gflat0 + 4 * tid) % p.Bmod);
+                const unsigned gstep = (unsigned)((4 * kThreads) % p.Bmod);
                 const bool gvec = (uB & 3u) == 0u;   // then every aligned 4-group of flat indices is contiguous mod B
                 for (int e4 = tid; e4 < n4; e4 += 4 * kThreads) {
                     Vec4<T> v[4], g4[4];
@@ -766,8 +768,8 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
             } else {
                 int k = tid / N, i = tid - k * N;
                 const int dk = kThreads / N, di = kThreads % N;
-                unsigned gi = (unsigned)((gflat0 + tid) % p.B);
-                const unsigned gstep = (unsigned)(kThreads % p.B);
+                unsigned gi = (unsigned)((gflat0 + tid) % p.Bmod);
+                const unsigned gstep = (unsigned)(kThreads % p.Bmod);
                 for (int e = tid; e < N * N; e += kThreads) {
                     const int c = posS[i];
                     if (c >= 0) Ac[k * CS + c] = Cb[e] * p.gamma[gi];
@@ -831,7 +833,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
                 __syncthreads();
             }
         } else {
-            gram_lower<T, kThreads, true>(Cb, p.gamma, gflat0, p.B, N, N, nullptr, pos, nF, arena + (kGlobal ? 0 : round_up(N * LDW, 4)),
+            gram_lower<T, kThreads, true>(Cb, p.gamma, gflat0, p.Bmod, N, N, nullptr, pos, nF, arena + (kGlobal ? 0 : round_up(N * LDW, 4)),
                                           p.AS, p.CH, Lb, ldl, absT(alpha));
         }
         T dmax = T(0);
@@ -892,9 +894,9 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
         }
     } else if (nF > 0) {
         // one warp per row, coalesced reads of covmat_sqrt (L2 resident after the Gram)
-        unsigned grow = (unsigned)((gflat0 + (long long)warp * N + lane) % p.B);
-        const unsigned growstep = (unsigned)(((long long)kWarps * N) % p.B);
-        const unsigned gstep = (unsigned)(32 % p.B);
+        unsigned grow = (unsigned)((gflat0 + (long long)warp * N + lane) % p.Bmod);
+        const unsigned growstep = (unsigned)(((long long)kWarps * N) % p.Bmod);
+        const unsigned gstep = (unsigned)(32 % p.Bmod);
         for (int j = warp; j < N; j += kWarps) {
             T sp = T(0), sq = T(0);
             unsigned gi = grow;
@@ -913,12 +915,12 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
     __syncthreads();
     if (p.vecs) for (int i = tid; i < N; i += kThreads) { p.vecs[(b * 2) * N + i] = pv[i]; p.vecs[(b * 2 + 1) * N + i] = qv[i]; }
     // d_covmat_sqrt = gamma_ * (-2) (p w' + q d'): one warp per row, 16-byte stores when rows are aligned
-    T *dC = p.d_C + gflat0;
+    T *dC = p.d_C + b * (long long)N * N;
     if ((N & 3) == 0) {
         // gamma index of (row j, column 4*lane): one 64-bit modulo per thread, then incremental
-        unsigned grow = (unsigned)((gflat0 + (long long)warp * N + 4 * lane) % p.B);
-        const unsigned growstep = (unsigned)(((long long)kWarps * N) % p.B);
-        const unsigned gstep = (unsigned)(128 % p.B);
+        unsigned grow = (unsigned)((gflat0 + (long long)warp * N + 4 * lane) % p.Bmod);
+        const unsigned growstep = (unsigned)(((long long)kWarps * N) % p.Bmod);
+        const unsigned gstep = (unsigned)(128 % p.Bmod);
         const bool gvec = (uB & 3u) == 0u;
         for (int j = warp; j < N; j += kWarps) {
             const T pj = T(-2) * pv[j], qj = T(-2) * qv[j];
@@ -941,8 +943,8 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
         const int total = N * N;
         int j = tid / N, k = tid - j * N;
         const int dj = kThreads / N, dkk = kThreads % N;
-        unsigned gi = (unsigned)((gflat0 + tid) % p.B);
-        const unsigned gstep = (unsigned)(kThreads % p.B);
+        unsigned gi = (unsigned)((gflat0 + tid) % p.Bmod);
+        const unsigned gstep = (unsigned)(kThreads % p.Bmod);
         for (int e = tid; e < total; e += kThreads) {
             dC[e] = p.gamma[gi] * T(-2) * fma(pv[j], wv[k], qv[j] * dv[k]);
             k += dkk; j += dj;
@@ -952,73 +954,51 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
     }
 }
 
-// d_gamma[m] = sum over flat = q B + m of covmat_sqrt[flat] * dA[flat]   (backward of the tiling)
-// grid: (ceil(B / 128), nsplit); each thread owns one m and a slice of q; partial sums via atomics.
-template <typename T>
+// d_gamma[m] += sum over the launch's elements with (flat % Bmod) == m of covmat_sqrt[flat] * dA[flat]
+// (backward of the tiling).  `flat` counts from the first problem of the whole batch; this launch holds the
+// `total` = B N^2 elements that start at flat = b0 N^2, so its local element f sits in bin (f + off) % Bmod with
+// off = (b0 N^2) % Bmod.  grid: (ceil(bins / 128), nsplit); each thread owns kV neighbouring bins and a slice of
+// q (local f = first + q Bmod); partial sums via atomics.  kV = 4 uses 128-bit loads and needs Bmod % 4 == 0
+// and N % 4 == 0 (then off % 4 == 0 and the four elements f .. f+3 sit in one row of one problem).
+template <typename T, int kV>
 __global__ void __launch_bounds__(128) markowitz_gamma_kernel(const T *__restrict__ C, const T *__restrict__ w,
                                                               const T *__restrict__ d, const T *__restrict__ vecs,
-                                                              long long B, int N, int q_per_split, T *d_gamma) {
-    const long long m = (long long)blockIdx.x * 128 + threadIdx.x;
-    if (m >= B) return;
+                                                              long long total, long long Bmod, long long off, int N,
+                                                              int q_per_split, T *d_gamma) {
+    const long long m = kV * ((long long)blockIdx.x * 128 + threadIdx.x);
+    if (m >= Bmod) return;
     const long long NN = (long long)N * N;
+    long long first = m - off;
+    if (first < 0) first += Bmod;
     const long long q0 = (long long)blockIdx.y * q_per_split;
-    const long long q1 = min(q0 + q_per_split, NN);
-    if (q0 >= q1) return;
-    // flat = q B + m walks with stride B; keep (b, j, k) incrementally instead of dividing per element
-    const long long flat0 = q0 * B + m;
+    const long long flat0 = first + q0 * Bmod;
+    if (flat0 >= total) return;
     long long b = flat0 / NN;
     int rem = (int)(flat0 - b * NN);
     int j = rem / N, k = rem - j * N;
-    const long long Bq = B / NN;
-    const int Br = (int)(B - Bq * NN), Brj = Br / N, Brk = Br - Brj * N;
+    const long long Bq = Bmod / NN;
+    const int Br = (int)(Bmod - Bq * NN), Brj = Br / N, Brk = Br - Brj * N;
     const int NNi = (int)NN;
-    T acc = T(0);
-    long long flat = flat0;
-#pragma unroll 8
-    for (long long q = q0; q < q1; ++q) {
-        const T pj = vecs[(b * 2) * N + j], qj = vecs[(b * 2 + 1) * N + j];
-        const T dA = T(-2) * fma(pj, w[b * N + k], qj * d[b * N + k]);
-        acc = fma(C[flat], dA, acc);
-        flat += B; b += Bq; rem += Br; j += Brj; k += Brk;
-        if (k >= N) { k -= N; ++j; }
-        if (rem >= NNi) { rem -= NNi; j -= N; ++b; }
-    }
-    atomicAdd(d_gamma + m, acc);
-}
-
-// Same reduction, four neighbouring bins per thread with 128-bit loads (needs B % 4 == 0 and N % 4 == 0,
-// then the four elements flat .. flat+3 sit in one row of one problem).
-template <typename T>
-__global__ void __launch_bounds__(128) markowitz_gamma_kernel4(const T *__restrict__ C, const T *__restrict__ w,
-                                                               const T *__restrict__ d, const T *__restrict__ vecs,
-                                                               long long B, int N, int q_per_split, T *d_gamma) {
-    const long long m = 4 * ((long long)blockIdx.x * 128 + threadIdx.x);
-    if (m >= B) return;
-    const long long NN = (long long)N * N;
-    const long long q0 = (long long)blockIdx.y * q_per_split;
-    const long long q1 = min(q0 + q_per_split, NN);
-    if (q0 >= q1) return;
-    const long long flat0 = q0 * B + m;
-    long long b = flat0 / NN;
-    int rem = (int)(flat0 - b * NN);
-    int j = rem / N, k = rem - j * N;
-    const long long Bq = B / NN;
-    const int Br = (int)(B - Bq * NN), Brj = Br / N, Brk = Br - Brj * N;
-    const int NNi = (int)NN;
-    T acc[4] = {T(0), T(0), T(0), T(0)};
+    T acc[kV];
+#pragma unroll
+    for (int x = 0; x < kV; ++x) acc[x] = T(0);
     long long flat = flat0;
 #pragma unroll 4
-    for (long long q = q0; q < q1; ++q) {
+    for (int q = 0; q < q_per_split && flat < total; ++q) {
         const T pj = T(-2) * vecs[(b * 2) * N + j], qj = T(-2) * vecs[(b * 2 + 1) * N + j];
-        const Vec4<T> c4 = ld4(C + flat), w4 = ld4(w + b * N + k), d4 = ld4(d + b * N + k);
+        if (kV == 4) {
+            const Vec4<T> c4 = ld4(C + flat), w4 = ld4(w + b * N + k), d4 = ld4(d + b * N + k);
 #pragma unroll
-        for (int x = 0; x < 4; ++x) acc[x] = fma(c4.v[x], fma(pj, w4.v[x], qj * d4.v[x]), acc[x]);
-        flat += B; b += Bq; rem += Br; j += Brj; k += Brk;
+            for (int x = 0; x < kV; ++x) acc[x] = fma(c4.v[x], fma(pj, w4.v[x], qj * d4.v[x]), acc[x]);
+        } else {
+            acc[0] = fma(C[flat], fma(pj, w[b * N + k], qj * d[b * N + k]), acc[0]);
+        }
+        flat += Bmod; b += Bq; rem += Br; j += Brj; k += Brk;
         if (k >= N) { k -= N; ++j; }
         if (rem >= NNi) { rem -= NNi; j -= N; ++b; }
     }
 #pragma unroll
-    for (int x = 0; x < 4; ++x) atomicAdd(d_gamma + m + x, acc[x]);
+    for (int x = 0; x < kV; ++x) atomicAdd(d_gamma + m + x, acc[x]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1152,7 +1132,8 @@ static int launch_fwd_variant(MkFwdParams<T> p, const MkPlan &pl, T *ipm_ws, boo
 
 template <typename T>
 int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const void *alpha, double u, long long B,
-                    int N, void *w, int8_t *state, int32_t *status, void *ws, size_t ws_bytes, cudaStream_t st) {
+                    int N, void *w, int8_t *state, int32_t *status, void *ws, size_t ws_bytes, cudaStream_t st,
+                    long long Bmod, long long b0) {
     if (ws_bytes < markowitz_workspace_bytes(B, N, sizeof(T)) || !ws) {
         set_error("ddw_markowitz_fwd: workspace too small (%zu < %zu)", ws_bytes, markowitz_workspace_bytes(B, N, sizeof(T)));
         return DDW_ERR_WORKSPACE;
@@ -1162,7 +1143,7 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
     WsLayout<T> l = ws_layout<T>(ws, B, N);
     MkFwdParams<T> p;
     p.rets = (const T *)rets; p.C = (const T *)C; p.gamma = (const T *)gamma; p.alpha = (const T *)alpha;
-    p.u = (T)u; p.B = B; p.N = N; p.LD = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
+    p.u = (T)u; p.B = B; p.Bmod = Bmod; p.b0 = b0; p.N = N; p.LD = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
     p.w = (T *)w; p.state = state; p.status = status; p.ws = l.q;
     p.fail_count = l.fail_count; p.fail_list = l.fail_list;
     p.work_count = l.work_count; p.work_list = l.work_list; p.bad_count = l.bad_count;
@@ -1188,8 +1169,12 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
 template <typename T, int kThreads, int NREG, bool kGlobal>
 static int launch_bwd_variant(const MkBwdParams<T> &p, const MkPlan &pl, cudaStream_t st) {
     auto kb = markowitz_bwd_kernel<T, kThreads, NREG, kGlobal>;
-    if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
-        return check_launch("cudaFuncSetAttribute(markowitz_bwd)");
+    static bool configured = false;   // per template instance; opt in to the device maximum once
+    if (!configured) {
+        if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(markowitz_bwd)");
+        configured = true;
+    }
     kb<<<(unsigned)p.B, kThreads, pl.smem, st>>>(p);
     return check_launch("markowitz_bwd_kernel");
 }
@@ -1197,7 +1182,7 @@ static int launch_bwd_variant(const MkBwdParams<T> &p, const MkPlan &pl, cudaStr
 template <typename T>
 int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, const void *C, const void *gamma,
                     const void *alpha, long long B, int N, void *d_rets, void *d_C, void *d_gamma, void *d_alpha,
-                    void *ws, size_t ws_bytes, cudaStream_t st) {
+                    void *ws, size_t ws_bytes, cudaStream_t st, long long Bmod, long long b0, int accumulate_gamma) {
     if (ws_bytes < markowitz_workspace_bytes(B, N, sizeof(T)) || !ws) {
         set_error("ddw_markowitz_bwd: workspace too small (%zu < %zu)", ws_bytes, markowitz_workspace_bytes(B, N, sizeof(T)));
         return DDW_ERR_WORKSPACE;
@@ -1207,7 +1192,7 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
     WsLayout<T> l = ws_layout<T>(ws, B, N);
     MkBwdParams<T> p;
     p.grad_w = (const T *)grad_w; p.w = (const T *)w; p.C = (const T *)C; p.gamma = (const T *)gamma;
-    p.alpha = (const T *)alpha; p.state = state; p.B = B; p.N = N; p.LDW = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
+    p.alpha = (const T *)alpha; p.state = state; p.B = B; p.Bmod = Bmod; p.b0 = b0; p.N = N; p.LDW = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
     p.d_rets = (T *)d_rets; p.d_C = (T *)d_C; p.d_alpha = (T *)d_alpha; p.vecs = d_gamma ? l.vecs : nullptr; p.ws = l.q;
     int rc;
     if (!pl.global_q && pl.threads == 128) rc = launch_bwd_variant<T, 128, 4, false>(p, pl, st);
@@ -1217,21 +1202,22 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
     else if (pl.nreg == 16) rc = launch_bwd_variant<T, 512, 16, true>(p, pl, st);
     else rc = launch_bwd_variant<T, 512, 32, true>(p, pl, st);
     if (rc || !d_gamma) return rc;
-    cudaMemsetAsync(d_gamma, 0, sizeof(T) * (size_t)B, st);
-    const long long NN = (long long)N * N;
-    const bool vec4 = (B % 4 == 0) && (N % 4 == 0);
-    const long long cols = vec4 ? B / 4 : B;   // threads along the bin dimension
+    if (!accumulate_gamma) cudaMemsetAsync(d_gamma, 0, sizeof(T) * (size_t)Bmod, st);
+    const long long NN = (long long)N * N, total = B * NN, off = (b0 * NN) % Bmod;
+    const bool vec4 = (Bmod % 4 == 0) && (N % 4 == 0);
+    const long long cols = vec4 ? Bmod / 4 : Bmod;   // threads along the bin dimension
+    const long long qn = (total + Bmod - 1) / Bmod;  // elements per bin (upper bound)
     // enough slices to fill the machine, few enough that atomics stay negligible
-    long long nsplit = max(1LL, min(min(NN, 65535LL), (148LL * 16 * 128 + cols - 1) / cols));
-    const int q_per = (int)((NN + nsplit - 1) / nsplit);
-    nsplit = (NN + q_per - 1) / q_per;
+    long long nsplit = max(1LL, min(min(qn, 65535LL), (148LL * 16 * 128 + cols - 1) / cols));
+    const int q_per = (int)((qn + nsplit - 1) / nsplit);
+    nsplit = (qn + q_per - 1) / q_per;
     dim3 grid((unsigned)((cols + 127) / 128), (unsigned)nsplit);
     if (vec4)
-        markowitz_gamma_kernel4<T><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, l.vecs, B, N,
-                                                         q_per, (T *)d_gamma);
+        markowitz_gamma_kernel<T, 4><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, l.vecs, total,
+                                                           Bmod, off, N, q_per, (T *)d_gamma);
     else
-        markowitz_gamma_kernel<T><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, l.vecs, B, N,
-                                                        q_per, (T *)d_gamma);
+        markowitz_gamma_kernel<T, 1><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, l.vecs, total,
+                                                           Bmod, off, N, q_per, (T *)d_gamma);
     return check_launch("markowitz_gamma_kernel");
 }
 

@@ -64,9 +64,9 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
     SpSmem<T> s = sp_carve<T>(smem_raw, N);
     T *As = s.As, *Qc = s.Qc, *Lb = s.Qc + 1;
     const T *Cb = p.C + b * (long long)N * N;
-    const long long gflat0 = b * (long long)N * N;
+    const long long gflat0 = (p.b0 + b) * (long long)N * N;
     const unsigned bytes = (unsigned)(N * N * sizeof(T));
-    const unsigned uB = (unsigned)p.B;
+    const unsigned uB = (unsigned)p.Bmod;
 
     // ---- A -> shared memory: one bulk TMA copy (40 KB at N = 100), completion on an mbarrier
     const bool use_tma = (bytes & 15u) == 0u && (reinterpret_cast<unsigned long long>(Cb) & 15ull) == 0ull;
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
     // ---- gamma tiling (allocate.py:268-270), in place; every thread touches the elements it will not
     // need before the next barrier
     if ((N & 3) == 0 && (uB & 3u) == 0u) {
-        unsigned gi = (unsigned)((gflat0 + 4 * tid) % p.B);
-        const unsigned gstep = (unsigned)((4 * kThreads) % p.B);
+        unsigned gi = (unsigned)((gflat0 + 4 * tid) % p.Bmod);
+        const unsigned gstep = (unsigned)((4 * kThreads) % p.Bmod);
         for (int e = 4 * tid; e < N * N; e += 4 * kThreads) {
             Vec4<T> a = ld4(As + e);
             const Vec4<T> g4 = ld4(p.gamma + gi);
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
             gi += gstep; if (gi >= uB) gi -= uB;
         }
     } else {
-        unsigned gi = (unsigned)((gflat0 + tid) % p.B);
-        const unsigned gstep = (unsigned)(kThreads % p.B);
+        unsigned gi = (unsigned)((gflat0 + tid) % p.Bmod);
+        const unsigned gstep = (unsigned)(kThreads % p.Bmod);
         for (int e = tid; e < N * N; e += kThreads) {
             As[e] *= p.gamma[gi];
             gi += gstep; if (gi >= uB) gi -= uB;

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DDW_VERSION 100
+#define DDW_VERSION 101
 
 enum ddw_dtype { DDW_F32 = 0, DDW_F64 = 1 };
 
@@ -85,6 +85,52 @@ int ddw_markowitz_bwd(const void *grad_w, const void *w, const int8_t *state,
                       double max_weight, int64_t B, int64_t N, int dtype,
                       void *d_rets, void *d_covmat_sqrt, void *d_gamma_sqrt, void *d_alpha,
                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Chunked launches of the two calls above: the same kernels on the `B` consecutive problems that start at
+ * index `batch_offset` of a batch of `batch_total` problems.  Every pointer addresses the chunk's first
+ * problem EXCEPT gamma_sqrt / d_gamma_sqrt, which address the whole batch's (batch_total) arrays: the
+ * reference's repeat/view tiling (allocate.py:268-270) indexes gamma_sqrt by the flat element index of the
+ * whole batch modulo batch_total.  With accumulate_gamma != 0 the chunk's contribution is added to
+ * d_gamma_sqrt (the caller zeroes it once per batch) instead of overwriting it.
+ * ddw_markowitz_fwd(B) == ddw_markowitz_fwd_chunk(B, batch_total = B, batch_offset = 0). */
+int ddw_markowitz_fwd_chunk(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                            double max_weight, int64_t B, int64_t N, int dtype, int64_t batch_total, int64_t batch_offset,
+                            void *w, int8_t *state, int32_t *status,
+                            void *workspace, size_t workspace_bytes, void *stream);
+int ddw_markowitz_bwd_chunk(const void *grad_w, const void *w, const int8_t *state,
+                            const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                            double max_weight, int64_t B, int64_t N, int dtype, int64_t batch_total, int64_t batch_offset,
+                            void *d_rets, void *d_covmat_sqrt, void *d_gamma_sqrt, int accumulate_gamma, void *d_alpha,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HOST-buffer entry point: what a CPU-resident caller of the reference layer binds.  The reference takes
+ * CPU tensors, solves on host threads and returns CPU tensors (allocate.py:273); here the batch is streamed
+ * through the GPU in chunks of `chunk` problems on three streams (host->device copies, solver kernels,
+ * device->host copies), so the PCIe transfers in both directions overlap each other and the kernels.
+ * All h_* pointers are HOST memory (page-locked for asynchronous copies; pageable memory works but
+ * serialises); dev_scratch is DEVICE memory of ddw_markowitz_host_scratch_bytes() bytes owned by the caller.
+ *   forward + backward : h_grad_w != NULL; writes h_w, h_status, h_d_rets, h_d_covmat_sqrt, h_d_alpha and
+ *                        (if non-NULL) h_d_gamma_sqrt
+ *   forward only       : h_grad_w == NULL; writes h_w, h_status (the h_d_* pointers are ignored)
+ * Work is ordered after everything already enqueued on `stream` and `stream` is made to wait for the last
+ * copy, so the call is asynchronous like the device entry points: synchronise `stream` (or record an event
+ * on it) before reading the host outputs.  A pipeline handle owns three streams and their events, nothing else.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ddw_host_pipeline ddw_host_pipeline;
+int ddw_host_pipeline_create(ddw_host_pipeline **out);
+void ddw_host_pipeline_destroy(ddw_host_pipeline *pipe);
+/* number of steps this handle served by replaying its cached CUDA graph: a step requested twice in a row with
+ * identical arguments and page-locked host buffers is captured once and replayed with one launch afterwards */
+int ddw_host_pipeline_graph_launches(const ddw_host_pipeline *pipe);
+size_t ddw_markowitz_host_scratch_bytes(int64_t B, int64_t N, int dtype, int64_t chunk);
+int ddw_markowitz_host_step(ddw_host_pipeline *pipe,
+                            const void *h_rets, const void *h_covmat_sqrt, const void *h_gamma_sqrt,
+                            const void *h_alpha, const void *h_grad_w,
+                            double max_weight, int64_t B, int64_t N, int dtype, int64_t chunk,
+                            void *h_w, int32_t *h_status,
+                            void *h_d_rets, void *h_d_covmat_sqrt, void *h_d_gamma_sqrt, void *h_d_alpha,
+                            void *dev_scratch, size_t dev_scratch_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SparsemaxAllocator -- replaces self.layer(x / temperature[:, None])[0] (allocate.py:586-595):

@@ -1,0 +1,115 @@
+"""GPU parity of the chunked C-ABI entry points and of the host-buffer pipeline
+(ddw_markowitz_fwd_chunk / ddw_markowitz_bwd_chunk / ddw_markowitz_host_step, include/ddw.h):
+a batch solved in chunks, or streamed from host buffers, must give bit-identical weights and the same
+gradients as the one-launch device path, including the reference's gamma tiling
+(deepdow/layers/allocate.py:268-270), which indexes gamma_sqrt by the flat element index of the WHOLE batch.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from deepdow_b200 import NumericalMarkowitz, SolverError, _C
+from deepdow_b200.host import MarkowitzHostPipeline
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def problems(B, N, seed, gamma="rand", dtype=np.float32):
+    rng = np.random.default_rng(seed)
+    R = rng.standard_normal((B, N, N))
+    C = R @ R.transpose(0, 2, 1) / N + 0.1 * np.eye(N)
+    rets = rng.standard_normal((B, N)) * 0.5
+    g = rng.uniform(0.5, 2.0, B) if gamma == "rand" else np.ones(B)
+    a = rng.uniform(0.5, 1.5, B) * rng.choice([-1.0, 1.0], B)
+    G = rng.standard_normal((B, N))
+    return [x.astype(dtype) for x in (rets, C, g, a, G)]
+
+
+def device_reference(rets, C, g, a, G, u):
+    tt = [torch.tensor(x, device=DEV, requires_grad=True) for x in (rets, C, g, a)]
+    w = NumericalMarkowitz(rets.shape[1], u)(*tt)
+    grads = torch.autograd.grad(w, tt, torch.tensor(G, device=DEV))
+    return [w.detach().cpu()] + [x.cpu() for x in grads]
+
+
+@pytest.mark.parametrize("B,N,u,chunk", [(96, 20, 0.3, 32), (70, 12, 1.0, 32), (50, 100, 0.2, 16), (33, 7, 0.5, 4)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_chunked_abi_matches_one_launch(B, N, u, chunk, dtype):
+    rets, C, g, a, G = problems(B, N, 100 + B + N, dtype=dtype)
+    ref = device_reference(rets, C, g, a, G, u)
+    lib = _C.lib()
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    d = lambda x: torch.tensor(x, device=DEV)
+    trets, tC, tg, ta, tG = d(rets), d(C), d(g), d(a), d(G)
+    dt = _C.dtype_code(trets)
+    w = torch.empty(B, N, dtype=tdt, device=DEV)
+    state = torch.empty(B, N, dtype=torch.int8, device=DEV)
+    status = torch.empty(B, dtype=torch.int32, device=DEV)
+    d_rets, d_C, d_g, d_a = torch.empty_like(trets), torch.empty_like(tC), torch.zeros_like(tg), torch.empty_like(ta)
+    for b0 in range(0, B, chunk):
+        c = min(chunk, B - b0)
+        ws = torch.empty(lib.ddw_markowitz_workspace_bytes(c, N, dt), dtype=torch.uint8, device=DEV)
+        sl = slice(b0, b0 + c)
+        rc = lib.ddw_markowitz_fwd_chunk(_C.ptr(trets[sl]), _C.ptr(tC[sl]), _C.ptr(tg), _C.ptr(ta[sl]), u, c, N, dt, B, b0,
+                                         _C.ptr(w[sl]), _C.ptr(state[sl]), _C.ptr(status[sl]), _C.ptr(ws), ws.numel(),
+                                         _C.stream())
+        _C.check(rc, "fwd_chunk")
+        rc = lib.ddw_markowitz_bwd_chunk(_C.ptr(tG[sl]), _C.ptr(w[sl]), _C.ptr(state[sl]), _C.ptr(tC[sl]), _C.ptr(tg),
+                                         _C.ptr(ta[sl]), u, c, N, dt, B, b0, _C.ptr(d_rets[sl]), _C.ptr(d_C[sl]),
+                                         _C.ptr(d_g), 1, _C.ptr(d_a[sl]), _C.ptr(ws), ws.numel(), _C.stream())
+        _C.check(rc, "bwd_chunk")
+    torch.cuda.synchronize()
+    # the chunk sizes above are multiples of 4 so that every slice passed to the ABI stays 16-byte aligned
+    assert torch.equal(w.cpu(), ref[0])
+    assert torch.equal(d_rets.cpu(), ref[1])
+    assert torch.equal(d_C.cpu(), ref[2])
+    assert torch.equal(d_a.cpu(), ref[4])
+    tol = 1e-5 if dtype == np.float32 else 1e-12
+    assert (d_g.cpu() - ref[3]).abs().max() <= tol * max(1.0, float(ref[3].abs().max()))   # atomics: order differs
+
+
+@pytest.mark.parametrize("B,N,u,chunk", [(100, 20, 0.3, 32), (64, 100, 0.2, 16), (20, 12, 1.0, 64), (45, 8, 0.5, 7)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_host_pipeline_matches_device_path_and_oracle(B, N, u, chunk, dtype):
+    rets, C, g, a, G = problems(B, N, 7 * B + N, dtype=dtype)
+    ref = device_reference(rets, C, g, a, G, u)
+    pipe = MarkowitzHostPipeline(N, u, chunk=chunk, device=DEV)
+    host = [torch.tensor(x).pin_memory() for x in (rets, C, g, a, G)]
+    out = pipe.step(*host)
+    assert torch.equal(out.w, ref[0]) and int(out.status.ne(0).sum()) == 0
+    out = pipe.step(*host[:4])                      # forward only
+    assert torch.equal(out.w, ref[0]) and out.d_rets is None
+    out = None
+    for _ in range(3):                              # repeated steps recycle slots and output buffers
+        out = pipe.step(*host, out=out)
+    assert pipe.graph_launches >= 2                 # same buffers again: captured once, then replayed
+    assert torch.equal(out.w, ref[0])
+    assert torch.equal(out.d_rets, ref[1]) and torch.equal(out.d_covmat_sqrt, ref[2]) and torch.equal(out.d_alpha, ref[4])
+    tol = 1e-5 if dtype == np.float32 else 1e-12
+    assert (out.d_gamma_sqrt - ref[3]).abs().max() <= tol * max(1.0, float(ref[3].abs().max()))
+    # and against the CPU oracle
+    w_ref, st_ref, kkt, _ = oracle.markowitz_fwd(rets, C, g, a, u)
+    d_ref = oracle.markowitz_bwd(G, w_ref, st_ref, C, g, a, u)
+    wtol, gtol = (1e-5, 1e-4) if dtype == np.float32 else (1e-9, 1e-8)
+    assert np.abs(out.w.double().numpy() - w_ref).max() < wtol
+    for got, want in zip(out[1:5], d_ref):
+        assert np.abs(got.double().numpy() - want).max() <= gtol * max(np.abs(want).max(), 1e-30)
+    pipe.close()
+
+
+def test_host_pipeline_errors():
+    pipe = MarkowitzHostPipeline(10, 0.05, device=DEV)
+    z = torch.zeros
+    with pytest.raises(SolverError):
+        pipe.step(z(4, 10), z(4, 10, 10), z(4), z(4))
+    pipe = MarkowitzHostPipeline(10, 0.5, device=DEV)
+    with pytest.raises(ValueError):
+        pipe.step(z(4, 9), z(4, 9, 9), z(4), z(4))
+    with pytest.raises(ValueError):
+        pipe.step(z(4, 10, device=DEV), z(4, 10, 10), z(4), z(4))
+    # pageable (non-pinned) host memory is accepted
+    rets, C, g, a, G = problems(8, 10, 3)
+    out = pipe.step(*[torch.tensor(x) for x in (rets, C, g, a, G)])
+    assert abs(float(out.w.sum()) - 8.0) < 1e-4

@@ -152,7 +152,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunk", type=int, default=256, help="problems per stage of the host-buffer pipeline (e2e)")
+    ap.add_argument("--chunk", type=int, default=128, help="problems per stage of the host-buffer pipeline (e2e)")
     ap.add_argument("--status-mode", default="lazy", choices=["lazy", "sync", "off"],
                     help="NumericalMarkowitz.check_status: lazy (default of the layer), sync (read the failure "
                          "counter inside every forward: a host sync) or off (diagnostic)")
@@ -215,6 +215,7 @@ def main():
         nfree = float(((w0 > 0) & (w0 < u)).sum(1).float().mean())
         ncap = float((w0 >= u).sum(1).float().mean())
         nfallback = int((layer.last_status & 1).ne(0).sum())
+        ndense = layer.solver_counters()[1]
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
@@ -321,7 +322,8 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world} (independent problems, no collective)",
                        "l2": "inputs (164 MB covmat_sqrt) + gradients (164 MB) per step exceed the 126 MB L2",
                        "status_check": args.status_mode,
-                       "active_set": {"mean_free": nfree, "mean_at_cap": ncap, "fallback_problems": nfallback}},
+                       "active_set": {"mean_free": nfree, "mean_at_cap": ncap, "fallback_problems": nfallback,
+                                      "dense_kernel_problems": ndense}},
             "e2e": {"value": world * B * steps_total / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / steps_total,
@@ -329,13 +331,13 @@ def main():
                            f"{args.chunk} problems on H2D / kernel / D2H streams)",
                     "layer_api_unpipelined": {"value": world * B * steps_total / (e2e_layer_ms * 1e-3),
                                               "ms_per_step": e2e_layer_ms / steps_total}},
-            "gpu_launches": 5 * steps_total,
-            "kernels_per_step": ["markowitz_fwd_sparse_kernel", "markowitz_fwd_kernel (dense work list, empty here)",
-                                 "markowitz_ipm_kernel (fallback list, empty here)", "markowitz_bwd_kernel",
-                                 "markowitz_gamma_kernel4"],
+            "gpu_launches": 6 * steps_total,
+            "kernels_per_step": ["markowitz_fwd_sparse_kernel", "markowitz_fwd_kernel (dense work list)",
+                                 "markowitz_ipm_kernel (fallback list, empty here)", "markowitz_bwd_sparse_kernel",
+                                 "markowitz_bwd_kernel (dense work list)", "markowitz_gamma_kernel"],
             "fwd_only": {"value": world * B * steps_total / (fwd_only_ms * 1e-3), "unit": UNIT},
             "phase_ms": {"fwd": fwd_ms, "bwd": bwd_ms, "host_enqueue": cpu_enqueue_ms},
-            "roofline": {"bound": "hbm", "kernel": "markowitz_fwd_sparse_kernel" if dom_fwd else "markowitz_bwd_kernel",
+            "roofline": {"bound": "hbm", "kernel": "markowitz_fwd_sparse_kernel" if dom_fwd else "markowitz_bwd_sparse_kernel",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": fwd_bytes if dom_fwd else bwd_bytes,

@@ -103,5 +103,15 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def stream(device=None):
+    """cudaStream_t of torch's current stream on `device` (default: the current device) as a c_void_p.
+
+    ``torch.cuda.current_stream()`` builds a Python Stream object (about 20 us per call, measured with
+    tools/host_profile.py); the raw accessor is the same lookup without the object."""
+    if _raw_stream is not None:
+        index = torch.cuda.current_device() if device is None else torch.device(device).index
+        return ctypes.c_void_p(_raw_stream(index if index is not None else torch.cuda.current_device()))
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

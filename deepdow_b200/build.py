@@ -10,10 +10,13 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "libddw_b200.so")
-SOURCES = ["api.cu", "markowitz_fwd_f32.cu", "markowitz_fwd_f64.cu", "markowitz_bwd_f32.cu", "markowitz_bwd_f64.cu",
+SOURCES = ["api.cu", "markowitz_fwd_sparse_f32.cu", "markowitz_fwd_sparse_f64.cu", "markowitz_bwd_sparse_f32.cu",
+           "markowitz_bwd_sparse_f64.cu", "markowitz_fwd_f32.cu", "markowitz_fwd_f64.cu", "markowitz_bwd_f32.cu", "markowitz_bwd_f64.cu",
            "rowproj.cu", "covariance.cu", "host_pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
+if os.environ.get("DDW_PHASE_TIMING"):      # debug build: per-phase cycle counters in the sparse kernels
+    NVCC_FLAGS.append("-DDDW_PHASE_TIMING")
 
 
 def _nvcc():
@@ -30,10 +33,24 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _deps(path, seen=None):
+    """The source and every header it includes (recursively, quoted includes only)."""
+    import re
+    seen = set() if seen is None else seen
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', open(path).read(), flags=re.M):
+        for d in (os.path.dirname(path), CSRC, INCLUDE):
+            cand = os.path.join(d, inc)
+            if os.path.exists(cand):
+                _deps(cand, seen)
+                break
+    return seen
+
+
 def build(force=False, verbose=False):
-    """Compile every .cu to an object (in parallel) and link the shared library."""
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    headers.append(os.path.join(INCLUDE, "ddw.h"))
+    """Compile every .cu to an object (in parallel, only those whose own includes changed) and link the shared library."""
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
@@ -43,11 +60,11 @@ def build(force=False, verbose=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
-        if force or _stale(o, [s] + headers):
+        if force or _stale(o, sorted(_deps(s))):
             extra = ["-Xptxas", "-v"] if verbose else []
             jobs.append([nvcc] + NVCC_FLAGS + extra + ["-c", s, "-o", o])
     if jobs:
-        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             results = list(ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs))
         for cmd, r in zip(jobs, results):
             if verbose or r.returncode != 0:

@@ -63,6 +63,9 @@ template <typename T, int kThreads> __device__ __forceinline__ T block_sum(T v, 
 template <typename T> __device__ __forceinline__ T clampT(T v, T lo, T hi) { return v < lo ? lo : (v > hi ? hi : v); }
 template <typename T> __device__ __forceinline__ T absT(T v) { return v < 0 ? -v : v; }
 
+// correctly rounded reciprocal: one MUFU.RCP plus a fix-up for float instead of the generic division sequence
+__device__ __forceinline__ float recipT(float v) { return __frcp_rn(v); }
+__device__ __forceinline__ double recipT(double v) { return 1.0 / v; }
 __device__ __forceinline__ float rsqrtT(float v) { return rsqrtf(v); }
 __device__ __forceinline__ double rsqrtT(double v) { return rsqrt(v); }
 __device__ __forceinline__ float sqrtT(float v) { return sqrtf(v); }

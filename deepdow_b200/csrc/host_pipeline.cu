@@ -5,7 +5,7 @@
 // host -> device -> host around the solver kernels.  Done naively that is three serial phases (copy in, solve,
 // copy out) and PCIe, not the GPU, sets the pace: at B = 4096, N = 100 the step moves 167 MB each way.
 // Here the (B,N,N) tensors -- 98% of the bytes -- are cut into chunks that flow through three streams
-//     s_in : H2D of chunk i+1      s_run : forward + backward of chunk i      s_out : D2H of chunk i-1
+//     s_in : H2D of chunk i+1      s_run[i % 2] : forward + backward of chunk i      s_out : D2H of chunk i-1
 // so that both PCIe directions and the kernels run at the same time; the small per-problem vectors travel once
 // per batch.  Chunk slots live in caller-owned device scratch and are recycled round-robin, guarded by events.
 //
@@ -14,6 +14,8 @@
 // cross-stream dependencies -- is therefore captured into a CUDA graph the second time it is requested with the
 // same arguments and replayed with a single launch from then on.  Capture needs page-locked host buffers;
 // pageable ones take the eager path.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ddw {
@@ -26,7 +28,8 @@ template <typename T>
 int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, const void *, const void *, long long,
                     int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int);
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;     // chunk slots in the device scratch
+constexpr int kRun = 2;       // solver streams: consecutive chunks are solved concurrently (a chunk alone cannot fill the GPU)
 
 static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -86,8 +89,8 @@ struct StepArgs {
 using namespace ddw;
 
 struct ddw_host_pipeline {
-    cudaStream_t s_in, s_run, s_out, s_origin;
-    cudaEvent_t start, in_done[kSlots], run_done[kSlots], out_done[kSlots], head_in, tail_in, tail_run, tail_out;
+    cudaStream_t s_in, s_run[kRun], s_out, s_origin;
+    cudaEvent_t start, in_done[kSlots], run_done[kSlots], out_done[kSlots], head_in, head_run, tail_in, tail_run[kRun], tail_out;
     // graph cache: the last argument set seen, and its instantiated graph once it has been seen twice
     StepArgs last;
     bool have_last;
@@ -116,7 +119,7 @@ static int enqueue_step(ddw_host_pipeline *pipe, const StepArgs &a, cudaStream_t
 
     cudaEventRecord(pipe->start, origin);
     cudaStreamWaitEvent(pipe->s_in, pipe->start, 0);
-    cudaStreamWaitEvent(pipe->s_run, pipe->start, 0);
+    for (int r = 0; r < kRun; ++r) cudaStreamWaitEvent(pipe->s_run[r], pipe->start, 0);
     cudaStreamWaitEvent(pipe->s_out, pipe->start, 0);
 
     // per-problem vectors of the whole batch: 2% of the bytes, one copy each
@@ -125,13 +128,16 @@ static int enqueue_step(ddw_host_pipeline *pipe, const StepArgs &a, cudaStream_t
     cudaMemcpyAsync(base + L.alpha, a.h_alpha, (size_t)B * ts, cudaMemcpyHostToDevice, pipe->s_in);
     if (bwd) cudaMemcpyAsync(base + L.grad_w, a.h_grad_w, (size_t)B * row, cudaMemcpyHostToDevice, pipe->s_in);
     cudaEventRecord(pipe->head_in, pipe->s_in);
-    cudaStreamWaitEvent(pipe->s_run, pipe->head_in, 0);
-    if (want_dgamma) cudaMemsetAsync(base + L.d_gamma, 0, (size_t)B * ts, pipe->s_run);
+    cudaStreamWaitEvent(pipe->s_run[0], pipe->head_in, 0);
+    if (want_dgamma) cudaMemsetAsync(base + L.d_gamma, 0, (size_t)B * ts, pipe->s_run[0]);
+    cudaEventRecord(pipe->head_run, pipe->s_run[0]);
+    for (int r = 1; r < kRun; ++r) cudaStreamWaitEvent(pipe->s_run[r], pipe->head_run, 0);
 
     int rc = 0, it = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, ++it) {
         const int64_t c = (B - b0 < chunk) ? (B - b0) : chunk;
         const int sl = it % kSlots;
+        cudaStream_t run = pipe->s_run[it % kRun];
         unsigned char *S = base + L.slots + (size_t)sl * L.slot_bytes;
         // the slot is free once its previous tenant has been copied out
         if (it >= kSlots) cudaStreamWaitEvent(pipe->s_in, pipe->out_done[sl], 0);
@@ -139,24 +145,24 @@ static int enqueue_step(ddw_host_pipeline *pipe, const StepArgs &a, cudaStream_t
                         cudaMemcpyHostToDevice, pipe->s_in);
         cudaEventRecord(pipe->in_done[sl], pipe->s_in);
 
-        cudaStreamWaitEvent(pipe->s_run, pipe->in_done[sl], 0);
+        cudaStreamWaitEvent(run, pipe->in_done[sl], 0);
         unsigned char *rets = base + L.rets + b0 * row, *alpha = base + L.alpha + b0 * ts, *w = base + L.w + b0 * row;
         unsigned char *grad_w = base + L.grad_w + b0 * row, *d_rets = base + L.d_rets + b0 * row;
         unsigned char *d_alpha = base + L.d_alpha + b0 * ts;
         int8_t *state = reinterpret_cast<int8_t *>(base + L.state) + b0 * n;
         int32_t *status = reinterpret_cast<int32_t *>(base + L.status) + b0;
         if (a.dtype == DDW_F64)
-            rc = markowitz_fwd_t<double>(rets, S + L.C, base + L.gamma, alpha, a.max_weight, c, n, w, state, status, S + L.ws, L.ws_bytes, pipe->s_run, B, b0);
+            rc = markowitz_fwd_t<double>(rets, S + L.C, base + L.gamma, alpha, a.max_weight, c, n, w, state, status, S + L.ws, L.ws_bytes, run, B, b0);
         else
-            rc = markowitz_fwd_t<float>(rets, S + L.C, base + L.gamma, alpha, a.max_weight, c, n, w, state, status, S + L.ws, L.ws_bytes, pipe->s_run, B, b0);
+            rc = markowitz_fwd_t<float>(rets, S + L.C, base + L.gamma, alpha, a.max_weight, c, n, w, state, status, S + L.ws, L.ws_bytes, run, B, b0);
         if (!rc && bwd) {
             void *dg = want_dgamma ? base + L.d_gamma : nullptr;
             if (a.dtype == DDW_F64)
-                rc = markowitz_bwd_t<double>(grad_w, w, state, S + L.C, base + L.gamma, alpha, c, n, d_rets, S + L.d_C, dg, d_alpha, S + L.ws, L.ws_bytes, pipe->s_run, B, b0, 1);
+                rc = markowitz_bwd_t<double>(grad_w, w, state, S + L.C, base + L.gamma, alpha, c, n, d_rets, S + L.d_C, dg, d_alpha, S + L.ws, L.ws_bytes, run, B, b0, 1);
             else
-                rc = markowitz_bwd_t<float>(grad_w, w, state, S + L.C, base + L.gamma, alpha, c, n, d_rets, S + L.d_C, dg, d_alpha, S + L.ws, L.ws_bytes, pipe->s_run, B, b0, 1);
+                rc = markowitz_bwd_t<float>(grad_w, w, state, S + L.C, base + L.gamma, alpha, c, n, d_rets, S + L.d_C, dg, d_alpha, S + L.ws, L.ws_bytes, run, B, b0, 1);
         }
-        cudaEventRecord(pipe->run_done[sl], pipe->s_run);
+        cudaEventRecord(pipe->run_done[sl], run);
         if (rc) break;
 
         cudaStreamWaitEvent(pipe->s_out, pipe->run_done[sl], 0);
@@ -166,7 +172,8 @@ static int enqueue_step(ddw_host_pipeline *pipe, const StepArgs &a, cudaStream_t
         cudaEventRecord(pipe->out_done[sl], pipe->s_out);
     }
     if (!rc) {
-        // s_out has waited for the last run_done, so every chunk's results are final
+        // s_out waits for the tail of every solver stream, so every chunk's results are final
+        for (int r = 0; r < kRun; ++r) { cudaEventRecord(pipe->tail_run[r], pipe->s_run[r]); cudaStreamWaitEvent(pipe->s_out, pipe->tail_run[r], 0); }
         cudaMemcpyAsync(a.h_w, base + L.w, (size_t)B * row, cudaMemcpyDeviceToHost, pipe->s_out);
         cudaMemcpyAsync(a.h_status, base + L.status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, pipe->s_out);
         if (bwd) {
@@ -177,10 +184,10 @@ static int enqueue_step(ddw_host_pipeline *pipe, const StepArgs &a, cudaStream_t
     }
     // `origin` resumes when all three streams have drained
     cudaEventRecord(pipe->tail_in, pipe->s_in);
-    cudaEventRecord(pipe->tail_run, pipe->s_run);
+    for (int r = 0; r < kRun; ++r) cudaEventRecord(pipe->tail_run[r], pipe->s_run[r]);
     cudaEventRecord(pipe->tail_out, pipe->s_out);
     cudaStreamWaitEvent(origin, pipe->tail_in, 0);
-    cudaStreamWaitEvent(origin, pipe->tail_run, 0);
+    for (int r = 0; r < kRun; ++r) cudaStreamWaitEvent(origin, pipe->tail_run[r], 0);
     cudaStreamWaitEvent(origin, pipe->tail_out, 0);
     return rc;
 }
@@ -194,11 +201,12 @@ int ddw_host_pipeline_create(ddw_host_pipeline **out) {
     ddw_host_pipeline *p = new ddw_host_pipeline();
     p->have_last = false; p->exec = nullptr; p->graph_launches = 0;
     bool ok = cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&p->s_origin, cudaStreamNonBlocking) == cudaSuccess;
+    for (int r = 0; r < kRun; ++r) ok = ok && cudaStreamCreateWithFlags(&p->s_run[r], cudaStreamNonBlocking) == cudaSuccess;
     auto ev = [&](cudaEvent_t *e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
-    ev(&p->start); ev(&p->head_in); ev(&p->tail_in); ev(&p->tail_run); ev(&p->tail_out);
+    ev(&p->start); ev(&p->head_in); ev(&p->head_run); ev(&p->tail_in); ev(&p->tail_out);
+    for (int r = 0; r < kRun; ++r) ev(&p->tail_run[r]);
     for (int i = 0; i < kSlots; ++i) { ev(&p->in_done[i]); ev(&p->run_done[i]); ev(&p->out_done[i]); }
     if (!ok) {
         check_launch("ddw_host_pipeline_create");
@@ -211,13 +219,15 @@ int ddw_host_pipeline_create(ddw_host_pipeline **out) {
 
 void ddw_host_pipeline_destroy(ddw_host_pipeline *p) {
     if (!p) return;
-    cudaStreamSynchronize(p->s_in); cudaStreamSynchronize(p->s_run); cudaStreamSynchronize(p->s_out);
+    cudaStreamSynchronize(p->s_in); cudaStreamSynchronize(p->s_out);
+    for (int r = 0; r < kRun; ++r) cudaStreamSynchronize(p->s_run[r]);
     cudaStreamSynchronize(p->s_origin);
     if (p->exec) cudaGraphExecDestroy(p->exec);
-    cudaEventDestroy(p->start); cudaEventDestroy(p->head_in);
-    cudaEventDestroy(p->tail_in); cudaEventDestroy(p->tail_run); cudaEventDestroy(p->tail_out);
+    cudaEventDestroy(p->start); cudaEventDestroy(p->head_in); cudaEventDestroy(p->head_run);
+    cudaEventDestroy(p->tail_in); cudaEventDestroy(p->tail_out);
+    for (int r = 0; r < kRun; ++r) { cudaEventDestroy(p->tail_run[r]); cudaStreamDestroy(p->s_run[r]); }
     for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(p->in_done[i]); cudaEventDestroy(p->run_done[i]); cudaEventDestroy(p->out_done[i]); }
-    cudaStreamDestroy(p->s_in); cudaStreamDestroy(p->s_run); cudaStreamDestroy(p->s_out); cudaStreamDestroy(p->s_origin);
+    cudaStreamDestroy(p->s_in); cudaStreamDestroy(p->s_out); cudaStreamDestroy(p->s_origin);
     delete p;
 }
 
@@ -251,7 +261,8 @@ int ddw_markowitz_host_step(ddw_host_pipeline *pipe, const void *h_rets, const v
     const StepArgs a = {h_rets, h_covmat_sqrt, h_gamma_sqrt, h_alpha, h_grad_w, max_weight, B, N, chunk, dtype, h_w, h_status,
                         h_d_rets, h_d_covmat_sqrt, h_d_gamma_sqrt, h_d_alpha, dev_scratch, dev_scratch_bytes};
     cudaStream_t user = (cudaStream_t)stream;
-    const bool same = pipe->have_last && pipe->last == a;
+    static const bool no_graph = getenv("DDW_HOST_PIPELINE_NO_GRAPH") != nullptr;   // diagnostic: always enqueue eagerly
+    const bool same = !no_graph && pipe->have_last && pipe->last == a;
     if (same && pipe->exec) {
         ++pipe->graph_launches;
         cudaGraphLaunch(pipe->exec, user);

@@ -15,361 +15,16 @@
 // answer is the exact optimum of the program that SCS only approximates.  Problems on which the
 // active set cycles are handed to a Mehrotra interior-point kernel (same primitives) and polished.
 #pragma once
-#include "common.cuh"
-#include "linalg.cuh"
+#include "markowitz_common.cuh"
+
 
 namespace ddw {
 
-constexpr int kMaxPdas = 24;   // active-set iterations before the fallback is asked for
-constexpr int kMaxIpm = 40;
-
-template <typename T> struct MkFwdParams {
-    const T *rets, *C, *gamma, *alpha;
-    T u;
-    long long B;       // problems in this launch
-    long long Bmod;    // n_samples of the whole batch = modulus of the gamma tiling
-    long long b0;      // index of this launch's first problem in the whole batch
-    int N, LD, AS, CH;
-    T *w;
-    int8_t *state;
-    int32_t *status;
-    T *ws;            // global Q/L storage when the matrix does not fit shared memory
-    int *fail_count;  // [0] = number of problems that need the fallback
-    int *fail_list;   // their indices
-    int *work_count;  // dense kernel in list mode: number of entries of work_list (nullptr: one CTA per problem)
-    int *work_list;
-    int *bad_count;   // number of portfolios left INFEASIBLE or INEXACT (what the host layer raises on)
-};
-
-template <typename T> __device__ __forceinline__ T sym_at(const T *Qs, int LD, int i, int j) {
-    return i >= j ? Qs[i * LD + j] : Qs[j * LD + i];
-}
-
-// Shared-memory carve-up used by the forward kernels
-template <typename T> struct MkSmem {
-    T *Qs, *As, *r, *wv, *g, *dinv, *red;
-    int *idx, *idxU, *misc;
-    int8_t *st;
-};
-
-template <typename T, bool kGlobal>
-__device__ __forceinline__ MkSmem<T> carve(unsigned char *raw, int N, int LD, int AS, int CH, T *ws, long long b) {
-    MkSmem<T> s;
-    const int NP = round_up(N + 2, 32);
-    T *p = reinterpret_cast<T *>(raw);
-    if (kGlobal) s.Qs = ws + b * (long long)N * LD;
-    else { s.Qs = p; p += round_up(N * LD, 4); }
-    s.As = p; p += 2 * CH * AS;
-    s.r = p; p += NP;
-    s.wv = p; p += NP;
-    s.g = p; p += NP;
-    s.dinv = p; p += NP;
-    s.red = p; p += 64;
-    int *q = reinterpret_cast<int *>(p);
-    s.idx = q; q += NP;
-    s.idxU = q; q += NP;
-    s.misc = q; q += 8;
-    s.st = reinterpret_cast<int8_t *>(q);
-    return s;
-}
-
-static size_t mk_smem_bytes(int N, int LD, int AS, int CH, int tsize, bool global_q) {
-    const int NP = round_up(N + 2, 32);
-    size_t elems = (global_q ? 0 : (size_t)round_up(N * LD, 4)) + (size_t)2 * CH * AS + (size_t)4 * NP + 64;
-    return elems * tsize + ((size_t)2 * NP + 8) * sizeof(int) + (size_t)NP;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Small reduced systems (the usual case: a handful of free assets): every element of the augmented
-// lower triangle (n columns, n + 2 rows: Q_FF on top of the two right-hand sides) lives in a
-// register of its owning thread for the whole factorisation.  Column k is published to shared
-// memory once it is final; all later columns then apply  v(i,j) -= L(i,k) L(j,k) / d_k  from
-// registers.  One barrier per column, no index arithmetic in the loop.
-// ------------------------------------------------------------------------------------------------
-constexpr int kSmallElemsMax = 8;   // elements per thread (variants with 2, 4 and 8 slots)
-
-template <typename T, int kThreads>
-__device__ __forceinline__ bool small_system_fits(int n) { return n * (n + 1) / 2 + 2 * n <= kThreads * kSmallElemsMax; }
-
-template <typename T, int kThreads, int kSmallElems, typename Init>
-__device__ __forceinline__ int factor_small_n(T *Lb, int ld, int nF, T *dinv, T dmin, Init init) {
-    const int tid = threadIdx.x;
-    const int E = nF * (nF + 1) / 2 + 2 * nF;
-    const int colh = nF + 2;   // column j holds rows j .. nF+1
-    T v[kSmallElems];
-    int ii[kSmallElems], jj[kSmallElems];
-#pragma unroll
-    for (int m = 0; m < kSmallElems; ++m) {
-        const int e = tid + m * kThreads;
-        ii[m] = 0; jj[m] = -1; v[m] = T(0);
-        if (e < E) {
-            // column-major enumeration: offset(j) = j*colh - j(j-1)/2
-            const float bq = (float)(2 * colh + 1);
-            int j = (int)((bq - sqrtf(bq * bq - 8.f * (float)e)) * 0.5f);
-            j = max(0, min(j, nF - 1));
-            while (j > 0 && j * colh - j * (j - 1) / 2 > e) --j;
-            while (j + 1 < nF && (j + 1) * colh - (j + 1) * j / 2 <= e) ++j;
-            const int i = j + (e - (j * colh - j * (j - 1) / 2));
-            ii[m] = i; jj[m] = j;
-            v[m] = init(i, j);
-        }
-    }
-    int lifted = 0;
-    for (int k = 0; k < nF; ++k) {
-        T *colk = Lb + k * ld;
-#pragma unroll
-        for (int m = 0; m < kSmallElems; ++m)
-            if (jj[m] == k) colk[ii[m]] = v[m];
-        __syncthreads();
-        T d = colk[k];
-        if (!(d > dmin)) { d = dmin; lifted = 1; }
-        const T invd = T(1) / d;
-        if (tid == 0) dinv[k] = invd;
-#pragma unroll
-        for (int m = 0; m < kSmallElems; ++m)
-            if (jj[m] > k) v[m] = fma(-colk[ii[m]], colk[jj[m]] * invd, v[m]);
-    }
-    __syncthreads();
-    return lifted;
-}
-
-// init(i, j) returns element (i, j) of the augmented lower triangle: rows 0..nF-1 the matrix, row nF
-// and nF+1 the two right-hand sides.
-template <typename T, int kThreads, typename Init>
-__device__ __forceinline__ int factor_small(T *Lb, int ld, int nF, T *dinv, T dmin, Init init) {
-    const int E = nF * (nF + 1) / 2 + 2 * nF;
-    if (E <= 2 * kThreads) return factor_small_n<T, kThreads, 2>(Lb, ld, nF, dinv, dmin, init);
-    if (E <= 4 * kThreads) return factor_small_n<T, kThreads, 4>(Lb, ld, nF, dinv, dmin, init);
-    return factor_small_n<T, kThreads, 8>(Lb, ld, nF, dinv, dmin, init);
-}
-
-// ------------------------------------------------------------------------------------------------
-// One reduced-KKT solve + state update (a primal-dual active-set step).  Returns `changed`.
-//   w_L = 0, w_U = u, [[2 Q_FF, 1],[1', 0]] [w_F; nu] = [r_F - 2 u Q_FU 1; 1 - u |U|]
-// ------------------------------------------------------------------------------------------------
-template <typename T, int kThreads, int NREG>
-__device__ __forceinline__ int pdas_step(const MkSmem<T> &s, int N, int LD, T u, T dmin, T tolw, int &lifted) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kWarps = kThreads / 32;
-    T *Qs = s.Qs, *Lb = s.Qs + 1;
-    // (a) ordered index lists of the free and the capped assets
-    if (warp == 0) {
-        int nf = 0, nu = 0;
-        for (int base = 0; base < N; base += 32) {
-            const int i = base + lane;
-            const int v = i < N ? (int)s.st[i] : 2;
-            const unsigned mf = __ballot_sync(kFullMask, v == 0), mu = __ballot_sync(kFullMask, v == 1);
-            const unsigned lt = (1u << lane) - 1u;
-            if (v == 0) s.idx[nf + __popc(mf & lt)] = i;
-            if (v == 1) s.idxU[nu + __popc(mu & lt)] = i;
-            nf += __popc(mf); nu += __popc(mu);
-        }
-        if (lane == 0) { s.misc[0] = nf; s.misc[1] = nu; }
-    }
-    for (int i = tid; i < N; i += kThreads) s.wv[i] = s.st[i] > 0 ? u : T(0);
-    __syncthreads();
-    const int nF = s.misc[0], nU = s.misc[1];
-    const T c = T(1) - u * (T)nU;
-    int changed = 0;
-    T nu_mult = T(0);
-    if (nF > 0) {
-        if (small_system_fits<T, kThreads>(nF)) {
-            // (b,c) gather straight into registers and factor there
-            auto init = [&](int i, int j) -> T {
-                const int cj = s.idx[j];
-                if (i < nF) return Qs[s.idx[i] * LD + cj];   // idx ascending: (idx[i], idx[j]) is in the lower triangle
-                if (i > nF) return T(1);
-                T acc = T(0);
-                for (int q = 0; q < nU; ++q) acc += sym_at(Qs, LD, cj, s.idxU[q]);
-                return s.r[cj] - T(2) * u * acc;
-            };
-            lifted |= factor_small<T, kThreads>(Lb, LD, nF, s.dinv, dmin, init);
-        } else {
-            // (b) gather Q_FF and the two right-hand sides
-            for (int cc = warp; cc < nF; cc += kWarps) {
-                const int jc = s.idx[cc];
-                for (int a = cc + lane; a < nF; a += 32) Lb[cc * LD + a] = Qs[s.idx[a] * LD + jc];
-            }
-            for (int a = tid; a < nF; a += kThreads) {
-                const int i = s.idx[a];
-                T acc = T(0);
-                for (int m = 0; m < nU; ++m) acc += sym_at(Qs, LD, i, s.idxU[m]);
-                Lb[a * LD + nF] = s.r[i] - T(2) * u * acc;
-                Lb[a * LD + nF + 1] = T(1);
-            }
-            __syncthreads();
-            // (c) factor, eliminating the right-hand sides on the way
-            lifted |= factor_ldl<T, kThreads>(Lb, LD, nF, 2, s.dinv, dmin);
-        }
-        // (d,e) multiplier of the budget constraint and back substitution -- warp 0
-        if (warp == 0) {
-            T s12 = T(0), s22 = T(0);
-            for (int k = lane; k < nF; k += 32) {
-                const T y1 = Lb[k * LD + nF], y2 = Lb[k * LD + nF + 1], di = s.dinv[k];
-                s12 = fma(y1 * y2, di, s12);
-                s22 = fma(y2 * y2, di, s22);
-            }
-            s12 = warp_sum(s12); s22 = warp_sum(s22);
-            const T nu = (s12 - T(2) * c) / s22;
-            T zt[NREG];
-#pragma unroll
-            for (int m = 0; m < NREG; ++m) {
-                const int k = lane + 32 * m;
-                zt[m] = k < nF ? T(0.5) * (Lb[k * LD + nF] - nu * Lb[k * LD + nF + 1]) : T(0);
-            }
-            backsub_warp<T, NREG>(Lb, LD, nF, s.dinv, zt);
-#pragma unroll
-            for (int m = 0; m < NREG; ++m) {
-                const int k = lane + 32 * m;
-                if (k < nF) s.wv[s.idx[k]] = zt[m];
-            }
-            if (lane == 0) s.red[32] = nu;
-        }
-        __syncthreads();
-        nu_mult = s.red[32];
-        // (f,g) gradient of the Lagrangian and the new active set
-        for (int i = tid; i < N; i += kThreads) {
-            T acc = T(0);
-            for (int m = 0; m < nF; ++m) { const int j = s.idx[m]; acc = fma(sym_at(Qs, LD, i, j), s.wv[j], acc); }
-            for (int m = 0; m < nU; ++m) acc = fma(sym_at(Qs, LD, i, s.idxU[m]), u, acc);
-            const T gi = T(2) * acc - s.r[i] + nu_mult;
-            const int8_t so = s.st[i];
-            int8_t sn = so;
-            if (so == 0) {
-                const T wi = s.wv[i];
-                if (wi < -tolw) sn = -1;
-                else if (wi > u + tolw) sn = 1;
-            } else if (so < 0) { if (gi < T(0)) sn = 0; }
-            else { if (gi > T(0)) sn = 0; }
-            if (sn != so) { s.st[i] = sn; changed = 1; }
-        }
-    } else {
-        // no free asset: w is fixed by the caps; optimal iff max_L(-h) <= min_U(-h) and u |U| = 1
-        for (int i = tid; i < N; i += kThreads) {
-            T acc = T(0);
-            for (int m = 0; m < nU; ++m) acc = fma(sym_at(Qs, LD, i, s.idxU[m]), u, acc);
-            s.g[i] = T(2) * acc - s.r[i];
-        }
-        __syncthreads();
-        if (warp == 0) {
-            T hl = Num<T>::inf(), hu = Num<T>::inf();  // min h over L, min (-h) over U
-            int il = 0x7fffffff, iu = 0x7fffffff;
-            for (int i = lane; i < N; i += 32) {
-                const T h = s.g[i];
-                if (s.st[i] < 0) { if (h < hl) { hl = h; il = i; } }
-                else if (s.st[i] > 0) { if (-h < hu) { hu = -h; iu = i; } }
-            }
-            warp_argmin(hl, il); warp_argmin(hu, iu);
-            const T ctol = T(4) * Num<T>::eps() * (T)N;
-            int ch = 0;
-            if (lane == 0) {
-                if (c > ctol && il < N) { s.st[il] = 0; ch = 1; }
-                else if (c < -ctol && iu < N) { s.st[iu] = 0; ch = 1; }
-                else if (il < N && iu < N && -hl > hu) { s.st[il] = 0; s.st[iu] = 0; ch = 1; }
-                s.misc[2] = ch;
-            }
-        }
-        __syncthreads();
-        changed = s.misc[2];
-    }
-    return __syncthreads_or(changed);
-}
-
-// Safeguarded Newton on nu for the separable problem with diag(Q): initial active set.  Warp 0.
-template <typename T, int NREG>
-__device__ __forceinline__ void diag_init_warp(const T *qdiag, int qstride, const T *r, int8_t *st_out, int N, T u,
-                                               T *dmax_out) {
-    const int lane = threadIdx.x & 31;
-    T i2q[NREG], rr[NREG];
-    T lo = Num<T>::inf(), hi = -Num<T>::inf(), sa = T(0), sb = T(0), dmax = T(0);
-#pragma unroll
-    for (int m = 0; m < NREG; ++m) {
-        const int i = lane + 32 * m;
-        if (i < N) {
-            T q = qdiag[i * qstride];
-            dmax = q > dmax ? q : dmax;
-            q = q > Num<T>::tiny() ? q : Num<T>::tiny();
-            i2q[m] = T(0.5) / q; rr[m] = r[i];
-            const T l = rr[m] - T(2) * q * u;
-            lo = l < lo ? l : lo; hi = rr[m] > hi ? rr[m] : hi;
-            sa = fma(rr[m], i2q[m], sa); sb += i2q[m];
-        } else { i2q[m] = T(0); rr[m] = T(0); }
-    }
-    lo = warp_min(lo); hi = warp_max(hi); sa = warp_sum(sa); sb = warp_sum(sb); dmax = warp_max(dmax);
-    T nu = (sa - T(1)) / sb;
-    nu = clampT(nu, lo, hi);
-    T dxold = hi - lo, dx = dxold;
-    for (int it = 0; it < 60; ++it) {
-        T sum = T(0), slope = T(0);
-#pragma unroll
-        for (int m = 0; m < NREG; ++m) {
-            const T v = (rr[m] - nu) * i2q[m];
-            sum += clampT(v, T(0), u);
-            slope += (v > T(0) && v < u) ? i2q[m] : T(0);
-        }
-        sum = warp_sum(sum); slope = warp_sum(slope);
-        if (absT(sum - T(1)) <= T(1e-6)) break;
-        if (sum > T(1)) lo = nu; else hi = nu;
-        T nn = nu;
-        bool ok = false;
-        if (slope > T(0)) {
-            nn = nu + (sum - T(1)) / slope;
-            ok = nn > lo && nn < hi && absT(T(2) * (nn - nu)) <= absT(dxold);
-        }
-        dxold = dx;
-        if (ok) dx = nn - nu;
-        else { dx = T(0.5) * (hi - lo); nn = lo + dx; }
-        if (nn == nu) break;
-        nu = nn;
-    }
-#pragma unroll
-    for (int m = 0; m < NREG; ++m) {
-        const int i = lane + 32 * m;
-        if (i < N) {
-            const T v = (rr[m] - nu) * i2q[m];
-            st_out[i] = v <= T(0) ? -1 : (v >= u ? 1 : 0);
-        }
-    }
-    *dmax_out = dmax;
-}
-
-// write the result of a converged / abandoned active-set iteration
-template <typename T, int kThreads>
-__device__ __forceinline__ void write_result(const MkSmem<T> &s, int N, T u, T *w_out, int8_t *st_out) {
-    for (int i = threadIdx.x; i < N; i += kThreads) {
-        int8_t st = s.st[i];
-        const T wi = st == 0 ? clampT(s.wv[i], T(0), u) : (st > 0 ? u : T(0));
-        // tie rule: a free asset whose weight lands exactly on a bound (within rounding) is reported as
-        // active, so the saved state is a function of the returned weights
-        if (st == 0) st = wi <= T(0) ? -1 : (wi >= u ? 1 : 0);
-        w_out[i] = wi;
-        st_out[i] = st;
-    }
-}
-
-// returns 1 when the problem was decided by the box alone (infeasible or a single feasible point)
-template <typename T, int kThreads>
-__device__ __forceinline__ int trivial_cases(int N, T u, T *w_out, int8_t *st_out, int32_t *status, int *bad_count) {
-    const T cap = u * (T)N;
-    const T tol = T(8) * Num<T>::eps() * (T)N;
-    if (cap < T(1) - tol || !(u > T(0))) {
-        for (int i = threadIdx.x; i < N; i += kThreads) { w_out[i] = Num<T>::inf() - Num<T>::inf(); st_out[i] = 0; }
-        if (threadIdx.x == 0) { *status = DDW_STATUS_INFEASIBLE; atomicAdd(bad_count, 1); }
-        return 1;
-    }
-    if (cap <= T(1) + tol) {
-        for (int i = threadIdx.x; i < N; i += kThreads) { w_out[i] = u; st_out[i] = 1; }
-        if (threadIdx.x == 0) *status = DDW_STATUS_OK;
-        return 1;
-    }
-    return 0;
-}
-
-}  // namespace ddw
-
-#include "markowitz_sparse.cuh"
-
-namespace ddw {
+// sparse-support kernels (markowitz_sparse.cuh / markowitz_bwd_sparse.cuh, compiled in their own translation units)
+bool fwd_sparse_eligible(int N, int tsize, int smem_limit);
+template <typename T> int launch_fwd_sparse(const MkFwdParams<T> &p, cudaStream_t st);
+bool bwd_sparse_eligible(int N, int tsize, int smem_limit);
+template <typename T> int launch_bwd_sparse(const MkBwdParams<T> &p, cudaStream_t st);
 
 // Dense forward kernel.  Direct mode (work_list == nullptr): one CTA per portfolio, grid = B.
 // List mode: a fixed grid walks the portfolios that the sparse kernel handed over.
@@ -638,15 +293,6 @@ __global__ void __launch_bounds__(kThreads) markowitz_ipm_kernel(MkFwdParams<T> 
 //   d_rets = d;  dA = -2 [(A d) w' + (A w) d'];  d_covmat_sqrt = gamma_ * dA;  d_alpha = sign(alpha)(-2 d.w)
 // The (A d, A w) vectors are also written to `vecs` (B,2,N) for the gamma scatter pass.
 // ------------------------------------------------------------------------------------------------
-template <typename T> struct MkBwdParams {
-    const T *grad_w, *w, *C, *gamma, *alpha;
-    const int8_t *state;
-    long long B, Bmod, b0;   // as in MkFwdParams
-    int N, LDW, AS, CH;
-    T *d_rets, *d_C, *d_alpha, *vecs;
-    T *ws;  // global factor storage when it does not fit shared memory
-};
-
 static size_t mk_bwd_smem_bytes(int N, int LDW, int AS, int CH, int tsize, bool global_l) {
     const int NP = round_up(N + 2, 32);
     size_t elems = (global_l ? 0 : (size_t)round_up(N * LDW, 4)) + (size_t)2 * CH * AS + (size_t)7 * NP + 64;
@@ -660,7 +306,9 @@ static size_t mk_bwd_smem_bytes(int N, int LDW, int AS, int CH, int tsize, bool 
 template <typename T, int kThreads, int NREG, bool kGlobal>
 __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const long long b = blockIdx.x;
+    // list mode: the sparse-support kernel handed over the portfolios whose free set is too large for it
+    if (p.work_list && (long long)blockIdx.x >= (long long)*p.work_count) return;
+    const long long b = p.work_list ? (long long)p.work_list[blockIdx.x] : (long long)blockIdx.x;
     const int N = p.N, LDW = p.LDW, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kThreads / 32;
     const int NP = round_up(N + 2, 32);
@@ -1108,17 +756,9 @@ static int launch_fwd_variant(MkFwdParams<T> p, const MkPlan &pl, T *ipm_ws, boo
     cudaMemsetAsync(p.fail_count, 0, 4 * sizeof(int), st);
     int rc;
     if (sparse_first) {
-        // small-support portfolios are finished by the sparse kernel; the rest land on work_list
-        auto ks = markowitz_fwd_sparse_kernel<T, 128, 4>;
-        const size_t sp_smem = sp_smem_bytes(p.N, sizeof(T));
-        static bool sp_configured = false;
-        if (!sp_configured) {
-            if (cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess)
-                return check_launch("cudaFuncSetAttribute(markowitz_fwd_sparse)");
-            sp_configured = true;
-        }
-        ks<<<(unsigned)p.B, 128, sp_smem, st>>>(p);
-        if ((rc = check_launch("markowitz_fwd_sparse_kernel"))) return rc;
+        // small-support portfolios are finished by the sparse kernel (its own translation unit); the rest land
+        // on work_list
+        if ((rc = launch_fwd_sparse<T>(p, st))) return rc;
         kf<<<(unsigned)min((long long)kDenseListGrid, p.B), kThreads, pl.smem, st>>>(p);
     } else {
         p.work_count = nullptr; p.work_list = nullptr;
@@ -1148,7 +788,7 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
     p.fail_count = l.fail_count; p.fail_list = l.fail_list;
     p.work_count = l.work_count; p.work_list = l.work_list; p.bad_count = l.bad_count;
     // sparse-support kernel first whenever A (4 N^2 bytes) fits shared memory with room for >= 2 CTAs per SM
-    const bool sparse_first = N <= 128 && sp_smem_bytes(N, sizeof(T)) <= (size_t)smem_limit() / 2 && N >= 8;
+    const bool sparse_first = fwd_sparse_eligible(N, sizeof(T), smem_limit());
     if (!pl.global_q) {
         if (pl.threads == 128) {
             // Gram tiles kept in registers: 1, 2, 3 or 5 tiles of 4x4 per thread (n_assets <= 60 / 88 / 108 / 128)
@@ -1195,6 +835,13 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
     p.alpha = (const T *)alpha; p.state = state; p.B = B; p.Bmod = Bmod; p.b0 = b0; p.N = N; p.LDW = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
     p.d_rets = (T *)d_rets; p.d_C = (T *)d_C; p.d_alpha = (T *)d_alpha; p.vecs = d_gamma ? l.vecs : nullptr; p.ws = l.q;
     int rc;
+    // sparse-support kernel first (A staged by TMA, free set <= kCandMax); it lists the portfolios it cannot take
+    p.work_count = nullptr; p.work_list = nullptr;
+    if (!pl.global_q && pl.threads == 128 && bwd_sparse_eligible(N, sizeof(T), smem_limit())) {
+        p.work_count = l.fail_count + 3; p.work_list = l.work_list;
+        cudaMemsetAsync(p.work_count, 0, sizeof(int), st);
+        if ((rc = launch_bwd_sparse<T>(p, st))) return rc;
+    }
     if (!pl.global_q && pl.threads == 128) rc = launch_bwd_variant<T, 128, 4, false>(p, pl, st);
     else if (!pl.global_q && pl.threads == 256) rc = launch_bwd_variant<T, 256, 8, false>(p, pl, st);
     else if (pl.threads == 128) rc = launch_bwd_variant<T, 128, 4, true>(p, pl, st);

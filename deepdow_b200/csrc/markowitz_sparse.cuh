@@ -1,4 +1,5 @@
-// markowitz_sparse.cuh -- forward solver for portfolios with a small support (included by markowitz.cu)
+// markowitz_sparse.cuh -- forward solver for portfolios with a small support
+// (compiled in markowitz_fwd_sparse_f32.cu / markowitz_fwd_sparse_f64.cu; problem statement in markowitz_impl.cuh)
 //
 // The dense kernel forms the whole Gram Q = A'A (N^3/2 flops) although an active-set iteration only
 // ever needs (i) the block of Q on the assets that are or were free and (ii) gradients 2 A'(A w).
@@ -7,25 +8,46 @@
 // they first become free ("candidates").  Work per portfolio drops from ~N^3/2 to
 // ~|cand|^2 N/2 + iterations * 2 N^2 flops.  Portfolios whose candidate set outgrows kCandMax are
 // appended to a work list that the dense kernel then processes.
+//
+// Per active-set iteration (one CTA of 128 threads per portfolio):
+//   lists      warp 0 compacts the free / capped sets and hands out candidate slots
+//   Gram       4x4 register tiles of a_s . a_c for the new candidates, rows split over 8 lanes per tile
+//   KKT solve  ONE warp (kkt_solve_warp): column-by-column LDL' in shared memory with the right-hand sides in
+//              registers; no block barrier inside
+//   gradient   t = A w on the support, then g = 2 A't as a column pass with 16-byte loads, rows split over
+//              the thread groups and combined through shared memory
 #pragma once
+#include <stdlib.h>
+#include "markowitz_common.cuh"
+#include "support_kernels.cuh"
 
 namespace ddw {
 
 constexpr int kCandMax = 48;
 constexpr int kCandLd = (kCandMax + 3) | 1;
+constexpr int kCandSlots = (kCandMax + 31) / 32;   // rows per lane in the one-warp KKT solve
 
 template <typename T> struct SpSmem {
     unsigned long long *mbar;
-    T *As, *Qc, *r, *wv, *tv, *g, *qd, *dinv, *red;
-    int *idx, *idxU, *slot, *cand, *misc;
+    T *As, *Qc, *part, *r, *wv, *tv, *g, *qd, *dinv, *wF, *red;   // g aliases dinv (only used when no asset is free)
+    int *idx, *idxU, *slot, *sF, *cand, *misc;
     int8_t *st;
 };
 
 static size_t sp_smem_bytes(int N, int tsize) {
     const int NP = round_up(N + 2, 32);
-    const size_t elems = (size_t)round_up(N * N, 4) + round_up(kCandMax * kCandLd, 4) + 6 * (size_t)NP + 64;
-    return 16 + elems * tsize + ((size_t)3 * NP + 64 + 8) * sizeof(int) + NP;
+    const size_t elems = (size_t)round_up(N * N, 4) + round_up(kCandMax * kCandLd, 4) + kPartElems + 6 * (size_t)NP + 40;
+    return 16 + elems * tsize + ((size_t)3 * NP + 64 + 64 + 8) * sizeof(int) + NP;
 }
+
+#ifdef DDW_MK_DEFINE_ELIGIBLE
+// sparse-support kernel first whenever A (4 N^2 bytes) fits shared memory with room for >= 2 CTAs per SM
+bool fwd_sparse_eligible(int N, int tsize, int smem_limit) {
+    return N <= 128 && N >= 8 && sp_smem_bytes(N, tsize) <= (size_t)smem_limit / 2;
+}
+#else
+bool fwd_sparse_eligible(int N, int tsize, int smem_limit);
+#endif
 
 template <typename T> __device__ __forceinline__ SpSmem<T> sp_carve(unsigned char *raw, int N) {
     SpSmem<T> s;
@@ -34,25 +56,27 @@ template <typename T> __device__ __forceinline__ SpSmem<T> sp_carve(unsigned cha
     T *p = reinterpret_cast<T *>(raw + 16);
     s.As = p; p += round_up(N * N, 4);
     s.Qc = p; p += round_up(kCandMax * kCandLd, 4);
+    s.part = p; p += kPartElems;
     s.r = p; p += NP;
     s.wv = p; p += NP;
     s.tv = p; p += NP;
-    s.g = p; p += NP;
     s.qd = p; p += NP;
-    s.dinv = p; p += NP;
-    s.red = p; p += 64;
+    s.dinv = p; s.g = p; p += NP;
+    s.wF = p; p += NP;
+    s.red = p; p += 40;
     int *q = reinterpret_cast<int *>(p);
     s.idx = q; q += NP;
     s.idxU = q; q += NP;
     s.slot = q; q += NP;
     s.cand = q; q += 64;
+    s.sF = q; q += 64;
     s.misc = q; q += 8;
     s.st = reinterpret_cast<int8_t *>(q);
     return s;
 }
 
 template <typename T, int kThreads, int NREG>
-__global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdParams<T> p) {
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fwd_sparse_kernel(MkFwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const long long b = blockIdx.x;
     const int N = p.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -65,56 +89,34 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
     T *As = s.As, *Qc = s.Qc, *Lb = s.Qc + 1;
     const T *Cb = p.C + b * (long long)N * N;
     const long long gflat0 = (p.b0 + b) * (long long)N * N;
-    const unsigned bytes = (unsigned)(N * N * sizeof(T));
-    const unsigned uB = (unsigned)p.Bmod;
 
     // ---- A -> shared memory: one bulk TMA copy (40 KB at N = 100), completion on an mbarrier
-    const bool use_tma = (bytes & 15u) == 0u && (reinterpret_cast<unsigned long long>(Cb) & 15ull) == 0ull;
-    if (use_tma) {
-        if (tid == 0) { mbar_init(s.mbar, 1); fence_mbar_init(); }
-        __syncthreads();
-        if (tid == 0) { mbar_expect_tx(s.mbar, bytes); tma_bulk_g2s(As, Cb, bytes, s.mbar); }
-    }
+    DDW_PHASE_INIT
+    DDW_PHASE_COUNT(11);
+    const bool use_tma = stage_matrix_begin<T, kThreads>(As, Cb, N, s.mbar);
     for (int i = tid; i < N; i += kThreads) { s.r[i] = p.rets[b * N + i]; s.slot[i] = -1; }
     if (tid == 0) { s.misc[3] = 0; }
     const T aabs = absT(p.alpha[b]);
-    if (use_tma) mbar_wait(s.mbar, 0);
-    else for (int e = tid; e < N * N; e += kThreads) As[e] = Cb[e];
-    // ---- gamma tiling (allocate.py:268-270), in place; every thread touches the elements it will not
-    // need before the next barrier
-    if ((N & 3) == 0 && (uB & 3u) == 0u) {
-        unsigned gi = (unsigned)((gflat0 + 4 * tid) % p.Bmod);
-        const unsigned gstep = (unsigned)((4 * kThreads) % p.Bmod);
-        for (int e = 4 * tid; e < N * N; e += 4 * kThreads) {
-            Vec4<T> a = ld4(As + e);
-            const Vec4<T> g4 = ld4(p.gamma + gi);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) a.v[q] *= g4.v[q];
-            st4(As + e, a);
-            gi += gstep; if (gi >= uB) gi -= uB;
-        }
-    } else {
-        unsigned gi = (unsigned)((gflat0 + tid) % p.Bmod);
-        const unsigned gstep = (unsigned)(kThreads % p.Bmod);
-        for (int e = tid; e < N * N; e += kThreads) {
-            As[e] *= p.gamma[gi];
-            gi += gstep; if (gi >= uB) gi -= uB;
-        }
-    }
+    stage_matrix_end<T, kThreads>(As, Cb, N, s.mbar, use_tma);
+    DDW_PHASE(0);
+    // ---- gamma tiling (allocate.py:268-270), in place
+    apply_gamma_tiling<T, kThreads>(As, N, p.gamma, gflat0, p.Bmod);
     __syncthreads();
     // ---- diag(Q) = column norms + |alpha|
-    for (int i = tid; i < N; i += kThreads) {
-        T acc = aabs;
-        for (int k = 0; k < N; ++k) { const T a = As[k * N + i]; acc = fma(a, a, acc); }
-        s.qd[i] = acc;
+    {
+        const int slices = column_pass<T, kThreads, true>(As, N, nullptr, s.part);
+        __syncthreads();
+        for (int i = tid; i < N; i += kThreads) s.qd[i] = column_pass_sum(s.part, N, slices, i) + aabs;
     }
     __syncthreads();
+    DDW_PHASE(1);
     if (warp == 0) {
         T dmax;
         diag_init_warp<T, NREG>(s.qd, 1, s.r, s.st, N, u, &dmax);
         if (lane == 0) s.red[33] = dmax;
     }
     __syncthreads();
+    DDW_PHASE(2);
     const T dmin = T(4) * Num<T>::eps() * s.red[33] + Num<T>::tiny();
     const T tolw = T(8) * Num<T>::eps();
     int lifted = 0, converged = 0, bail = 0;
@@ -143,33 +145,14 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
         }
         for (int i = tid; i < N; i += kThreads) s.wv[i] = s.st[i] > 0 ? u : T(0);
         __syncthreads();
+        DDW_PHASE(3);
+        DDW_PHASE_COUNT(10);
+        DDW_PHASE_ADD(12, s.misc[0]);
+        if (it == 0) DDW_PHASE_ADD(14, s.misc[0]);
         const int nF = s.misc[0], nU = s.misc[1], nc0 = s.misc[2], nc1 = s.misc[3];
         if (nc1 > kCandMax) { bail = 1; break; }
-        // (b) Gram entries of the new candidates against all candidates: Q(s,c) = a_s . a_c
-        if (nc1 > nc0) {
-            const int base_cnt = nc0 * (nc0 + 1) / 2, tot = nc1 * (nc1 + 1) / 2 - base_cnt;
-            for (int e = tid; e < tot; e += kThreads) {
-                const int t = base_cnt + e;
-                int sr = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-                while (sr * (sr + 1) / 2 > t) --sr;
-                while ((sr + 1) * (sr + 2) / 2 <= t) ++sr;
-                const int c = t - sr * (sr + 1) / 2;
-                const int ia = s.cand[sr], ic = s.cand[c];
-                T acc;
-                if (sr == c) acc = s.qd[ia];
-                else {
-                    T a0 = T(0), a1 = T(0);
-                    int k = 0;
-                    for (; k + 1 < N; k += 2) {
-                        a0 = fma(As[k * N + ia], As[k * N + ic], a0);
-                        a1 = fma(As[(k + 1) * N + ia], As[(k + 1) * N + ic], a1);
-                    }
-                    if (k < N) a0 = fma(As[k * N + ia], As[k * N + ic], a0);
-                    acc = a0 + a1;
-                }
-                Qc[sr * LDC + c] = acc;
-            }
-        }
+        // (b) Gram entries of the new candidates against all candidates
+        if (nc1 > nc0) gram_columns<T, kThreads>(As, N, s.cand, s.qd, T(0), nc0, nc1, Qc, LDC, 1);
         // (c) t_U = A (u 1_U)
         if (nU > 0) {
             for (int k = tid; k < N; k += kThreads) {
@@ -184,13 +167,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
         T nu_mult = T(0);
         if (nF > 0) {
             // (d) reduced KKT system: Q_FF from the candidate block, rhs r_F - 2 A_F' t_U and 1
-            auto init = [&](int i, int j) -> T {
-                const int cj = s.idx[j];
-                if (i < nF) {
-                    const int sa = s.slot[s.idx[i]], sc = s.slot[cj];
-                    return sa >= sc ? Qc[sa * LDC + sc] : Qc[sc * LDC + sa];
-                }
-                if (i > nF) return T(1);
+            auto rhs1 = [&](int cj) -> T {
                 T acc = s.r[cj];
                 if (nU > 0) {
                     T d0 = T(0);
@@ -199,60 +176,73 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
                 }
                 return acc;
             };
-            if (small_system_fits<T, kThreads>(nF)) lifted |= factor_small<T, kThreads>(Lb, LDC, nF, s.dinv, dmin, init);
-            else {
-                for (int e = tid; e < nF * (nF + 2); e += kThreads) {
-                    const int j = e / (nF + 2), i = e - j * (nF + 2);
-                    if (i >= j) Lb[j * LDC + i] = init(i, j);
+            for (int m = tid; m < nF; m += kThreads) s.sF[m] = s.slot[s.idx[m]];
+            __syncthreads();
+            DDW_PHASE(4);
+            if (nF > 32) {
+                // rare: all warps gather Q_FF from the candidate block into the factor area
+                for (int j = warp; j < nF; j += kThreads / 32) {
+                    const int sj = s.sF[j];
+                    for (int i = j + lane; i < nF; i += 32) {
+                        const int si = s.sF[i];
+                        Lb[j * LDC + i] = Qc[max(si, sj) * LDC + min(si, sj)];
+                    }
                 }
                 __syncthreads();
-                lifted |= factor_ldl<T, kThreads>(Lb, LDC, nF, 2, s.dinv, dmin);
             }
+            DDW_PHASE(5);
+            // ONE warp solves; the other warps wait at the barrier below
             if (warp == 0) {
-                T s12 = T(0), s22 = T(0);
-                for (int k = lane; k < nF; k += 32) {
-                    const T y1 = Lb[k * LDC + nF], y2 = Lb[k * LDC + nF + 1], di = s.dinv[k];
-                    s12 = fma(y1 * y2, di, s12);
-                    s22 = fma(y2 * y2, di, s22);
-                }
-                s12 = warp_sum(s12); s22 = warp_sum(s22);
-                const T nu = (s12 - T(2) * c) / s22;
-                T zt[NREG];
+                T nu;
+                if (nF <= 32) {
+                    // rows of Q_FF straight from the candidate block into registers
+                    T m[32];
+                    const int si = lane < nF ? s.sF[lane] : 0;
 #pragma unroll
-                for (int m = 0; m < NREG; ++m) {
-                    const int k = lane + 32 * m;
-                    zt[m] = k < nF ? T(0.5) * (Lb[k * LDC + nF] - nu * Lb[k * LDC + nF + 1]) : T(0);
-                }
-                backsub_warp<T, NREG>(Lb, LDC, nF, s.dinv, zt);
+                    for (int j = 0; j < 32; ++j) {
+                        const int sj = __shfl_sync(kFullMask, si, j);
+                        m[j] = (lane < nF && j <= lane && j < nF) ? Qc[max(si, sj) * LDC + min(si, sj)] : T(0);
+                    }
+                    T x = lane < nF ? rhs1(s.idx[lane]) : T(0);
+                    nu = kkt_solve_regs<T>(m, x, nF, c, dmin, Lb, LDC, s.dinv, s.part, lifted);   // part: free between column passes
+                    if (lane < nF) { s.wv[s.idx[lane]] = x; s.wF[lane] = x; }
+                } else {
+                    T x[kCandSlots];
 #pragma unroll
-                for (int m = 0; m < NREG; ++m) {
-                    const int k = lane + 32 * m;
-                    if (k < nF) s.wv[s.idx[k]] = zt[m];
+                    for (int r = 0; r < kCandSlots; ++r) x[r] = lane + 32 * r < nF ? rhs1(s.idx[lane + 32 * r]) : T(0);
+                    nu = kkt_solve_warp<T, kCandSlots>(Lb, LDC, nF, x, c, dmin, s.dinv, lifted);
+#pragma unroll
+                    for (int r = 0; r < kCandSlots; ++r) {
+                        const int k = lane + 32 * r;
+                        if (k < nF) { s.wv[s.idx[k]] = x[r]; s.wF[k] = x[r]; }
+                    }
                 }
                 if (lane == 0) s.red[32] = nu;
             }
             __syncthreads();
+            DDW_PHASE(6);
             nu_mult = s.red[32];
         }
         // (e) t = A w on the support, then the gradient 2 (A' t + |alpha| w) - r + nu
         for (int k = tid; k < N; k += kThreads) {
             T acc = nU > 0 ? s.tv[k] : T(0);
-            for (int m = 0; m < nF; ++m) { const int j = s.idx[m]; acc = fma(As[k * N + j], s.wv[j], acc); }
+            const T *row = As + k * N;
+            int m = 0;
+            for (; m + 3 < nF; m += 4) {
+                const int4 j4 = *reinterpret_cast<const int4 *>(s.idx + m);
+                const Vec4<T> w4 = ld4(s.wF + m);
+                acc = fma(row[j4.x], w4.v[0], acc); acc = fma(row[j4.y], w4.v[1], acc);
+                acc = fma(row[j4.z], w4.v[2], acc); acc = fma(row[j4.w], w4.v[3], acc);
+            }
+            for (; m < nF; ++m) acc = fma(row[s.idx[m]], s.wF[m], acc);
             s.tv[k] = acc;
         }
         __syncthreads();
+        DDW_PHASE(7);
+        const int slices = column_pass<T, kThreads, false>(As, N, s.tv, s.part);
+        __syncthreads();
         for (int i = tid; i < N; i += kThreads) {
-            T a0 = T(0), a1 = T(0);
-            int k = 0;
-            for (; k + 3 < N; k += 4) {
-                const Vec4<T> t4 = ld4(s.tv + k);
-                a0 = fma(As[k * N + i], t4.v[0], a0);
-                a1 = fma(As[(k + 1) * N + i], t4.v[1], a1);
-                a0 = fma(As[(k + 2) * N + i], t4.v[2], a0);
-                a1 = fma(As[(k + 3) * N + i], t4.v[3], a1);
-            }
-            for (; k < N; ++k) a0 = fma(As[k * N + i], s.tv[k], a0);
-            const T h = T(2) * (a0 + a1 + aabs * s.wv[i]) - s.r[i];
+            const T h = T(2) * (column_pass_sum(s.part, N, slices, i) + aabs * s.wv[i]) - s.r[i];
             if (nF > 0) {
                 const T gi = h + nu_mult;
                 const int8_t so = s.st[i];
@@ -290,7 +280,9 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
             __syncthreads();
             changed = s.misc[4];
         }
-        if (!__syncthreads_or(changed)) { converged = 1; break; }
+        const int any_change = __syncthreads_or(changed);
+        DDW_PHASE(8);
+        if (!any_change) { converged = 1; break; }
     }
     if (bail) {
         // support too large for this kernel: hand the portfolio to the dense kernel
@@ -313,6 +305,37 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_sparse_kernel(MkFwdPar
         }
         p.status[b] = st;
     }
+}
+
+#ifdef DDW_PHASE_TIMING
+}  // namespace ddw
+// debug only: copy (and optionally clear) the phase table of this translation unit's kernels
+extern "C" int DDW_PHASE_EXPORT(unsigned long long *out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, ddw::ddw_phase_cycles, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(ddw::ddw_phase_cycles, z, sizeof(z)); }
+    return 0;
+}
+namespace ddw {
+#endif
+
+template <typename T> int launch_fwd_sparse(const MkFwdParams<T> &p, cudaStream_t st) {
+    auto ks = markowitz_fwd_sparse_kernel<T, 128, 4>;
+    static bool configured = false;
+    if (!configured) {
+        int dev = 0, lim = 48 * 1024;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(markowitz_fwd_sparse)");
+        configured = true;
+    }
+    size_t smem = sp_smem_bytes(p.N, sizeof(T));
+#ifdef DDW_PHASE_TIMING
+    if (const char *pad = getenv("DDW_DEBUG_SMEM_PAD")) smem += (size_t)atoi(pad);   // fewer resident CTAs per SM
+#endif
+    ks<<<(unsigned)p.B, 128, smem, st>>>(p);
+    return check_launch("markowitz_fwd_sparse_kernel");
 }
 
 }  // namespace ddw

@@ -32,7 +32,7 @@ class MarkowitzHostPipeline:
         GPU that does the work.
     """
 
-    def __init__(self, n_assets, max_weight=1, chunk=256, device=None):
+    def __init__(self, n_assets, max_weight=1, chunk=128, device=None):
         self.n_assets = int(n_assets)
         self.max_weight = float(max_weight)
         self.chunk = int(chunk)
@@ -93,7 +93,7 @@ class MarkowitzHostPipeline:
             rc = lib.ddw_markowitz_host_step(self._handle, p(rets_h), p(cov_h), p(gam_h), p(alp_h), p(g_h),
                                              self.max_weight, B, N, dt, self.chunk, p(w), p(status),
                                              p(d_rets), p(d_cov), p(d_gam), p(d_alp),
-                                             p(self._scratch), self._scratch.numel(), _C.stream())
+                                             p(self._scratch), self._scratch.numel(), _C.stream(self.device))
         _C.check(rc, "ddw_markowitz_host_step")
         self._keep = (rets_h, cov_h, gam_h, alp_h, g_h)   # the copies read these until the stream has drained
         if sync:

@@ -40,18 +40,21 @@ class _StatusWatch:
 
     def __init__(self):
         self.buf = None
+        self.events = None
+        self.last_header = None
         self.pending = []   # (slot, event, description)
         self.next = 0
 
     def push(self, counter, what):
         if self.buf is None:
             self.buf = torch.zeros(self.SLOTS, dtype=torch.int32).pin_memory()
+            self.events = [torch.cuda.Event() for _ in range(self.SLOTS)]
         if len(self.pending) >= self.SLOTS:
             self.poll(block=True)
         slot = self.next
         self.next = (self.next + 1) % self.SLOTS
         self.buf[slot:slot + 1].copy_(counter, non_blocking=True)
-        ev = torch.cuda.Event()
+        ev = self.events[slot]      # free again: its previous use has been polled (pending < SLOTS)
         ev.record()
         self.pending.append((slot, ev, what))
 
@@ -84,10 +87,11 @@ class _MarkowitzFn(torch.autograd.Function):
         ws = _workspace(lib.ddw_markowitz_workspace_bytes(B, N, dt), rets.device)
         rc = lib.ddw_markowitz_fwd(_C.ptr(rets_c), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
                                    float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status),
-                                   _C.ptr(ws), ws.numel(), _C.stream())
+                                   _C.ptr(ws), ws.numel(), _C.stream(rets.device))
         _C.check(rc, "ddw_markowitz_fwd")
         what = f"batch of {B}, n_assets={N}, max_weight={max_weight}"
         counter = ws[8:12].view(torch.int32)          # counter [2] of the workspace header (include/ddw.h)
+        watch.last_header = ws[:16].view(torch.int32)  # [fallback, dense hand-over, unsolved, -] of this call (device)
         if check_status is True:
             bad = int(counter)
             if bad:
@@ -114,7 +118,7 @@ class _MarkowitzFn(torch.autograd.Function):
         ws = _workspace(lib.ddw_markowitz_workspace_bytes(B, N, dt), w.device)
         rc = lib.ddw_markowitz_bwd(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
                                    ctx.max_weight, B, N, dt, _C.ptr(d_rets), _C.ptr(d_cov), _C.ptr(d_gamma),
-                                   _C.ptr(d_alpha), _C.ptr(ws), ws.numel(), _C.stream())
+                                   _C.ptr(d_alpha), _C.ptr(ws), ws.numel(), _C.stream(w.device))
         _C.check(rc, "ddw_markowitz_bwd")
         return d_rets, d_cov, d_gamma, d_alpha, None, None, None
 
@@ -176,6 +180,12 @@ class NumericalMarkowitz(nn.Module):
                                        alpha.reshape(-1).to(dtype), self.max_weight, self.check_status, self._watch)
         self.last_status = status
         return w
+
+    def solver_counters(self):
+        """(problems sent to the interior-point fallback, problems handed from the sparse-support kernel to the
+        dense kernel, problems left unsolved) of the latest forward; synchronises with the device."""
+        h = self._watch.last_header
+        return None if h is None else tuple(int(v) for v in h[:3].tolist())
 
     def synchronize_status(self):
         """Block until every outstanding solve has reported; raise SolverError if any failed."""

@@ -48,11 +48,20 @@ def make_inputs_numpy(B, N, seed):
     return rets, C.astype(np.float32), np.ones(B, np.float32), np.ones(B, np.float32), G
 
 
-def time_cpu_oracle(sample, repeats, seed=4000, nthreads=0, budget_s=None):
+def host_threads():
+    """Every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which would pin the CPU arm to one)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def time_cpu_oracle(sample, repeats, seed=4000, nthreads=None, budget_s=None):
     """Oracle port (float64, OpenMP) forward+backward on `sample` problems; returns (solves/s, threads, seconds).
     With `budget_s` the number of repeats is chosen so that about that many seconds of CPU work are timed."""
     import numpy as np
     import oracle
+    nthreads = host_threads() if nthreads is None else nthreads
     rets, C, g, a, G = make_inputs_numpy(sample, N_ASSETS, seed)
     rets, C, g, a, G = [x.astype(np.float64) for x in (rets, C, g, a, G)]
     oracle.markowitz_fwd(rets[:8], C[:8], g[:8], a[:8], MAX_WEIGHT, nthreads)  # load + warm
@@ -67,7 +76,7 @@ def time_cpu_oracle(sample, repeats, seed=4000, nthreads=0, budget_s=None):
         w, st, kkt, status = oracle.markowitz_fwd(rets, C, g, a, MAX_WEIGHT, nthreads)
         oracle.markowitz_bwd(G, w, st, C, g, a, MAX_WEIGHT, nthreads)
         times.append(time.perf_counter() - t0)
-    return sample / statistics.median(times), oracle.num_threads(), sum(times)
+    return sample / statistics.median(times), nthreads, sum(times)
 
 
 def run_reference(args, rank, world):
@@ -80,17 +89,17 @@ def run_reference(args, rank, world):
     import numpy as np
     import oracle
     rets, C, g, a, G = [x.astype(np.float64) for x in make_inputs_numpy(sample, N_ASSETS, 4000)]
+    cores = host_threads()
     per_step = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        w, st, kkt, status = oracle.markowitz_fwd(rets, C, g, a, MAX_WEIGHT, 0)
-        oracle.markowitz_bwd(G, w, st, C, g, a, MAX_WEIGHT, 0)
+        w, st, kkt, status = oracle.markowitz_fwd(rets, C, g, a, MAX_WEIGHT, cores)
+        oracle.markowitz_bwd(G, w, st, C, g, a, MAX_WEIGHT, cores)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             per_step.append(dt)
     total = sum(per_step)
     value = sample * len(per_step) / total
-    cores = oracle.num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(per_step),
@@ -178,7 +187,18 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        # NCCL prints its version banner to stdout at the first collective; the contract is ONE JSON line there
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     B, N, u = B_PER_GPU, N_ASSETS, MAX_WEIGHT
     gen = torch.Generator(device=dev).manual_seed(1000 * 4 + rank)

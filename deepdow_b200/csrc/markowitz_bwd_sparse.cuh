@@ -6,8 +6,8 @@
 //   d_rets = d;  dA = -2 [(A d) w' + (A w) d'];  d_covmat_sqrt = gamma_ * dA;  d_alpha = sign(alpha)(-2 d.w)
 //
 // One CTA of 128 threads per portfolio.  A (gamma-tiled covmat_sqrt) is brought into shared memory by one bulk
-// TMA copy; Q_FF is formed from the free columns as 4x4 register tiles, the reduced KKT system is solved by one
-// warp, A d and A w are row passes over the support, and the rank-2 gradient is streamed out with 16-byte stores
+// TMA copy; Q_FF is formed from the free columns as 4x4 register tiles, the reduced KKT system is factored by all
+// four warps with every element in a register, A d and A w are row passes over the support, and the rank-2 gradient is streamed out with 16-byte stores
 // (gamma loads issued one step ahead).  Portfolios with more than kCandMax free assets go to the dense kernel.
 #pragma once
 #include "markowitz_common.cuh"
@@ -98,26 +98,42 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_bw
         // Q_FF = A_F' A_F + |alpha| I straight into the factor area (element (s,c) at Lb[c*LDC + s])
         gram_columns<T, kThreads>(As, N, idx, (const T *)nullptr, absT(alpha), 0, nF, Lb, 1, LDC);
         __syncthreads();
+        T dmax = T(0);
+        for (int i = tid; i < nF; i += kThreads) dmax = max(dmax, Lb[i * LDC + i]);
+        dmax = warp_max(dmax);
+        if (lane == 0) red[warp] = dmax;
+        __syncthreads();
+        dmax = T(0);
+        for (int i = 0; i < kThreads / 32; ++i) dmax = max(dmax, red[i]);
+        const T dmin = T(4) * Num<T>::eps() * dmax + Num<T>::tiny();
+        // all four warps factor the augmented triangle [Q_FF; g_F; 1'] (markowitz_common.cuh), warp 0 finishes
+        auto init = [&](int i, int j) -> T { return i < nF ? Lb[j * LDC + i] : (i == nF ? gv[idx[j]] : T(1)); };
+        if (small_system_fits<T, kThreads>(nF)) factor_small<T, kThreads>(Lb, LDC, nF, dinv, dmin, init);
+        else {
+            for (int a = tid; a < nF; a += kThreads) { Lb[a * LDC + nF] = gv[idx[a]]; Lb[a * LDC + nF + 1] = T(1); }
+            __syncthreads();
+            factor_ldl<T, kThreads>(Lb, LDC, nF, 2, dinv, dmin);
+        }
         if (warp == 0) {
-            T dmax = T(0);
-            for (int i = lane; i < nF; i += 32) dmax = max(dmax, Lb[i * LDC + i]);
-            dmax = warp_max(dmax);
-            const T dmin = T(4) * Num<T>::eps() * dmax + Num<T>::tiny();
-            int lifted = 0;
-            if (nF <= 32) {
-                T x[1] = {lane < nF ? gv[idx[lane]] : T(0)};
-                kkt_solve_warp<T, 1>(Lb, LDC, nF, x, T(0), dmin, dinv, lifted);
-                if (lane < nF) { dv[idx[lane]] = x[0]; dS[lane] = x[0]; }
-            } else {
-                T x[kBwdSlots];
+            T s12 = T(0), s22 = T(0);
+            for (int k = lane; k < nF; k += 32) {
+                const T y1 = Lb[k * LDC + nF], y2 = Lb[k * LDC + nF + 1], di = dinv[k];
+                s12 = fma(y1 * y2, di, s12);
+                s22 = fma(y2 * y2, di, s22);
+            }
+            s12 = warp_sum(s12); s22 = warp_sum(s22);
+            const T eta = s12 / s22;
+            T zt[kBwdSlots];
 #pragma unroll
-                for (int r = 0; r < kBwdSlots; ++r) x[r] = lane + 32 * r < nF ? gv[idx[lane + 32 * r]] : T(0);
-                kkt_solve_warp<T, kBwdSlots>(Lb, LDC, nF, x, T(0), dmin, dinv, lifted);
+            for (int m = 0; m < kBwdSlots; ++m) {
+                const int k = lane + 32 * m;
+                zt[m] = k < nF ? T(0.5) * (Lb[k * LDC + nF] - eta * Lb[k * LDC + nF + 1]) : T(0);
+            }
+            backsub_warp<T, kBwdSlots>(Lb, LDC, nF, dinv, zt);
 #pragma unroll
-                for (int r = 0; r < kBwdSlots; ++r) {
-                    const int k = lane + 32 * r;
-                    if (k < nF) { dv[idx[k]] = x[r]; dS[k] = x[r]; }
-                }
+            for (int m = 0; m < kBwdSlots; ++m) {
+                const int k = lane + 32 * m;
+                if (k < nF) { dv[idx[k]] = zt[m]; dS[k] = zt[m]; }
             }
         }
     }

@@ -105,14 +105,19 @@ static size_t mk_smem_bytes(int N, int LD, int AS, int CH, int tsize, bool globa
 // ------------------------------------------------------------------------------------------------
 constexpr int kSmallElemsMax = 8;   // elements per thread (variants with 2, 4 and 8 slots)
 
+// number of register slots the augmented triangle of an n x n system needs: the matrix part is enumerated as a
+// folded rectangle (row r of the rectangle = matrix row n-1-r followed by matrix row r, n+1 entries), the two
+// right-hand-side rows follow.  The fold makes element -> (i,j) two multiplications instead of a square root.
+__host__ __device__ __forceinline__ int small_system_elems(int n) { return ((n + 1) >> 1) * (n + 1) + 2 * n; }
+
 template <typename T, int kThreads>
-__device__ __forceinline__ bool small_system_fits(int n) { return n * (n + 1) / 2 + 2 * n <= kThreads * kSmallElemsMax; }
+__device__ __forceinline__ bool small_system_fits(int n) { return small_system_elems(n) <= kThreads * kSmallElemsMax; }
 
 template <typename T, int kThreads, int kSmallElems, typename Init>
 __device__ __forceinline__ int factor_small_n(T *Lb, int ld, int nF, T *dinv, T dmin, Init init) {
     const int tid = threadIdx.x;
-    const int E = nF * (nF + 1) / 2 + 2 * nF;
-    const int colh = nF + 2;   // column j holds rows j .. nF+1
+    const int np1 = nF + 1, EM = ((nF + 1) >> 1) * np1, E = EM + 2 * nF;
+    const float inv_np1 = 1.f / (float)np1, inv_n = 1.f / (float)nF;
     T v[kSmallElems];
     int ii[kSmallElems], jj[kSmallElems];
 #pragma unroll
@@ -120,15 +125,17 @@ __device__ __forceinline__ int factor_small_n(T *Lb, int ld, int nF, T *dinv, T 
         const int e = tid + m * kThreads;
         ii[m] = 0; jj[m] = -1; v[m] = T(0);
         if (e < E) {
-            // column-major enumeration: offset(j) = j*colh - j(j-1)/2
-            const float bq = (float)(2 * colh + 1);
-            int j = (int)((bq - sqrtf(bq * bq - 8.f * (float)e)) * 0.5f);
-            j = max(0, min(j, nF - 1));
-            while (j > 0 && j * colh - j * (j - 1) / 2 > e) --j;
-            while (j + 1 < nF && (j + 1) * colh - (j + 1) * j / 2 <= e) ++j;
-            const int i = j + (e - (j * colh - j * (j - 1) / 2));
-            ii[m] = i; jj[m] = j;
-            v[m] = init(i, j);
+            int i, j;
+            bool valid = true;
+            if (e < EM) {
+                const int r = (int)(((float)e + 0.5f) * inv_np1), c = e - r * np1;   // exact: e < 2^11, margin 0.5/np1
+                if (c < nF - r) { i = nF - 1 - r; j = c; }
+                else { i = r; j = c - (nF - r); valid = (r != nF - 1 - r); }             // odd n: the middle row folds onto itself
+            } else {
+                const int e2 = e - EM, q = (int)(((float)e2 + 0.5f) * inv_n);
+                i = nF + q; j = e2 - q * nF;
+            }
+            if (valid) { ii[m] = i; jj[m] = j; v[m] = init(i, j); }
         }
     }
     int lifted = 0;
@@ -140,7 +147,7 @@ __device__ __forceinline__ int factor_small_n(T *Lb, int ld, int nF, T *dinv, T 
         __syncthreads();
         T d = colk[k];
         if (!(d > dmin)) { d = dmin; lifted = 1; }
-        const T invd = T(1) / d;
+        const T invd = recipT(d);
         if (tid == 0) dinv[k] = invd;
 #pragma unroll
         for (int m = 0; m < kSmallElems; ++m)
@@ -154,7 +161,7 @@ __device__ __forceinline__ int factor_small_n(T *Lb, int ld, int nF, T *dinv, T 
 // and nF+1 the two right-hand sides.
 template <typename T, int kThreads, typename Init>
 __device__ __forceinline__ int factor_small(T *Lb, int ld, int nF, T *dinv, T dmin, Init init) {
-    const int E = nF * (nF + 1) / 2 + 2 * nF;
+    const int E = small_system_elems(nF);
     if (E <= 2 * kThreads) return factor_small_n<T, kThreads, 2>(Lb, ld, nF, dinv, dmin, init);
     if (E <= 4 * kThreads) return factor_small_n<T, kThreads, 4>(Lb, ld, nF, dinv, dmin, init);
     return factor_small_n<T, kThreads, 8>(Lb, ld, nF, dinv, dmin, init);

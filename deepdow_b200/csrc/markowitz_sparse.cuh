@@ -12,8 +12,8 @@
 // Per active-set iteration (one CTA of 128 threads per portfolio):
 //   lists      warp 0 compacts the free / capped sets and hands out candidate slots
 //   Gram       4x4 register tiles of a_s . a_c for the new candidates, rows split over 8 lanes per tile
-//   KKT solve  ONE warp (kkt_solve_warp): column-by-column LDL' in shared memory with the right-hand sides in
-//              registers; no block barrier inside
+//   KKT solve  all four warps factor the augmented triangle with every element in a register (one barrier per
+//              column); warp 0 then does the multiplier and the back substitution
 //   gradient   t = A w on the support, then g = 2 A't as a column pass with 16-byte loads, rows split over
 //              the thread groups and combined through shared memory
 #pragma once
@@ -179,43 +179,49 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fw
             for (int m = tid; m < nF; m += kThreads) s.sF[m] = s.slot[s.idx[m]];
             __syncthreads();
             DDW_PHASE(4);
-            if (nF > 32) {
-                // rare: all warps gather Q_FF from the candidate block into the factor area
-                for (int j = warp; j < nF; j += kThreads / 32) {
-                    const int sj = s.sF[j];
-                    for (int i = j + lane; i < nF; i += 32) {
-                        const int si = s.sF[i];
-                        Lb[j * LDC + i] = Qc[max(si, sj) * LDC + min(si, sj)];
-                    }
+            // all four warps factor the augmented triangle [Q_FF; rhs; 1'] (every element in a register of its owning
+            // thread, one block barrier per column), then warp 0 finishes: multiplier and back substitution.  A one-warp
+            // factorisation was tried in three forms (rows in registers with shuffles, with shared-memory broadcasts,
+            // and a loop over shared memory): a lone warp retires one instruction every 5-8 cycles on this dependent
+            // code, 15k cycles per solve at 21 free assets against ~7k for the four-warp form (tools/phase_timing.py).
+            auto init = [&](int i, int j) -> T {
+                if (i < nF) {
+                    const int sa = s.sF[i], sc = s.sF[j];
+                    return Qc[max(sa, sc) * LDC + min(sa, sc)];
+                }
+                if (i > nF) return T(1);
+                return rhs1(s.idx[j]);
+            };
+            if (small_system_fits<T, kThreads>(nF)) lifted |= factor_small<T, kThreads>(Lb, LDC, nF, s.dinv, dmin, init);
+            else {
+                for (int e = tid; e < nF * (nF + 2); e += kThreads) {
+                    const int j = e / (nF + 2), i = e - j * (nF + 2);
+                    if (i >= j) Lb[j * LDC + i] = init(i, j);
                 }
                 __syncthreads();
+                lifted |= factor_ldl<T, kThreads>(Lb, LDC, nF, 2, s.dinv, dmin);
             }
             DDW_PHASE(5);
-            // ONE warp solves; the other warps wait at the barrier below
             if (warp == 0) {
-                T nu;
-                if (nF <= 32) {
-                    // rows of Q_FF straight from the candidate block into registers
-                    T m[32];
-                    const int si = lane < nF ? s.sF[lane] : 0;
+                T s12 = T(0), s22 = T(0);
+                for (int k = lane; k < nF; k += 32) {
+                    const T y1 = Lb[k * LDC + nF], y2 = Lb[k * LDC + nF + 1], di = s.dinv[k];
+                    s12 = fma(y1 * y2, di, s12);
+                    s22 = fma(y2 * y2, di, s22);
+                }
+                s12 = warp_sum(s12); s22 = warp_sum(s22);
+                const T nu = (s12 - T(2) * c) / s22;
+                T zt[kCandSlots];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int sj = __shfl_sync(kFullMask, si, j);
-                        m[j] = (lane < nF && j <= lane && j < nF) ? Qc[max(si, sj) * LDC + min(si, sj)] : T(0);
-                    }
-                    T x = lane < nF ? rhs1(s.idx[lane]) : T(0);
-                    nu = kkt_solve_regs<T>(m, x, nF, c, dmin, Lb, LDC, s.dinv, s.part, lifted);   // part: free between column passes
-                    if (lane < nF) { s.wv[s.idx[lane]] = x; s.wF[lane] = x; }
-                } else {
-                    T x[kCandSlots];
+                for (int m = 0; m < kCandSlots; ++m) {
+                    const int k = lane + 32 * m;
+                    zt[m] = k < nF ? T(0.5) * (Lb[k * LDC + nF] - nu * Lb[k * LDC + nF + 1]) : T(0);
+                }
+                backsub_warp<T, kCandSlots>(Lb, LDC, nF, s.dinv, zt);
 #pragma unroll
-                    for (int r = 0; r < kCandSlots; ++r) x[r] = lane + 32 * r < nF ? rhs1(s.idx[lane + 32 * r]) : T(0);
-                    nu = kkt_solve_warp<T, kCandSlots>(Lb, LDC, nF, x, c, dmin, s.dinv, lifted);
-#pragma unroll
-                    for (int r = 0; r < kCandSlots; ++r) {
-                        const int k = lane + 32 * r;
-                        if (k < nF) { s.wv[s.idx[k]] = x[r]; s.wF[k] = x[r]; }
-                    }
+                for (int m = 0; m < kCandSlots; ++m) {
+                    const int k = lane + 32 * m;
+                    if (k < nF) { s.wv[s.idx[k]] = zt[m]; s.wF[k] = zt[m]; }
                 }
                 if (lane == 0) s.red[32] = nu;
             }

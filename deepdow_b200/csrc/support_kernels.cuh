@@ -206,9 +206,13 @@ __device__ __forceinline__ void gram_columns(const T *As, int N, const int *cols
 // ------------------------------------------------------------------------------------------------
 // Reduced KKT solve by ONE warp, no block barrier:  [[2 M, 1], [1', 0]] [x; nu] = [rhs; c]  with M (n x n, SPD,
 // n <= 32 NR) stored as a lower triangle in factor_ldl's layout (M(i,k) at Lb[k*ld + i]) and overwritten by its
-// unscaled LDL' factor.  Row i belongs to lane i % 32, slot i / 32: b1 holds rhs on entry and x on return, b2 is
-// scratch.  Same arithmetic as factor_ldl + backsub_warp, with the two right-hand sides carried in registers
-// (element k is broadcast by a shuffle instead of living in an extra matrix row).
+// unscaled LDL' factor.  Row i belongs to lane i % 32, slot i / 32: b1 holds rhs on entry and x on return.
+// Same arithmetic as factor_ldl + backsub_warp, with the two right-hand sides carried in registers.
+// The loops are compact (the whole solve is ~150 SASS instructions, resident in the instruction cache: the fully
+// unrolled register variant below executes each instruction once and is fetch bound when one warp runs it) and
+// the trailing update is batched by hand, four columns at a time: four broadcast loads of column-k entries and
+// the lane's four row elements first, then the FMAs, then the stores, so that one shared-memory round trip covers
+// four columns.  Up to three columns past n are read (never stored): they lie inside the caller's array.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int NR>
 __device__ __forceinline__ T kkt_solve_warp(T *Lb, int ld, int n, T (&b1)[NR], T c, T dmin, T *dinv_s, int &lifted) {
@@ -217,38 +221,41 @@ __device__ __forceinline__ T kkt_solve_warp(T *Lb, int ld, int n, T (&b1)[NR], T
 #pragma unroll
     for (int r = 0; r < NR; ++r) b2[r] = lane + 32 * r < n ? T(1) : T(0);
     for (int k = 0; k < n; ++k) {
-        const T *colk = Lb + k * ld;
+        T *colk = Lb + k * ld;
         T d = colk[k];
         if (!(d > dmin)) { d = dmin; lifted = 1; }
         const T invd = recipT(d);
         if (lane == 0) dinv_s[k] = invd;
-        // column k lives in registers for the whole step: its entries reach the other lanes by shuffle, so the
-        // only shared-memory traffic of the trailing update is each lane's own row (provably distinct addresses,
-        // which lets the compiler keep several columns in flight)
-        T ck[NR], li[NR];
+        T li[NR];
         T y1 = T(0), y2 = T(0);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             const int i = lane + 32 * r;
-            ck[r] = (i > k && i < n) ? colk[i] : T(0);
-            li[r] = ck[r] * invd;
+            li[r] = (i > k && i < n) ? colk[i] * invd : T(0);
             if (NR == 1 || (k >> 5) == r) { y1 = __shfl_sync(kFullMask, b1[r], k & 31); y2 = __shfl_sync(kFullMask, b2[r], k & 31); }
         }
 #pragma unroll
         for (int r = 0; r < NR; ++r) { b1[r] = fma(-li[r], y1, b1[r]); b2[r] = fma(-li[r], y2, b2[r]); }
-        T *colj = Lb + (k + 1) * ld;
-#pragma unroll 4
-        for (int j = k + 1; j < n; ++j, colj += ld) {
-            T cj = __shfl_sync(kFullMask, ck[0], j & 31);
-            if (NR > 1) {
+        for (int j0 = k + 1; j0 < n; j0 += 4) {
+            T cj[4], a[4][NR];
+            T *colj = Lb + j0 * ld;
 #pragma unroll
-                for (int r = 1; r < NR; ++r) { const T c2 = __shfl_sync(kFullMask, ck[r], j & 31); if ((j >> 5) == r) cj = c2; }
-            }
+            for (int q = 0; q < 4; ++q) cj[q] = colk[j0 + q];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const int i = lane + 32 * r;
-                if (i >= j && i < n) colj[i] = fma(-li[r], cj, colj[i]);
-            }
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < NR; ++r) a[q][r] = colj[q * ld + lane + 32 * r];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < NR; ++r) a[q][r] = fma(-li[r], cj[q], a[q][r]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const int i = lane + 32 * r;
+                    if (j0 + q < n && i >= j0 + q && i < n) colj[q * ld + i] = a[q][r];
+                }
         }
         __syncwarp();
     }

@@ -375,6 +375,12 @@ def main():
         fwd_bytes = (N * N + 2 * N + 2) * s * B       # read covmat_sqrt, rets, gamma, alpha; write w
         bwd_bytes = (2 * N * N + 3 * N + 2) * s * B
         dom_fwd = fwd_ms >= bwd_ms
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_final", "ncu_traffic.json")
+        if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+            tj = json.load(open(tpath))
+            tk = tj["markowitz_fwd_sparse_kernel" if dom_fwd else "markowitz_bwd_sparse_kernel"]
+            traffic, traffic_src = tk["dram_bytes_read"] + tk["dram_bytes_write"], tj["source"]
         ach = (fwd_bytes / (fwd_ms * 1e-3) if dom_fwd else bwd_bytes / (bwd_ms * 1e-3)) / 1e9
         steps_total = args.steps
         value = world * B * steps_total / (elapsed_ms * 1e-3)
@@ -403,7 +409,8 @@ def main():
             "fwd_only": {"value": world * B * steps_total / (fwd_only_ms * 1e-3), "unit": UNIT},
             "phase_ms": {"fwd": fwd_ms, "bwd": bwd_ms, "host_enqueue": cpu_enqueue_ms},
             "roofline": {"bound": "hbm", "kernel": "markowitz_fwd_sparse_kernel" if dom_fwd else "markowitz_bwd_sparse_kernel",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": fwd_bytes if dom_fwd else bwd_bytes,
                          "note": "solver is FP32/shared-memory/latency bound; HBM is the iteration-free ceiling"},

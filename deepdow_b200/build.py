@@ -51,7 +51,8 @@ def _deps(path, seen=None):
 
 def build(force=False, verbose=False):
     """Compile every .cu to an object (in parallel, only those whose own includes changed) and link the shared library."""
-    objdir = os.path.join(HERE, "build")
+    # debug (phase-timing) objects live apart from the product objects, so the two flag sets never mix
+    objdir = os.path.join(HERE, "build_dbg" if os.environ.get("DDW_PHASE_TIMING") else "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     jobs = []
@@ -71,12 +72,16 @@ def build(force=False, verbose=False):
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode != 0:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    if jobs or force or _stale(LIB, objs):
+    stamp = os.path.join(HERE, "build", ".linked_from")
+    last = open(stamp).read() if os.path.exists(stamp) else ""
+    if jobs or force or _stale(LIB, objs) or last != objdir:
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+        os.makedirs(os.path.dirname(stamp), exist_ok=True)
+        open(stamp, "w").write(objdir)
     return LIB
 
 

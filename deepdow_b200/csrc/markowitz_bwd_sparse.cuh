@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_bw
 
     const T *Cb = p.C + b * (long long)N * N;
     const long long gflat0 = (p.b0 + b) * (long long)N * N;
+    DDW_PHASE_INIT
+    DDW_PHASE_COUNT(11);
     const bool use_tma = stage_matrix_begin<T, kThreads>(As, Cb, N, mbar);
     // support list from the state saved by the forward: free assets first (ascending), then the capped ones
     if (warp == 0) {
@@ -85,8 +87,10 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_bw
     }
     const T alpha = p.alpha[b];
     stage_matrix_end<T, kThreads>(As, Cb, N, mbar, use_tma);
+    DDW_PHASE(0);
     apply_gamma_tiling<T, kThreads>(As, N, p.gamma, gflat0, p.Bmod);
     __syncthreads();
+    DDW_PHASE(1);
     const int nF = misc[0], nS = misc[0] + misc[1];
     if (nF > kBwdFreeMax) {
         // free set too large for this kernel: hand the portfolio to the dense backward
@@ -98,6 +102,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_bw
         // Q_FF = A_F' A_F + |alpha| I straight into the factor area (element (s,c) at Lb[c*LDC + s])
         gram_columns<T, kThreads>(As, N, idx, (const T *)nullptr, absT(alpha), 0, nF, Lb, 1, LDC);
         __syncthreads();
+        DDW_PHASE(2);
         T dmax = T(0);
         for (int i = tid; i < nF; i += kThreads) dmax = max(dmax, Lb[i * LDC + i]);
         dmax = warp_max(dmax);
@@ -114,6 +119,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_bw
             __syncthreads();
             factor_ldl<T, kThreads>(Lb, LDC, nF, 2, dinv, dmin);
         }
+        DDW_PHASE(3);
         if (warp == 0) {
             T s12 = T(0), s22 = T(0);
             for (int k = lane; k < nF; k += 32) {
@@ -138,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_bw
         }
     }
     __syncthreads();
+    DDW_PHASE(4);
     // d_rets, d_alpha
     T ldot = T(0);
     for (int i = tid; i < N; i += kThreads) { p.d_rets[b * N + i] = dv[i]; ldot = fma(dv[i], wv[i], ldot); }
@@ -163,6 +170,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_bw
         pv[k] = sp; qv[k] = sq;      // no free asset: d = 0 and every gradient vanishes
     }
     __syncthreads();
+    DDW_PHASE(5);
     if (p.vecs) for (int i = tid; i < N; i += kThreads) { p.vecs[(b * 2) * N + i] = pv[i]; p.vecs[(b * 2 + 1) * N + i] = qv[i]; }
     // d_covmat_sqrt = gamma_ * (-2) (p w' + q d'), flat over the N^2 elements so that every lane stores
     T *dC = p.d_C + b * (long long)N * N;
@@ -200,7 +208,19 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_bw
             gi += gstep; if (gi >= uB) gi -= uB;
         }
     }
+    DDW_PHASE(6);
 }
+
+#ifdef DDW_PHASE_TIMING
+}  // namespace ddw
+extern "C" int DDW_PHASE_EXPORT(unsigned long long *out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, ddw::ddw_phase_cycles, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(ddw::ddw_phase_cycles, z, sizeof(z)); }
+    return 0;
+}
+namespace ddw {
+#endif
 
 template <typename T> int launch_bwd_sparse(const MkBwdParams<T> &p, cudaStream_t st) {
     auto kb = markowitz_bwd_sparse_kernel<T, 128>;

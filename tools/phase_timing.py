@@ -26,3 +26,19 @@ tot = sum(buf[i] for i in range(9))
 for i in range(9):
     print(f"  {names[i]:16s} {buf[i]/n:9.0f} cycles/problem  {100*buf[i]/tot:5.1f}%")
 print(f"  total            {tot/n:9.0f} cycles/problem = {tot/n/1.965e3:.1f} us at 1965 MHz")
+
+# ---- backward
+G = torch.randn(B, N, generator=gen, device=dev)
+ins = [t.requires_grad_() for t in (rets, C, g, a)]
+for _ in range(3):
+    w = layer(*ins); torch.autograd.grad(w, ins, G)
+lib.ddw_debug_bwd_phases_f32(buf, 1)
+w = layer(*ins); torch.autograd.grad(w, ins, G)
+lib.ddw_debug_bwd_phases_f32(buf, 0)
+names = ["load(TMA)", "gamma+lists", "gram", "factor", "finish(backsub)", "d_rets+p,q", "dC write"]
+n = max(buf[11], 1)
+tot = sum(buf[i] for i in range(7))
+print("backward:")
+for i in range(7):
+    print(f"  {names[i]:16s} {buf[i]/n:9.0f} cycles/problem  {100*buf[i]/tot:5.1f}%")
+print(f"  total            {tot/n:9.0f} cycles/problem = {tot/n/1.965e3:.1f} us at 1965 MHz")

@@ -25,7 +25,7 @@ namespace ddw {
 
 constexpr int kCandMax = 48;
 constexpr int kCandLd = (kCandMax + 3) | 1;
-constexpr int kCandSlots = (kCandMax + 31) / 32;   // rows per lane in the one-warp KKT solve
+constexpr int kCandSlots = (kCandMax + 31) / 32;   // vector elements per lane in the one-warp back substitution
 
 template <typename T> struct SpSmem {
     unsigned long long *mbar;

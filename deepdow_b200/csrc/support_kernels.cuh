@@ -1,6 +1,8 @@
 // support_kernels.cuh -- building blocks of the sparse-support NumericalMarkowitz kernels (forward and backward):
 // A (gamma-tiled covmat_sqrt) sits in shared memory, row-major N x N, and everything is computed from gathered
-// columns of it -- column passes, 4x4 Gram tiles of selected columns, and a reduced KKT solve done by ONE warp.
+// columns of it -- column passes and 4x4 Gram tiles of selected columns.  (The reduced KKT solve is the four-warp
+// register factorisation of markowitz_common.cuh; the one-warp forms that were tried are recorded in
+// profiles/r01_final/phase_timing.txt and in the history of this file.)
 #pragma once
 #include "common.cuh"
 #include "linalg.cuh"
@@ -201,151 +203,6 @@ __device__ __forceinline__ void gram_columns(const T *As, int N, const int *cols
                 out[sx * rs + c * cs] = (c == sx) ? (qd ? qd[cols[sx]] : h2[y] + diag_add) : h2[y];
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Reduced KKT solve by ONE warp, no block barrier:  [[2 M, 1], [1', 0]] [x; nu] = [rhs; c]  with M (n x n, SPD,
-// n <= 32 NR) stored as a lower triangle in factor_ldl's layout (M(i,k) at Lb[k*ld + i]) and overwritten by its
-// unscaled LDL' factor.  Row i belongs to lane i % 32, slot i / 32: b1 holds rhs on entry and x on return.
-// Same arithmetic as factor_ldl + backsub_warp, with the two right-hand sides carried in registers.
-// The loops are compact (the whole solve is ~150 SASS instructions, resident in the instruction cache: the fully
-// unrolled register variant below executes each instruction once and is fetch bound when one warp runs it) and
-// the trailing update is batched by hand, four columns at a time: four broadcast loads of column-k entries and
-// the lane's four row elements first, then the FMAs, then the stores, so that one shared-memory round trip covers
-// four columns.  Up to three columns past n are read (never stored): they lie inside the caller's array.
-// ------------------------------------------------------------------------------------------------
-template <typename T, int NR>
-__device__ __forceinline__ T kkt_solve_warp(T *Lb, int ld, int n, T (&b1)[NR], T c, T dmin, T *dinv_s, int &lifted) {
-    const int lane = threadIdx.x & 31;
-    T b2[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) b2[r] = lane + 32 * r < n ? T(1) : T(0);
-    for (int k = 0; k < n; ++k) {
-        T *colk = Lb + k * ld;
-        T d = colk[k];
-        if (!(d > dmin)) { d = dmin; lifted = 1; }
-        const T invd = recipT(d);
-        if (lane == 0) dinv_s[k] = invd;
-        T li[NR];
-        T y1 = T(0), y2 = T(0);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int i = lane + 32 * r;
-            li[r] = (i > k && i < n) ? colk[i] * invd : T(0);
-            if (NR == 1 || (k >> 5) == r) { y1 = __shfl_sync(kFullMask, b1[r], k & 31); y2 = __shfl_sync(kFullMask, b2[r], k & 31); }
-        }
-#pragma unroll
-        for (int r = 0; r < NR; ++r) { b1[r] = fma(-li[r], y1, b1[r]); b2[r] = fma(-li[r], y2, b2[r]); }
-        for (int j0 = k + 1; j0 < n; j0 += 4) {
-            T cj[4], a[4][NR];
-            T *colj = Lb + j0 * ld;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) cj[q] = colk[j0 + q];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int r = 0; r < NR; ++r) a[q][r] = colj[q * ld + lane + 32 * r];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int r = 0; r < NR; ++r) a[q][r] = fma(-li[r], cj[q], a[q][r]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    const int i = lane + 32 * r;
-                    if (j0 + q < n && i >= j0 + q && i < n) colj[q * ld + i] = a[q][r];
-                }
-        }
-        __syncwarp();
-    }
-    // multiplier of the budget constraint, then back substitution
-    T s12 = T(0), s22 = T(0);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const int i = lane + 32 * r;
-        const T di = i < n ? dinv_s[i] : T(0);
-        s12 = fma(b1[r] * b2[r], di, s12);
-        s22 = fma(b2[r] * b2[r], di, s22);
-    }
-    s12 = warp_sum(s12); s22 = warp_sum(s22);
-    const T nu = (s12 - T(2) * c) / s22;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) b1[r] = lane + 32 * r < n ? T(0.5) * (b1[r] - nu * b2[r]) : T(0);
-    backsub_warp<T, NR>(Lb, ld, n, dinv_s, b1);
-    return nu;
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same solve for n <= 32 with the matrix in REGISTERS: lane i owns row i of the lower triangle
-// (m[j] = M(i,j) for j <= i; entries j > i are scratch, lanes >= n hold zeros) and element i of the right-hand
-// side.  Both loops are fully unrolled, so every register index is a compile-time constant.  At step k the lanes
-// publish column k (one store each) to `colbuf` (2 x 32 elements, 16-byte aligned, double buffered) and read it
-// back as 16-byte broadcasts: 8 loads deliver what 31 shuffles would, and the pivot arrives with them.  Measured
-// on B200: the shuffle formulation is bound by the SM-wide shuffle rate (one warp instruction per clock shared by
-// all resident CTAs) and took 7-10k cycles per solve at n = 21; this one has ~110 cycles of latency per column.
-// Columns are processed in blocks of 8 up to n rounded up (entries beyond n are zeros).
-// The factor is then published in factor_ldl's layout for the back substitution.  On return b1 holds x_i on
-// lane i < n; the multiplier nu is returned to every lane.
-// ------------------------------------------------------------------------------------------------
-#ifndef DDW_SUBPHASE
-#define DDW_SUBPHASE(id) do { } while (0)
-#define DDW_SUBPHASE_INIT
-#endif
-template <typename T>
-__device__ __forceinline__ T kkt_solve_regs(T (&m)[32], T &b1, int n, T c, T dmin, T *Lb, int ld, T *dinv_s, T *colbuf,
-                                            int &lifted) {
-    const int lane = threadIdx.x & 31;
-    const int nb = (n + 7) & ~7;
-    T b2 = lane < n ? T(1) : T(0), dinv = T(0);
-    DDW_SUBPHASE_INIT
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        if (k < n) {   // uniform
-            T *cb = colbuf + (k & 1) * 32;
-            const T mk = m[k];
-            cb[lane] = mk;
-            __syncwarp();
-            T d = cb[k];
-            if (!(d > dmin)) { d = dmin; lifted = 1; }
-            const T invd = recipT(d);
-            if (lane == k) dinv = invd;
-            const T li = lane > k ? mk * invd : T(0);   // zero keeps rows <= k (and idle lanes) untouched
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                if (8 * h + 7 > k && 8 * h < nb) {      // first test folds at compile time, second is uniform
-#pragma unroll
-                    for (int g = 2 * h; g < 2 * h + 2; ++g) {
-                        if (4 * g + 3 > k) {
-                            const Vec4<T> c4 = ld4(cb + 4 * g);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (4 * g + q > k) m[4 * g + q] = fma(-li, c4.v[q], m[4 * g + q]);
-                        }
-                    }
-                }
-            }
-            const T y1 = __shfl_sync(kFullMask, b1, k), y2 = __shfl_sync(kFullMask, b2, k);
-            b1 = fma(-li, y1, b1);
-            b2 = fma(-li, y2, b2);
-        }
-    }
-    DDW_SUBPHASE(13);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        if (k < n) {
-            if (lane >= k && lane < n) Lb[k * ld + lane] = m[k];
-        }
-    }
-    if (lane < n) dinv_s[lane] = dinv;
-    const T s12 = warp_sum(b1 * b2 * dinv), s22 = warp_sum(b2 * b2 * dinv);
-    const T nu = (s12 - T(2) * c) / s22;
-    T zt[1] = {lane < n ? T(0.5) * (b1 - nu * b2) : T(0)};
-    __syncwarp();
-    backsub_warp<T, 1>(Lb, ld, n, dinv_s, zt);
-    b1 = zt[0];
-    DDW_SUBPHASE(15);
-    return nu;
 }
 
 }  // namespace ddw

@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libddw_b200.so")
+LIB_PATH = os.environ.get("DDW_LIB_PATH") or os.path.join(_HERE, "libddw_b200.so")   # override: A/B builds (tools/ab_variants.sh)
 
 DDW_F32, DDW_F64 = 0, 1
 SHRINKAGE = {None: 0, "diagonal": 1, "identity": 2, "scaled_identity": 3}

@@ -19,11 +19,12 @@ constexpr int kBwdFreeMax = 48;
 constexpr int kBwdLd = (kBwdFreeMax + 3) | 1;
 constexpr int kBwdSlots = (kBwdFreeMax + 31) / 32;
 
-static size_t bs_smem_bytes(int N, int tsize) {
-    const int NP = round_up(N + 2, 32);
-    const size_t elems = (size_t)round_up(N * N, 4) + round_up(kBwdFreeMax * kBwdLd, 4) + 8 * (size_t)NP + 40;
-    return 16 + elems * tsize + ((size_t)NP + 8) * sizeof(int);
+constexpr int bs_round_up(int v, int m) { return (v + m - 1) / m * m; }
+constexpr size_t bs_smem_bytes(int N, int tsize) {
+    return 16 + ((size_t)bs_round_up(N * N, 4) + bs_round_up(kBwdFreeMax * kBwdLd, 4) + 8 * (size_t)bs_round_up(N + 2, 32) + 40) * tsize +
+           ((size_t)bs_round_up(N + 2, 32) + 8) * sizeof(int);
 }
+static_assert(4 * (bs_smem_bytes(100, 4) + 1024) <= 228 * 1024, "sparse backward kernel: n_assets=100 must fit 4 CTAs per SM");
 
 #ifdef DDW_MK_DEFINE_ELIGIBLE
 bool bwd_sparse_eligible(int N, int tsize, int smem_limit) {

@@ -323,8 +323,9 @@ __device__ __forceinline__ void diag_init_warp(const T *qdiag, int qstride, cons
     T nu = (sa - T(1)) / sb;
     nu = clampT(nu, lo, hi);
     T dxold = hi - lo, dx = dxold;
+    // keep this a loop (a single warp runs it; straight-line copies would be instruction-fetch bound)
+#pragma unroll 1
     for (int it = 0; it < 60; ++it) {
-        DDW_PHASE_COUNT(9);
         T sum = T(0), slope = T(0);
 #pragma unroll
         for (int m = 0; m < NREG; ++m) {

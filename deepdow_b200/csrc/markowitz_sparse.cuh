@@ -10,7 +10,7 @@
 // appended to a work list that the dense kernel then processes.
 //
 // Per active-set iteration (one CTA of 128 threads per portfolio):
-//   lists      warp 0 compacts the free / capped sets and hands out candidate slots
+//   lists      every warp compacts its 32 assets of the free / capped sets and hands out candidate slots
 //   Gram       4x4 register tiles of a_s . a_c for the new candidates, rows split over 8 lanes per tile
 //   KKT solve  all four warps factor the augmented triangle with every element in a register (one barrier per
 //              column); warp 0 then does the multiplier and the back substitution
@@ -30,15 +30,18 @@ constexpr int kCandSlots = (kCandMax + 31) / 32;   // vector elements per lane i
 template <typename T> struct SpSmem {
     unsigned long long *mbar;
     T *As, *Qc, *part, *r, *wv, *tv, *g, *qd, *dinv, *wF, *red;   // g aliases dinv (only used when no asset is free)
-    int *idx, *idxU, *slot, *sF, *cand, *misc;
+    int *idx, *idxU, *slot, *sF, *cand, *misc, *cnt;
     int8_t *st;
 };
 
-static size_t sp_smem_bytes(int N, int tsize) {
-    const int NP = round_up(N + 2, 32);
-    const size_t elems = (size_t)round_up(N * N, 4) + round_up(kCandMax * kCandLd, 4) + kPartElems + 6 * (size_t)NP + 40;
-    return 16 + elems * tsize + ((size_t)3 * NP + 64 + 64 + 8) * sizeof(int) + NP;
+constexpr int sp_round_up(int v, int m) { return (v + m - 1) / m * m; }
+constexpr size_t sp_smem_bytes(int N, int tsize) {
+    return 16 + ((size_t)sp_round_up(N * N, 4) + sp_round_up(kCandMax * kCandLd, 4) + kPartElems + 6 * (size_t)sp_round_up(N + 2, 32) + 40) * tsize +
+           ((size_t)3 * sp_round_up(N + 2, 32) + 64 + 64 + 8) * sizeof(int) + sp_round_up(N + 2, 32);
 }
+// the headline shape (n_assets = 100, float) lives on 4 resident CTAs per SM: 228 KB of shared memory per SM, 1 KB
+// reserved per CTA.  64 bytes more once cost 40 us per 4096 portfolios (measured) -- keep it a compile-time fact.
+static_assert(4 * (sp_smem_bytes(100, 4) + 1024) <= 228 * 1024, "sparse forward kernel: n_assets=100 must fit 4 CTAs per SM");
 
 #ifdef DDW_MK_DEFINE_ELIGIBLE
 // sparse-support kernel first whenever A (4 N^2 bytes) fits shared memory with room for >= 2 CTAs per SM
@@ -71,12 +74,15 @@ template <typename T> __device__ __forceinline__ SpSmem<T> sp_carve(unsigned cha
     s.cand = q; q += 64;
     s.sF = q; q += 64;
     s.misc = q; q += 8;
+    s.cnt = reinterpret_cast<int *>(s.red);   // 12 ints over red[0..], which the sparse kernel uses only from index 32 up:
+                                              // 64 more bytes would drop the SM from 4 resident CTAs to 3 (4 x (57.3 KB + 1 KB) = 228 KB)
     s.st = reinterpret_cast<int8_t *>(q);
     return s;
 }
 
 template <typename T, int kThreads, int NREG>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fwd_sparse_kernel(MkFwdParams<T> p) {
+    static_assert(kThreads == 128, "the list phase maps one thread to one asset (n_assets <= 128)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const long long b = blockIdx.x;
     const int N = p.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -120,28 +126,36 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fw
     const T dmin = T(4) * Num<T>::eps() * s.red[33] + Num<T>::tiny();
     const T tolw = T(8) * Num<T>::eps();
     int lifted = 0, converged = 0, bail = 0;
+#pragma unroll 1
     for (int it = 0; it < kMaxPdas; ++it) {
-        // (a) lists of free / capped assets; first-time free assets get a candidate slot
-        if (warp == 0) {
-            int nf = 0, nu = 0;
-            const int nc0 = s.misc[3];
-            int nc = nc0;
-            for (int base = 0; base < N; base += 32) {
-                const int i = base + lane;
-                const int v = i < N ? (int)s.st[i] : 2;
-                const unsigned lt = (1u << lane) - 1u;
-                const unsigned mf = __ballot_sync(kFullMask, v == 0), mu = __ballot_sync(kFullMask, v == 1);
-                if (v == 0) s.idx[nf + __popc(mf & lt)] = i;
-                if (v == 1) s.idxU[nu + __popc(mu & lt)] = i;
-                const bool need = v == 0 && s.slot[i] < 0;
-                const unsigned mn = __ballot_sync(kFullMask, need);
-                if (need) {
-                    const int sl = nc + __popc(mn & lt);
-                    if (sl < kCandMax) { s.slot[i] = sl; s.cand[sl] = i; }
-                }
-                nf += __popc(mf); nu += __popc(mu); nc += __popc(mn);
+        // (a) lists of free / capped assets; first-time free assets get a candidate slot.  Warp w owns assets
+        // 32w .. 32w+31 (n_assets <= 128 here): ballots, per-warp counts through shared memory, then each warp
+        // writes its part of the lists at its prefix offset (same order as a serial scan)
+        {
+            const int i = tid;                       // kThreads == 128 covers every asset
+            const int v = i < N ? (int)s.st[i] : 2;
+            const bool need = v == 0 && s.slot[i < N ? i : 0] < 0;
+            const unsigned lt = (1u << lane) - 1u;
+            const unsigned mf = __ballot_sync(kFullMask, v == 0), mu = __ballot_sync(kFullMask, v == 1);
+            const unsigned mn = __ballot_sync(kFullMask, need);
+            if (lane == 0) { s.cnt[3 * warp] = __popc(mf); s.cnt[3 * warp + 1] = __popc(mu); s.cnt[3 * warp + 2] = __popc(mn); }
+            __syncthreads();
+            int of = 0, ou = 0, on = 0, nf = 0, nu = 0, nn = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < kThreads / 32; ++w2) {
+                const int cf = s.cnt[3 * w2], cu = s.cnt[3 * w2 + 1], cn = s.cnt[3 * w2 + 2];
+                if (w2 < warp) { of += cf; ou += cu; on += cn; }
+                nf += cf; nu += cu; nn += cn;
             }
-            if (lane == 0) { s.misc[0] = nf; s.misc[1] = nu; s.misc[2] = nc0; s.misc[3] = nc; }
+            const int nc0 = s.misc[3];
+            if (v == 0) s.idx[of + __popc(mf & lt)] = i;
+            if (v == 1) s.idxU[ou + __popc(mu & lt)] = i;
+            if (need) {
+                const int sl = nc0 + on + __popc(mn & lt);
+                if (sl < kCandMax) { s.slot[i] = sl; s.cand[sl] = i; }
+            }
+            __syncthreads();     // every thread has read misc[3] before it is advanced
+            if (tid == 0) { s.misc[0] = nf; s.misc[1] = nu; s.misc[2] = nc0; s.misc[3] = nc0 + nn; }
         }
         for (int i = tid; i < N; i += kThreads) s.wv[i] = s.st[i] > 0 ? u : T(0);
         __syncthreads();

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) capped_simplex_fwd_kernel(RowP
     T tau = vmax - (u < T(1) ? u : T(1));
     if (tau < lo) tau = lo;
     T dxold = hi - lo, dx = dxold;
+#pragma unroll 1
     for (int it = 0; it < 200; ++it) {
         T sumF = T(0);
         int cntF = 0, cntU = 0;

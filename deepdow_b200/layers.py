@@ -123,6 +123,26 @@ class _MarkowitzFn(torch.autograd.Function):
         return d_rets, d_cov, d_gamma, d_alpha, None, None, None
 
 
+class _MarkowitzHostFn(torch.autograd.Function):
+    """CPU tensors in, CPU tensors out, solved on the GPU through the host-buffer pipeline (opt-in, see
+    ``NumericalMarkowitz.host_device``).  The backward re-streams the batch (forward + backward in one pass of
+    ``ddw_markowitz_host_step``): the step is PCIe bound, so recomputing the forward costs no extra transfer of w."""
+
+    @staticmethod
+    def forward(ctx, rets, covmat_sqrt, gamma_sqrt, alpha, pipe):
+        out = pipe.step(rets, covmat_sqrt, gamma_sqrt, alpha)
+        ctx.save_for_backward(rets, covmat_sqrt, gamma_sqrt, alpha)
+        ctx.pipe = pipe
+        ctx.mark_non_differentiable(out.status)
+        return out.w, out.status
+
+    @staticmethod
+    def backward(ctx, grad_w, _grad_status):
+        rets, covmat_sqrt, gamma_sqrt, alpha = ctx.saved_tensors
+        out = ctx.pipe.step(rets, covmat_sqrt, gamma_sqrt, alpha, grad_w.contiguous())
+        return out.d_rets, out.d_covmat_sqrt, out.d_gamma_sqrt, out.d_alpha, None
+
+
 class NumericalMarkowitz(nn.Module):
     """Convex optimization layer stylized into portfolio optimization problem.
 
@@ -155,6 +175,11 @@ class NumericalMarkowitz(nn.Module):
         self.check_status = "lazy"
         self.last_status = None
         self._watch = _StatusWatch()
+        # Opt-in for callers whose tensors live on the host (the reference takes CPU tensors): set to a CUDA device
+        # ("cuda:0") and CPU inputs are streamed through that GPU by the host-buffer pipeline (deepdow_b200.host),
+        # CPU tensors come back.  None (default): CPU tensors are rejected -- there is no CPU compute path.
+        self.host_device = None
+        self._host_pipe = None
 
     def forward(self, rets, covmat_sqrt, gamma_sqrt, alpha):
         """Same arguments as the reference (allocate.py:240-273).
@@ -176,6 +201,14 @@ class NumericalMarkowitz(nn.Module):
                 # the box leaves no fully invested portfolio: the reference's solver raises here too
                 raise SolverError(f"infeasible: n_assets * max_weight = {n_assets * float(self.max_weight):g} < 1")
         dtype = rets.dtype
+        if self.host_device is not None and not rets.is_cuda:
+            from .host import MarkowitzHostPipeline        # late import: host.py imports this module
+            if self._host_pipe is None or self._host_pipe.device != torch.device(self.host_device):
+                self._host_pipe = MarkowitzHostPipeline(self.n_assets, self.max_weight, device=self.host_device)
+            w, status = _MarkowitzHostFn.apply(rets, covmat_sqrt.to(dtype), gamma_sqrt.reshape(-1).to(dtype),
+                                               alpha.reshape(-1).to(dtype), self._host_pipe)
+            self.last_status = status
+            return w
         w, status = _MarkowitzFn.apply(rets, covmat_sqrt.to(dtype), gamma_sqrt.reshape(-1).to(dtype),
                                        alpha.reshape(-1).to(dtype), self.max_weight, self.check_status, self._watch)
         self.last_status = status
@@ -198,6 +231,7 @@ class NumericalMarkowitz(nn.Module):
         state = self.__dict__.copy()
         state["last_status"] = None
         state["_watch"] = None            # pinned buffers and CUDA events are not picklable
+        state["_host_pipe"] = None        # streams and device scratch are rebuilt on demand
         return state
 
     def __setstate__(self, state):

@@ -113,3 +113,25 @@ def test_host_pipeline_errors():
     rets, C, g, a, G = problems(8, 10, 3)
     out = pipe.step(*[torch.tensor(x) for x in (rets, C, g, a, G)])
     assert abs(float(out.w.sum()) - 8.0) < 1e-4
+
+
+def test_module_streams_cpu_tensors_when_opted_in():
+    """NumericalMarkowitz.host_device: CPU tensors in, CPU tensors out (same dtype/device as the inputs, like the
+    reference, tests/test_layers.py:447-448), gradients equal to the device path; default stays "CUDA tensors only"."""
+    from deepdow_b200._C import ExtensionError
+    B, N, u = 40, 16, 0.4
+    rets, C, g, a, G = problems(B, N, 11)
+    ref = device_reference(rets, C, g, a, G, u)
+    layer = NumericalMarkowitz(N, u)
+    cpu = [torch.tensor(x, requires_grad=True) for x in (rets, C, g, a)]
+    with pytest.raises(ExtensionError):
+        layer(*cpu)
+    layer.host_device = DEV
+    w = layer(*cpu)
+    assert w.device.type == "cpu" and w.dtype == torch.float32 and torch.equal(w.detach(), ref[0])
+    (w * torch.tensor(G)).sum().backward()
+    assert torch.equal(cpu[0].grad, ref[1]) and torch.equal(cpu[1].grad, ref[2]) and torch.equal(cpu[3].grad, ref[4])
+    assert (cpu[2].grad - ref[3]).abs().max() <= 1e-5 * max(1.0, float(ref[3].abs().max()))
+    import pickle
+    layer2 = pickle.loads(pickle.dumps(layer))
+    assert torch.equal(layer2(*[t.detach() for t in cpu]), ref[0])

@@ -225,6 +225,43 @@ def test_markowitz_full_size_properties():
     assert np.abs(w[idx].double().cpu().numpy() - w_ref).max() < 1e-5
 
 
+def test_markowitz_config5_full_size_properties():
+    """Config 5 per-GPU share at full size (B=1024, N=500, lookback 250): CovarianceMatrix(sqrt) -> NumericalMarkowitz
+    through the dense kernels with Q in the global workspace; KKT certificate in float64 on the GPU, fwd + bwd."""
+    B, L, N, u = 1024, 250, 500, 0.05
+    gen = torch.Generator(device=DEV).manual_seed(5000)
+    x = torch.randn(B, L, N, generator=gen, device=DEV) * 0.01
+    C = CovarianceMatrix(sqrt=True, shrinkage_strategy="diagonal")(x)
+    rets = torch.randn(B, N, generator=gen, device=DEV) * 0.01
+    g = torch.ones(B, device=DEV)
+    a = torch.ones(B, device=DEV)
+    layer = NumericalMarkowitz(N, u)
+    ins = [t.requires_grad_() for t in (rets, C.detach().clone(), g, a)]
+    w = layer(*ins)
+    layer.synchronize_status()
+    assert int((layer.last_status & 12).ne(0).sum()) == 0        # nothing infeasible / inexact
+    wd, Cd = w.detach().double(), ins[1].detach().double()
+    Aw = (Cd @ wd[..., None])[..., 0]
+    h = 2 * ((Cd.transpose(1, 2) @ Aw[..., None])[..., 0] + wd) - ins[0].detach().double()
+    free = (wd > 1e-7) & (wd < u - 1e-7)
+    nu = -(h * free).sum(1) / free.sum(1).clamp(min=1)
+    grad = h + nu[:, None]
+    res = torch.where(free, grad.abs(), torch.where(wd <= 1e-7, (-grad).clamp(min=0), grad.clamp(min=0)))
+    assert (wd.sum(1) - 1).abs().max() < 1e-5
+    assert wd.min() >= 0 and wd.max() <= u + 1e-7
+    assert res.max() < 1e-4, res.max()
+    G = torch.randn(B, N, generator=gen, device=DEV)
+    grads = torch.autograd.grad(w, ins, G)
+    assert all(torch.isfinite(t).all() for t in grads)
+    # the adjoint of a budget-preserving map: d_rets sums to zero over each portfolio (1'd = 0)
+    assert grads[0].double().sum(1).abs().max() < 1e-4 * grads[0].abs().max().clamp(min=1.0)
+    # sample of problems against the oracle
+    idx = torch.arange(0, B, 256)
+    w_ref, *_ = oracle.markowitz_fwd(ins[0][idx].detach().cpu().numpy(), ins[1][idx].detach().cpu().numpy(),
+                                     np.ones(len(idx)), np.ones(len(idx)), u)
+    assert np.abs(w[idx].detach().double().cpu().numpy() - w_ref).max() < 1e-5
+
+
 # ------------------------------------------------------------------ sparsemax / softmax
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("B,N,u,scale", [(1024, 100, 1.0, 1.0), (1024, 100, 0.05, 10.0), (33, 5, 0.25, 1.0),

@@ -91,6 +91,25 @@ def require_cuda(*tensors):
                 f"got a tensor on {t.device}")
 
 
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(t):
+    """Context manager that makes `t`'s GPU the current CUDA device for the launch (kernels go to the current
+    device); free when it already is -- the common case pays one integer comparison."""
+    if t.device.index is None or t.device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(t.device)
+
+
 def aligned(t):
     """Contiguous and 16-byte aligned (the kernels use 128-bit loads/stores); copies only if needed."""
     if t is None:

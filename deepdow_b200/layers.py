@@ -85,9 +85,10 @@ class _MarkowitzFn(torch.autograd.Function):
         state = torch.empty((B, N), dtype=torch.int8, device=rets.device)
         status = torch.empty((B,), dtype=torch.int32, device=rets.device)
         ws = _workspace(lib.ddw_markowitz_workspace_bytes(B, N, dt), rets.device)
-        rc = lib.ddw_markowitz_fwd(_C.ptr(rets_c), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
-                                   float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status),
-                                   _C.ptr(ws), ws.numel(), _C.stream(rets.device))
+        with _C.device_guard(rets):
+            rc = lib.ddw_markowitz_fwd(_C.ptr(rets_c), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
+                                       float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status),
+                                       _C.ptr(ws), ws.numel(), _C.stream(rets.device))
         _C.check(rc, "ddw_markowitz_fwd")
         what = f"batch of {B}, n_assets={N}, max_weight={max_weight}"
         counter = ws[8:12].view(torch.int32)          # counter [2] of the workspace header (include/ddw.h)
@@ -97,7 +98,8 @@ class _MarkowitzFn(torch.autograd.Function):
             if bad:
                 raise SolverError(f"{bad} portfolio problems could not be solved ({what})")
         elif check_status == "lazy":
-            watch.push(counter, what)
+            with _C.device_guard(rets):              # the event is recorded on this tensor's device
+                watch.push(counter, what)
         ctx.save_for_backward(w, state, cov_c, gam_c, alp_c)
         ctx.max_weight = float(max_weight)
         ctx.mark_non_differentiable(status)
@@ -116,9 +118,10 @@ class _MarkowitzFn(torch.autograd.Function):
         need_gamma = ctx.needs_input_grad[2]
         d_gamma = torch.empty_like(gam_c) if need_gamma else None
         ws = _workspace(lib.ddw_markowitz_workspace_bytes(B, N, dt), w.device)
-        rc = lib.ddw_markowitz_bwd(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
-                                   ctx.max_weight, B, N, dt, _C.ptr(d_rets), _C.ptr(d_cov), _C.ptr(d_gamma),
-                                   _C.ptr(d_alpha), _C.ptr(ws), ws.numel(), _C.stream(w.device))
+        with _C.device_guard(w):
+            rc = lib.ddw_markowitz_bwd(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
+                                       ctx.max_weight, B, N, dt, _C.ptr(d_rets), _C.ptr(d_cov), _C.ptr(d_gamma),
+                                       _C.ptr(d_alpha), _C.ptr(ws), ws.numel(), _C.stream(w.device))
         _C.check(rc, "ddw_markowitz_bwd")
         return d_rets, d_cov, d_gamma, d_alpha, None, None, None
 
@@ -253,8 +256,9 @@ class _RowFn(torch.autograd.Function):
         t_c = None if temperature is None else temperature.to(x.dtype).contiguous()
         w = torch.empty_like(x_c)
         fwd = lib.ddw_capped_simplex_fwd if kind == "sparsemax" else lib.ddw_capped_softmax_fwd
-        rc = fwd(_C.ptr(x_c), _C.ptr(t_c), float(temperature_scalar), float(max_weight), B, N, dt, _C.ptr(w),
-                 _C.stream())
+        with _C.device_guard(x):
+            rc = fwd(_C.ptr(x_c), _C.ptr(t_c), float(temperature_scalar), float(max_weight), B, N, dt, _C.ptr(w),
+                     _C.stream(x.device))
         _C.check(rc, f"ddw_capped_{kind}_fwd")
         ctx.save_for_backward(w, x_c, t_c)
         ctx.args = (float(temperature_scalar), float(max_weight), kind)
@@ -271,8 +275,9 @@ class _RowFn(torch.autograd.Function):
         d_x = torch.empty_like(w)
         d_t = torch.empty_like(t_c) if (t_c is not None and ctx.needs_input_grad[1]) else None
         bwd = lib.ddw_capped_simplex_bwd if kind == "sparsemax" else lib.ddw_capped_softmax_bwd
-        rc = bwd(_C.ptr(g), _C.ptr(w), _C.ptr(x_c), _C.ptr(t_c), tscalar, max_weight, B, N, dt, _C.ptr(d_x),
-                 _C.ptr(d_t), _C.stream())
+        with _C.device_guard(w):
+            rc = bwd(_C.ptr(g), _C.ptr(w), _C.ptr(x_c), _C.ptr(t_c), tscalar, max_weight, B, N, dt, _C.ptr(d_x),
+                     _C.ptr(d_t), _C.stream(w.device))
         _C.check(rc, f"ddw_capped_{kind}_bwd")
         return d_x, d_t, None, None, None
 
@@ -370,8 +375,9 @@ class _CovarianceFn(torch.autograd.Function):
             eigvec = torch.empty((B, N, N), dtype=x.dtype, device=x.device)
             eigval = torch.empty((B, N), dtype=x.dtype, device=x.device)
         ws = _workspace(lib.ddw_covariance_workspace_bytes(B, L, N, dt, int(do_sqrt)), x.device)
-        rc = lib.ddw_covariance_fwd(_C.ptr(x_c), _C.ptr(coef_c), strategy, int(do_sqrt), B, L, N, dt, _C.ptr(out),
-                                    _C.ptr(eigvec), _C.ptr(eigval), None, _C.ptr(ws), ws.numel(), _C.stream())
+        with _C.device_guard(x):
+            rc = lib.ddw_covariance_fwd(_C.ptr(x_c), _C.ptr(coef_c), strategy, int(do_sqrt), B, L, N, dt, _C.ptr(out),
+                                        _C.ptr(eigvec), _C.ptr(eigval), None, _C.ptr(ws), ws.numel(), _C.stream(x.device))
         _C.check(rc, "ddw_covariance_fwd")
         ctx.save_for_backward(x_c, coef_c, eigvec, eigval)
         ctx.args = (strategy, int(do_sqrt))
@@ -388,9 +394,10 @@ class _CovarianceFn(torch.autograd.Function):
         d_x = torch.empty_like(x_c)
         d_coef = torch.empty_like(coef_c) if (coef_c is not None and ctx.needs_input_grad[1]) else None
         ws = _workspace(lib.ddw_covariance_workspace_bytes(B, L, N, dt, do_sqrt), x_c.device)
-        rc = lib.ddw_covariance_bwd(_C.ptr(g), _C.ptr(x_c), _C.ptr(coef_c), strategy, do_sqrt, _C.ptr(eigvec),
-                                    _C.ptr(eigval), B, L, N, dt, _C.ptr(d_x), _C.ptr(d_coef), _C.ptr(ws),
-                                    ws.numel(), _C.stream())
+        with _C.device_guard(x_c):
+            rc = lib.ddw_covariance_bwd(_C.ptr(g), _C.ptr(x_c), _C.ptr(coef_c), strategy, do_sqrt, _C.ptr(eigvec),
+                                        _C.ptr(eigval), B, L, N, dt, _C.ptr(d_x), _C.ptr(d_coef), _C.ptr(ws),
+                                        ws.numel(), _C.stream(x_c.device))
         _C.check(rc, "ddw_covariance_bwd")
         return d_x, d_coef, None, None
 
@@ -409,8 +416,9 @@ class _PsdSqrtFn(torch.autograd.Function):
             eigvec = torch.empty_like(m_c)
             eigval = torch.empty((B, N), dtype=m.dtype, device=m.device)
         ws = _workspace(lib.ddw_covariance_workspace_bytes(B, 2, N, dt, 1), m.device)
-        rc = lib.ddw_psd_sqrt_fwd(_C.ptr(m_c), B, N, dt, _C.ptr(out), _C.ptr(eigvec), _C.ptr(eigval), _C.ptr(ws),
-                                  ws.numel(), _C.stream())
+        with _C.device_guard(m):
+            rc = lib.ddw_psd_sqrt_fwd(_C.ptr(m_c), B, N, dt, _C.ptr(out), _C.ptr(eigvec), _C.ptr(eigval), _C.ptr(ws),
+                                      ws.numel(), _C.stream(m.device))
         _C.check(rc, "ddw_psd_sqrt_fwd")
         ctx.save_for_backward(eigvec, eigval)
         return out
@@ -424,8 +432,9 @@ class _PsdSqrtFn(torch.autograd.Function):
         g = _C.aligned(grad_out)
         d_m = torch.empty_like(eigvec)
         ws = _workspace(lib.ddw_covariance_workspace_bytes(B, 2, N, dt, 1), eigvec.device)
-        rc = lib.ddw_psd_sqrt_bwd(_C.ptr(g), _C.ptr(eigvec), _C.ptr(eigval), B, N, dt, _C.ptr(d_m), _C.ptr(ws),
-                                  ws.numel(), _C.stream())
+        with _C.device_guard(eigvec):
+            rc = lib.ddw_psd_sqrt_bwd(_C.ptr(g), _C.ptr(eigvec), _C.ptr(eigval), B, N, dt, _C.ptr(d_m), _C.ptr(ws),
+                                      ws.numel(), _C.stream(eigvec.device))
         _C.check(rc, "ddw_psd_sqrt_bwd")
         return d_m
 

@@ -76,3 +76,26 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "ddw_oracle" not in text, f
+
+
+def test_chunked_and_host_entry_points_validate_without_gpu(lib):
+    # chunk outside the batch
+    rc = lib.ddw_markowitz_fwd_chunk(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 1.0,
+                                     8, 5, 0, 10, 4, ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), None, 0, None)
+    assert rc == -1 and b"outside the batch" in lib.ddw_last_error()
+    rc = lib.ddw_markowitz_bwd_chunk(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16),
+                                     ctypes.c_void_p(16), ctypes.c_void_p(16), 1.0, 8, 5, 0, 10, -1, ctypes.c_void_p(16),
+                                     ctypes.c_void_p(16), None, 0, ctypes.c_void_p(16), None, 0, None)
+    assert rc == -1 and b"outside the batch" in lib.ddw_last_error()
+    # host step: argument errors are reported before any CUDA call
+    z = ctypes.c_void_p(64)
+    assert lib.ddw_markowitz_host_step(None, z, z, z, z, None, 1.0, 4, 5, 9, 2, z, z, None, None, None, None, z, 0, None) == -1
+    assert b"dtype" in lib.ddw_last_error()
+    assert lib.ddw_markowitz_host_step(None, z, z, z, z, None, 1.0, 4, 5000, 0, 2, z, z, None, None, None, None, z, 0, None) == -2
+    assert lib.ddw_markowitz_host_step(None, z, z, z, z, None, 1.0, 4, 5, 0, 2, z, z, None, None, None, None, z, 0, None) == -1
+    assert b"null" in lib.ddw_last_error()                      # no pipeline handle
+    assert lib.ddw_markowitz_host_step(None, z, z, z, z, None, 1.0, 0, 5, 0, 2, z, z, None, None, None, None, z, 0, None) == 0   # empty batch
+    assert lib.ddw_markowitz_host_scratch_bytes(4096, 100, 0, 128) > 3 * 128 * 100 * 100 * 4
+    assert lib.ddw_markowitz_host_scratch_bytes(0, 100, 0, 128) == 0
+    assert lib.ddw_host_pipeline_graph_launches(None) == 0
+    lib.ddw_host_pipeline_destroy(None)                         # no-op

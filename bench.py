@@ -257,7 +257,7 @@ def main():
     # the same step captured once into a CUDA graph and replayed: the layer's fwd+bwd is a fixed sequence of 6
     # kernels + 3 memsets, and at ~0.6 ms per step the Python side (autograd engine, ctypes, allocator: ~0.3 ms)
     # is of the same order as the kernels.  `value` is the replayed step; the eager loop is reported beside it.
-    graph_ms, graph_note = None, "eager launches (graph capture unavailable)"
+    graph_ms, fwd_graph_ms, graph_note = None, None, "eager launches (graph capture unavailable)"
     try:
         layer.check_status = False              # the status copy to pinned memory + event is not capturable
         side = torch.cuda.Stream()
@@ -279,6 +279,24 @@ def main():
         g1.record()
         barrier()
         graph_ms = g0.elapsed_time(g1)
+        # forward alone, replayed the same way: the per-kernel times behind `roofline` must not contain host gaps
+        detached_g = [t.detach() for t in inputs]
+        with torch.cuda.stream(side), torch.no_grad():
+            side.wait_stream(torch.cuda.current_stream())
+            layer(*detached_g)
+        torch.cuda.current_stream().wait_stream(side)
+        fgraph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(fgraph):
+            w_f = layer(*detached_g)
+        for _ in range(3):
+            fgraph.replay()
+        barrier()
+        g0.record()
+        for _ in range(args.steps):
+            fgraph.replay()
+        g1.record()
+        barrier()
+        fwd_graph_ms = g0.elapsed_time(g1) / args.steps
         w_e, grads_e = step_device()
         torch.cuda.synchronize()
         assert torch.equal(w_g, w_e) and torch.equal(grads_g[1], grads_e[1]), "graph replay and eager step disagree"
@@ -374,6 +392,9 @@ def main():
         s = 4
         fwd_bytes = (N * N + 2 * N + 2) * s * B       # read covmat_sqrt, rets, gamma, alpha; write w
         bwd_bytes = (2 * N * N + 3 * N + 2) * s * B
+        if graph_ms is not None and fwd_graph_ms is not None:
+            # device-only durations (graph replays): forward alone, and the step minus the forward
+            fwd_ms, bwd_ms = fwd_graph_ms, graph_max / args.steps - fwd_graph_ms
         dom_fwd = fwd_ms >= bwd_ms
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "r01_final", "ncu_traffic.json")
@@ -407,7 +428,9 @@ def main():
                                  "markowitz_ipm_kernel (fallback list, empty here)", "markowitz_bwd_sparse_kernel",
                                  "markowitz_bwd_kernel (dense work list)", "markowitz_gamma_kernel"],
             "fwd_only": {"value": world * B * steps_total / (fwd_only_ms * 1e-3), "unit": UNIT},
-            "phase_ms": {"fwd": fwd_ms, "bwd": bwd_ms, "host_enqueue": cpu_enqueue_ms},
+            "phase_ms": {"fwd": fwd_ms, "bwd": bwd_ms, "host_enqueue": cpu_enqueue_ms,
+                         "source": "CUDA-graph replays (forward alone; step minus forward)" if graph_ms is not None
+                         else "CUDA events around the eager layer calls"},
             "roofline": {"bound": "hbm", "kernel": "markowitz_fwd_sparse_kernel" if dom_fwd else "markowitz_bwd_sparse_kernel",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "traffic_source": traffic_src,

@@ -66,6 +66,15 @@ template <typename T> __device__ __forceinline__ T absT(T v) { return v < 0 ? -v
 // correctly rounded reciprocal: one MUFU.RCP plus a fix-up for float instead of the generic division sequence
 __device__ __forceinline__ float recipT(float v) { return __frcp_rn(v); }
 __device__ __forceinline__ double recipT(double v) { return 1.0 / v; }
+// reciprocal without the denormal/overflow side path of __frcp_rn: hardware approximation + one Newton step
+// (for pivots of an SPD matrix that were already lifted to dmin; error below 1 ulp)
+__device__ __forceinline__ float recipFastT(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return fmaf(r, fmaf(-v, r, 1.0f), r);
+}
+__device__ __forceinline__ double recipFastT(double v) { return 1.0 / v; }
+
 __device__ __forceinline__ float rsqrtT(float v) { return rsqrtf(v); }
 __device__ __forceinline__ double rsqrtT(double v) { return rsqrt(v); }
 __device__ __forceinline__ float sqrtT(float v) { return sqrtf(v); }

@@ -145,13 +145,20 @@ __device__ __forceinline__ int factor_small_n(T *Lb, int ld, int nF, T *dinv, T 
         for (int m = 0; m < kSmallElems; ++m)
             if (jj[m] == k) colk[ii[m]] = v[m];
         __syncthreads();
+        // the column entries first, the pivot's reciprocal second: the loads do not wait for the reciprocal chain
+        T ci[kSmallElems], cj[kSmallElems];
+#pragma unroll
+        for (int m = 0; m < kSmallElems; ++m) {
+            const bool act = jj[m] > k;
+            ci[m] = act ? colk[ii[m]] : T(0);
+            cj[m] = act ? colk[jj[m]] : T(0);
+        }
         T d = colk[k];
         if (!(d > dmin)) { d = dmin; lifted = 1; }
-        const T invd = recipT(d);
+        const T invd = recipFastT(d);
         if (tid == 0) dinv[k] = invd;
 #pragma unroll
-        for (int m = 0; m < kSmallElems; ++m)
-            if (jj[m] > k) v[m] = fma(-colk[ii[m]], colk[jj[m]] * invd, v[m]);
+        for (int m = 0; m < kSmallElems; ++m) v[m] = fma(-ci[m], cj[m] * invd, v[m]);
     }
     __syncthreads();
     return lifted;

@@ -16,4 +16,20 @@ with torch.no_grad():
     e0.record()
     for _ in range(50): layer(rets, C, g, a)
     e1.record(); torch.cuda.synchronize()
-print(f"{os.environ.get('DDW_LIB_PATH', 'default'):50s} fwd {e0.elapsed_time(e1) / 50 * 1e3:.1f} us")
+    w = layer(rets, C, g, a)
+Q = C.double().transpose(1, 2) @ C.double() + torch.eye(N, device=dev, dtype=torch.float64)
+obj = ((w.double()[:, None, :] @ Q @ w.double()[:, :, None])[:, 0, 0] - (rets.double() * w.double()).sum(1)).sum().item()
+ins = [t.clone().requires_grad_() for t in (rets, C, g, a)]
+G = torch.randn(B, N, generator=gen, device=dev)
+for _ in range(3):
+    torch.autograd.grad(layer(*ins), ins, G)
+evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
+for e in evs:
+    wg = layer(*ins)
+    e[0].record(); grads = torch.autograd.grad(wg, ins, G); e[1].record()
+torch.cuda.synchronize()
+bwd_us = sum(a_.elapsed_time(b_) for a_, b_ in evs) / len(evs) * 1e3
+gsum = sum(float(t.double().abs().sum()) for t in grads)
+print(f"{os.path.basename(os.environ.get('DDW_LIB_PATH', 'default')):28s} fwd {e0.elapsed_time(e1) / 50 * 1e3:.1f} us   objective sum {obj:.9f}  "
+      f"budget err {float((w.double().sum(1) - 1).abs().max()):.1e}  status!=0 {int(layer.last_status.ne(0).sum())}  "
+      f"| bwd {bwd_us:.1f} us  |grads| {gsum:.6f}")

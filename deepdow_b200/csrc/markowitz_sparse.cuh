@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fw
         const int nF = s.misc[0], nU = s.misc[1], nc0 = s.misc[2], nc1 = s.misc[3];
         if (nc1 > kCandMax) { bail = 1; break; }
         // (b) Gram entries of the new candidates against all candidates
+        for (int m = tid; m < nF; m += kThreads) s.sF[m] = s.slot[s.idx[m]];   // candidate slots of the free assets
         if (nc1 > nc0) gram_columns<T, kThreads>(As, N, s.cand, s.qd, T(0), nc0, nc1, Qc, LDC, 1);
         // (c) t_U = A (u 1_U)
         if (nU > 0) {
@@ -190,8 +191,6 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fw
                 }
                 return acc;
             };
-            for (int m = tid; m < nF; m += kThreads) s.sF[m] = s.slot[s.idx[m]];
-            __syncthreads();
             DDW_PHASE(4);
             // all four warps factor the augmented triangle [Q_FF; rhs; 1'] (every element in a register of its owning
             // thread, one block barrier per column), then warp 0 finishes: multiplier and back substitution.  A one-warp

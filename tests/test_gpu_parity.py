@@ -123,6 +123,39 @@ def test_markowitz_vertex_degenerate_and_edge_cases(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_markowitz_backward_without_free_assets_and_with_many_capped(dtype):
+    """Backward edge cases of the sparse-support kernel: (i) no free asset at the optimum (all weight on capped assets):
+    every gradient is exactly zero; (ii) most of the weight on capped assets, a few free ones."""
+    rng = np.random.default_rng(12)
+    B, N, u = 16, 30, 0.2
+    rets = rng.standard_normal((B, N))
+    C = np.broadcast_to(np.eye(N) * 1e-3, (B, N, N)).copy()
+    g, a = np.ones(B), np.zeros(B)
+    G = rng.standard_normal((B, N))
+    w_ref, st_ref, *_ = oracle.markowitz_fwd(rets, C, g, a, u)
+    assert (st_ref == 0).sum() == 0                       # the case is what it claims to be
+    ins = [t(rets, dtype, True), t(C, dtype, True), t(g, dtype, True), t(a, dtype, True)]
+    w = NumericalMarkowitz(N, u)(*ins)
+    grads = torch.autograd.grad(w, ins, t(G, dtype))
+    assert all(float(x.abs().max()) == 0.0 for x in grads)
+    # (ii) strong returns, tight cap: ~18 of 64 assets at the cap, a few free
+    B, N, u = 24, 64, 0.05
+    rets, C, g, a = make_problems(rng, B, N, "sym", 1.0, 3.0, "rand")
+    G = rng.standard_normal((B, N))
+    w_ref, st_ref, kkt, _ = oracle.markowitz_fwd(rets, C, g, a, u)
+    assert (st_ref == 1).sum(1).min() >= 10
+    ref = oracle.markowitz_bwd(G, w_ref, st_ref, C, g, a, u)
+    ins = [t(rets, dtype, True), t(C, dtype, True), t(g, dtype, True), t(a, dtype, True)]
+    layer = NumericalMarkowitz(N, u)
+    w = layer(*ins)
+    assert np.abs(w.detach().double().cpu().numpy() - w_ref).max() < W_ATOL[dtype]
+    assert layer.solver_counters()[1] == 0                # stayed on the sparse-support kernel
+    grads = torch.autograd.grad(w, ins, t(G, dtype))
+    for name, got, want in zip(["rets", "covmat_sqrt", "gamma", "alpha"], grads, ref):
+        assert rel_err(got, want) < G_RTOL[dtype], (name, rel_err(got, want))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_markowitz_hard_problems_use_fallback_and_stay_exact(dtype):
     """Ill-conditioned Q where the active set can cycle: the interior-point fallback must kick in."""
     rng = np.random.default_rng(12)

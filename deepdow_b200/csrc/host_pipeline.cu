@@ -28,8 +28,17 @@ template <typename T>
 int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, const void *, const void *, long long,
                     int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int);
 
-constexpr int kSlots = 4;     // chunk slots in the device scratch
-constexpr int kRun = 2;       // solver streams: consecutive chunks are solved concurrently (a chunk alone cannot fill the GPU)
+constexpr int kMaxSlots = 8, kMaxRun = 4;
+// chunk slots in the device scratch / solver streams (consecutive chunks are solved concurrently: a chunk alone cannot
+// fill the GPU).  Environment overrides are for tuning runs (tools/time_e2e.py).
+static int env_int(const char *name, int dflt, int lo, int hi) {
+    const char *v = getenv(name);
+    if (!v) return dflt;
+    const int x = atoi(v);
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+static const int kSlots = env_int("DDW_HP_SLOTS", 4, 2, kMaxSlots);
+static const int kRun = env_int("DDW_HP_RUN", 2, 1, kMaxRun);
 
 static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -89,8 +98,8 @@ struct StepArgs {
 using namespace ddw;
 
 struct ddw_host_pipeline {
-    cudaStream_t s_in, s_run[kRun], s_out, s_origin;
-    cudaEvent_t start, in_done[kSlots], run_done[kSlots], out_done[kSlots], head_in, head_run, tail_in, tail_run[kRun], tail_out;
+    cudaStream_t s_in, s_run[kMaxRun], s_out, s_origin;
+    cudaEvent_t start, in_done[kMaxSlots], run_done[kMaxSlots], out_done[kMaxSlots], head_in, head_run, tail_in, tail_run[kMaxRun], tail_out;
     // graph cache: the last argument set seen, and its instantiated graph once it has been seen twice
     StepArgs last;
     bool have_last;
@@ -133,9 +142,24 @@ static int enqueue_step(ddw_host_pipeline *pipe, const StepArgs &a, cudaStream_t
     cudaEventRecord(pipe->head_run, pipe->s_run[0]);
     for (int r = 1; r < kRun; ++r) cudaStreamWaitEvent(pipe->s_run[r], pipe->head_run, 0);
 
+    // Chunk schedule: full chunks in the middle, a quarter and a half chunk at both ends -- the first kernels start
+    // after a quarter chunk has arrived instead of a whole one, and the last copy-out is a quarter chunk long
+    // (fill and drain are the only parts of the step that do not overlap).
+    static const bool no_ramp = getenv("DDW_HOST_PIPELINE_NO_RAMP") != nullptr;   // diagnostic
+    const bool ramp = !no_ramp && B >= 4 * chunk && chunk >= 4;
+    const int64_t q4 = chunk / 4, q2 = chunk / 2;
     int rc = 0, it = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++it) {
-        const int64_t c = (B - b0 < chunk) ? (B - b0) : chunk;
+    int64_t c = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += c, ++it) {
+        const int64_t left = B - b0;
+        c = left < chunk ? left : chunk;
+        if (ramp) {
+            if (it == 0) c = q4;
+            else if (it == 1) c = q2;
+            else if (left <= q4) c = left;
+            else if (left <= q2 + q4) c = left - q4;
+            else if (left <= chunk + q2 + q4) c = left - (q2 + q4);
+        }
         const int sl = it % kSlots;
         cudaStream_t run = pipe->s_run[it % kRun];
         unsigned char *S = base + L.slots + (size_t)sl * L.slot_bytes;

@@ -99,3 +99,25 @@ def test_chunked_and_host_entry_points_validate_without_gpu(lib):
     assert lib.ddw_markowitz_host_scratch_bytes(0, 100, 0, 128) == 0
     assert lib.ddw_host_pipeline_graph_launches(None) == 0
     lib.ddw_host_pipeline_destroy(None)                         # no-op
+
+
+def test_hot_kernels_stage_their_matrix_with_bulk_tma(lib):
+    """SASS evidence (B200_PROFILING.md): the sparse-support forward and backward kernels bring covmat_sqrt into shared
+    memory with cp.async.bulk, which shows up as UBLKCP + SYNCS (mbarrier) in the sm_100a code of the built library."""
+    import shutil
+    import subprocess
+    from deepdow_b200 import _C
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", _C.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    seen = {}
+    current = None
+    for line in out.splitlines():
+        if "Function :" in line:
+            current = line.split("Function :")[1].strip()
+        elif "UBLKCP" in line and current:
+            seen[current] = seen.get(current, 0) + 1
+    assert any("markowitz_fwd_sparse_kernelIf" in k for k in seen), sorted(seen)
+    assert any("markowitz_bwd_sparse_kernelIf" in k for k in seen), sorted(seen)
+    assert "arch = sm_100a" in out

@@ -119,7 +119,20 @@ def aligned(t):
 
 
 def ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    """Device (or host) address of a tensor for a ``c_void_p`` argument: a plain int converts for free; None is NULL."""
+    return None if t is None else t.data_ptr()
+
+
+_ws_bytes_cache = {}
+
+
+def markowitz_workspace_bytes(B, N, dt):
+    """ddw_markowitz_workspace_bytes, memoised (it is a pure function of the shape; the call costs ~2 us of ctypes)."""
+    key = (B, N, dt)
+    v = _ws_bytes_cache.get(key)
+    if v is None:
+        v = _ws_bytes_cache[key] = int(lib().ddw_markowitz_workspace_bytes(B, N, dt))
+    return v
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)

@@ -25,7 +25,7 @@ int check_launch(const char *what) {
     return 0;
 }
 
-// implemented in markowitz.cu / rowproj.cu / covariance.cu
+// implemented in markowitz_impl.cuh (instantiated in markowitz_{fwd,bwd}_{f32,f64}.cu) / rowproj.cu / covariance.cu
 size_t markowitz_workspace_bytes(long long B, int N, int tsize);
 template <typename T>
 int markowitz_fwd_t(const void *, const void *, const void *, const void *, double, long long, int, void *, int8_t *,

@@ -40,6 +40,7 @@ class _StatusWatch:
 
     def __init__(self):
         self.buf = None
+        self.views = None
         self.events = None
         self.last_header = None
         self.pending = []   # (slot, event, description)
@@ -48,12 +49,13 @@ class _StatusWatch:
     def push(self, counter, what):
         if self.buf is None:
             self.buf = torch.zeros(self.SLOTS, dtype=torch.int32).pin_memory()
+            self.views = [self.buf[i:i + 1] for i in range(self.SLOTS)]
             self.events = [torch.cuda.Event() for _ in range(self.SLOTS)]
         if len(self.pending) >= self.SLOTS:
             self.poll(block=True)
         slot = self.next
         self.next = (self.next + 1) % self.SLOTS
-        self.buf[slot:slot + 1].copy_(counter, non_blocking=True)
+        self.views[slot].copy_(counter, non_blocking=True)
         ev = self.events[slot]      # free again: its previous use has been polled (pending < SLOTS)
         ev.record()
         self.pending.append((slot, ev, what))
@@ -84,7 +86,7 @@ class _MarkowitzFn(torch.autograd.Function):
         w = torch.empty_like(rets_c)
         state = torch.empty((B, N), dtype=torch.int8, device=rets.device)
         status = torch.empty((B,), dtype=torch.int32, device=rets.device)
-        ws = _workspace(lib.ddw_markowitz_workspace_bytes(B, N, dt), rets.device)
+        ws = _workspace(_C.markowitz_workspace_bytes(B, N, dt), rets.device)
         with _C.device_guard(rets):
             rc = lib.ddw_markowitz_fwd(_C.ptr(rets_c), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
                                        float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status),
@@ -117,7 +119,7 @@ class _MarkowitzFn(torch.autograd.Function):
         d_alpha = torch.empty_like(alp_c)
         need_gamma = ctx.needs_input_grad[2]
         d_gamma = torch.empty_like(gam_c) if need_gamma else None
-        ws = _workspace(lib.ddw_markowitz_workspace_bytes(B, N, dt), w.device)
+        ws = _workspace(_C.markowitz_workspace_bytes(B, N, dt), w.device)
         with _C.device_guard(w):
             rc = lib.ddw_markowitz_bwd(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
                                        ctx.max_weight, B, N, dt, _C.ptr(d_rets), _C.ptr(d_cov), _C.ptr(d_gamma),

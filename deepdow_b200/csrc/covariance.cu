@@ -439,6 +439,134 @@ __global__ void __launch_bounds__(kThreads) covariance_bwd_kernel(CovParams<T> p
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CovarianceMatrix(sqrt=False) for samples that fit shared memory (BachelierNet's covariance, nn.py:170-171): one CTA per
+// sample, the (L, N) lookback tile staged by ONE bulk TMA copy, centred into a padded copy, the Gram formed as 4x4 register
+// tiles over the lower triangle with 16-byte shared loads, scale + shrinkage applied on the tile, the symmetric result
+// assembled in shared memory and streamed out flat with 16-byte stores.  HBM traffic is the algorithmic
+// (L N + N^2 + 1) elements per sample.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPlainThreads = 128;
+constexpr int kPlainParts = 4;     // row slices of the column-mean pass
+
+template <typename T>
+__global__ void __launch_bounds__(kPlainThreads) covariance_plain_kernel(CovParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long mbar;
+    const long long b = blockIdx.x;
+    const int N = p.N, L = p.L, XS = p.AS, tid = threadIdx.x;
+    T *X = reinterpret_cast<T *>(smem_raw);                 // (L, N) dense, as in HBM
+    T *Xc = X + round_up(L * N, 4);                          // (L, XS) centred, columns N..XS-1 zero
+    T *S = Xc + L * XS;                                      // (N, N) dense result
+    T *part = S + round_up(N * N, 4);                        // (kPlainParts, N) partial column sums
+    T *red = part + kPlainParts * round_up(N, 4);
+    const T *xb = p.x + b * (long long)L * N;
+    const unsigned bytes = (unsigned)(L * N * sizeof(T));
+    const bool use_tma = (bytes & 15u) == 0u && (reinterpret_cast<unsigned long long>(xb) & 15ull) == 0ull;
+    if (use_tma) {
+        if (tid == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) { mbar_expect_tx(&mbar, bytes); tma_bulk_g2s(X, xb, bytes, &mbar); }
+        mbar_wait(&mbar, 0);
+    } else {
+        for (int e = tid; e < L * N; e += kPlainThreads) X[e] = xb[e];
+        __syncthreads();
+    }
+    // column means: kPlainParts row slices per column, combined in the centring pass
+    for (int e = tid; e < kPlainParts * N; e += kPlainThreads) {
+        const int q = e / N, i = e - q * N;
+        T acc = T(0);
+        for (int l = q; l < L; l += kPlainParts) acc += X[l * N + i];
+        part[q * round_up(N, 4) + i] = acc;
+    }
+    __syncthreads();
+    {
+        const T invL = T(1) / (T)L;
+        int l = tid / XS, i = tid - l * XS;
+        const int dl = kPlainThreads / XS, di = kPlainThreads % XS;
+        for (int e = tid; e < L * XS; e += kPlainThreads) {
+            T v = T(0);
+            if (i < N) {
+                T m = T(0);
+#pragma unroll
+                for (int q = 0; q < kPlainParts; ++q) m += part[q * round_up(N, 4) + i];
+                v = X[l * N + i] - m * invL;
+            }
+            Xc[e] = v;
+            i += di; l += dl;
+            if (i >= XS) { i -= XS; ++l; }
+        }
+    }
+    __syncthreads();
+    const T fact = T(1) / (T)(L - 1);
+    const int strategy = p.strategy;
+    const T c = strategy == DDW_SHRINK_NONE ? T(1) : p.coef[b];
+    T tr = T(0);
+    if (strategy == DDW_SHRINK_SCALED_IDENTITY) {   // mean of the sample variances (misc.py:157-161)
+        T loc = T(0);
+        for (int i = tid; i < N; i += kPlainThreads) {
+            T a = T(0);
+            for (int l = 0; l < L; ++l) a = fma(Xc[l * XS + i], Xc[l * XS + i], a);
+            loc += a;
+        }
+        tr = block_sum<T, kPlainThreads>(loc, red) * fact / (T)N;
+    }
+    const int NT = XS >> 2, ntiles = NT * (NT + 1) / 2;
+    for (int t = tid; t < ntiles; t += kPlainThreads) {
+        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while (ti * (ti + 1) / 2 > t) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        T acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = T(0);
+        const T *pa = Xc + 4 * ti, *pb = Xc + 4 * tj;
+#pragma unroll 4
+        for (int l = 0; l < L; ++l) {
+            const Vec4<T> a = ld4(pa + l * XS), bb = ld4(pb + l * XS);
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = fma(a.v[x], bb.v[y], acc[x][y]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int i = 4 * ti + x;
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const int j = 4 * tj + y;
+                if (i < N && j < N) {
+                    const T sij = acc[x][y] * fact;
+                    T v = sij;
+                    if (strategy == DDW_SHRINK_DIAGONAL) v = i == j ? c * sij + (T(1) - c) * sij : c * sij;
+                    else if (strategy == DDW_SHRINK_IDENTITY) v = c * sij + (i == j ? (T(1) - c) : T(0));
+                    else if (strategy == DDW_SHRINK_SCALED_IDENTITY) v = c * sij + (i == j ? (T(1) - c) * tr : T(0));
+                    S[i * N + j] = v;
+                    S[j * N + i] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    T *outb = p.out + b * (long long)N * N;
+    const int nn = N * N;
+    if ((nn & 3) == 0 && (reinterpret_cast<unsigned long long>(outb) & (4 * sizeof(T) - 1)) == 0ull) {
+        for (int e = 4 * tid; e < nn; e += 4 * kPlainThreads) st4(outb + e, ld4(S + e));
+    } else {
+        for (int e = tid; e < nn; e += kPlainThreads) outb[e] = S[e];
+    }
+}
+
+static size_t cov_plain_smem(int L, int N, int tsize) {
+    const int XS = round_up(N, 4);
+    return ((size_t)round_up(L * N, 4) + (size_t)L * XS + (size_t)round_up(N * N, 4) + (size_t)kPlainParts * XS + 64) * tsize;
+}
+// at least 3 samples resident per SM, else the generic kernel (which streams the lookback rows) is the better fit
+static bool cov_plain_fits(int L, int N, int tsize) { return L >= 2 && cov_plain_smem(L, N, tsize) <= 75 * 1024; }
+
 // ------------------------------------------------------------------------------------------------
 struct CovPlan {
     int threads, LDS, LDV, AS, CH;
@@ -508,6 +636,22 @@ size_t covariance_workspace_bytes(long long B, int L, int N, int tsize, int do_s
 template <typename T>
 int covariance_fwd_t(const void *x, const void *coef, int strategy, int do_sqrt, long long B, int L, int N, void *out,
                      void *eigvec, void *eigval, int32_t *sweeps, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!do_sqrt && cov_plain_fits(L, N, sizeof(T))) {
+        CovParams<T> q;
+        memset(&q, 0, sizeof(q));
+        q.x = (const T *)x; q.coef = (const T *)coef; q.strategy = strategy; q.B = B; q.L = L; q.N = N;
+        q.AS = round_up(N, 4); q.out = (T *)out;
+        const size_t smem = cov_plain_smem(L, N, sizeof(T));
+        static size_t attr_set[2] = {0, 0};   // largest dynamic size already granted per dtype (the attribute is per function)
+        size_t &granted = attr_set[sizeof(T) == 8];
+        if (smem > 48 * 1024 && smem > granted) {
+            if (cudaFuncSetAttribute(covariance_plain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return check_launch("cudaFuncSetAttribute(covariance_plain_kernel)");
+            granted = smem;
+        }
+        covariance_plain_kernel<T><<<(unsigned)B, kPlainThreads, smem, st>>>(q);
+        return check_launch("covariance_plain_kernel");
+    }
     const CovPlan pl = cov_plan_fwd(L, N, sizeof(T), do_sqrt);
     if (pl.global_m && (ws_bytes < (size_t)B * pl.per_sample_ws || !ws)) { set_error("ddw_covariance_fwd: workspace too small"); return DDW_ERR_WORKSPACE; }
     if (pl.smem > (size_t)cov_smem_limit()) { set_error("ddw_covariance_fwd: n_assets=%d needs %zu B of shared memory", N, pl.smem); return DDW_ERR_UNSUPPORTED; }

@@ -2,10 +2,13 @@
 // deepdow/layers/allocate.py:554-560,580-595) and capped softmax (variational SoftmaxAllocator,
 // allocate.py:470-475,495-514), forward and backward.
 //
-// One warp per row; the row lives in registers (NREG values per lane), every reduction is a
-// warp shuffle, so a row costs exactly one coalesced read of x and one coalesced write of w:
-// (2N+1) elements of HBM traffic forward, 3N backward.
+// A row is owned by a GROUP of LPR lanes (4, 8, 16 or 32) holding NREG = 16+ values each, so a warp works on
+// 32 / LPR rows at once: a row of 100 is 8 lanes x 16 values, and a reduction over the row is 3 shuffle steps shared by
+// four rows instead of 5 for one (the kernels were bound by the SM's shuffle rate with one warp per row).  Integer counts
+// travel packed in one word.  A row costs one coalesced read of x and one coalesced write of w: (2N+1) elements of HBM
+// traffic forward, 3N backward.  Rows whose length is a multiple of 4 move as 16-byte vectors (row_load / row_store).
 #include "common.cuh"
+#include "linalg.cuh"   // st4
 
 namespace ddw {
 
@@ -19,212 +22,363 @@ template <typename T> struct RowParams {
     T *out, *d_x, *d_t;
 };
 
-// ---- capped simplex: w = clip(v - tau, 0, u), sum w = 1 ----------------------------------------
-template <typename T, int NREG>
-__global__ void __launch_bounds__(kRowWarps * 32) capped_simplex_fwd_kernel(RowParams<T> p) {
+// Element m of lane `sub` of a group.  Scalar layout: i = sub + LPR m (any n_assets).  Vector layout (n_assets % 4 == 0,
+// 16-byte aligned rows): the lane owns 4 consecutive elements per 4 LPR-element block, i = 4 (sub + LPR (m / 4)) + m % 4,
+// and moves them with one 16-byte access.
+template <int LPR, bool kVec> __device__ __forceinline__ int row_elem(int sub, int m) {
+    return kVec ? 4 * (sub + LPR * (m >> 2)) + (m & 3) : sub + LPR * m;
+}
+template <typename T, int NREG, int LPR, bool kVec>
+__device__ __forceinline__ void row_load(const T *__restrict__ src, int N, int sub, T (&v)[NREG], T fill) {
+    if (kVec) {
+#pragma unroll
+        for (int mv = 0; mv < NREG / 4; ++mv) {
+            const int i = 4 * (sub + LPR * mv);
+            if (i < N) {
+                const Vec4<T> q = ld4(src + i);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[4 * mv + c] = q.v[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[4 * mv + c] = fill;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < NREG; ++m) { const int i = sub + LPR * m; v[m] = i < N ? src[i] : fill; }
+    }
+}
+template <typename T, int NREG, int LPR, bool kVec>
+__device__ __forceinline__ void row_store(T *__restrict__ dst, int N, int sub, const T (&v)[NREG]) {
+    if (kVec) {
+#pragma unroll
+        for (int mv = 0; mv < NREG / 4; ++mv) {
+            const int i = 4 * (sub + LPR * mv);
+            if (i < N) {
+                Vec4<T> q;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) q.v[c] = v[4 * mv + c];
+                st4(dst + i, q);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < NREG; ++m) { const int i = sub + LPR * m; if (i < N) dst[i] = v[m]; }
+    }
+}
+// reductions over the LPR lanes of a group (xor offsets below LPR stay inside the aligned group); every lane of the
+// warp executes them, so groups whose row is finished or out of range keep stepping with the others
+template <int LPR, typename V> __device__ __forceinline__ V group_sum(V v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+template <int LPR, typename V> __device__ __forceinline__ V group_max(V v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) { V t = __shfl_xor_sync(kFullMask, v, o); v = t > v ? t : v; }
+    return v;
+}
+template <int LPR, typename V> __device__ __forceinline__ V group_min(V v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) { V t = __shfl_xor_sync(kFullMask, v, o); v = t < v ? t : v; }
+    return v;
+}
+
+// v / t for the whole row from ONE division: q = v * (1/t) plus one residual correction, which is the correctly rounded
+// quotient except at the ends of the exponent range (what the division's own fast path computes, without its checks)
+__device__ __forceinline__ float div_by(float v, float t, float rt) { const float q = v * rt; return fmaf(fmaf(-q, t, v), rt, q); }
+__device__ __forceinline__ double div_by(double v, double t, double) { return v / t; }
+
+__device__ __forceinline__ float fminT(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double fminT(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float fmaxT(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double fmaxT(double a, double b) { return fmax(a, b); }
+// 0 < c < u for a c already clipped to [0, u].  float: one unsigned compare on the bit patterns (c = 0 wraps to the top
+// of the range), which keeps the unrolled loop free of long-lived predicates.
+// quotient for a search step (any point of the bracket would do): the hardware reciprocal is enough
+__device__ __forceinline__ float step_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double step_div(double a, double b) { return a / b; }
+__device__ __forceinline__ unsigned inside_key(float u) { return (unsigned)__float_as_int(u) - 1u; }
+__device__ __forceinline__ bool is_inside(float c, unsigned key) { return (unsigned)__float_as_int(c) - 1u < key; }
+__device__ __forceinline__ double inside_key(double u) { return u; }
+__device__ __forceinline__ bool is_inside(double c, double u) { return c > 0.0 && c < u; }
+
+// The row of this lane's group; `live` is false for the groups past the end of the batch, which shadow the last row
+// (same loads, no stores) so that the warp-wide shuffles stay convergent.  Returns false when the whole warp is past the end.
+template <int LPR> __device__ __forceinline__ bool row_of_group(long long B, long long &row, int &sub, bool &live) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-    if (row >= p.B) return;
+    sub = lane & (LPR - 1);
+    const long long first = ((long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5)) * (32 / LPR);
+    if (first >= B) return false;
+    row = first + lane / LPR;
+    live = row < B;
+    if (!live) row = B - 1;
+    return true;
+}
+
+// ---- capped simplex: w = clip(v - tau, 0, u), sum w = 1 ----------------------------------------
+template <typename T, int NREG, int LPR, bool kVec>
+__global__ void __launch_bounds__(kRowWarps * 32) capped_simplex_fwd_kernel(RowParams<T> p) {
+    long long row; int sub; bool live;
+    if (!row_of_group<LPR>(p.B, row, sub, live)) return;
     const int N = p.N;
     const T u = p.u;
     const T t = p.temperature ? p.temperature[row] : p.temperature_scalar;
-    const T *x = p.x + row * N;
     T v[NREG];
+    row_load<T, NREG, LPR, kVec>(p.x + row * N, N, sub, v, T(0));
     T vmax = -Num<T>::inf(), vmin = Num<T>::inf();
+    const bool unit_t = t == T(1);
+    const T rt = T(1) / t;
 #pragma unroll
     for (int m = 0; m < NREG; ++m) {
-        const int i = lane + 32 * m;
-        if (i < N) { v[m] = x[i] / t; vmax = v[m] > vmax ? v[m] : vmax; vmin = v[m] < vmin ? v[m] : vmin; }
-        else v[m] = -Num<T>::inf();   // never in the support
+        const bool in = row_elem<LPR, kVec>(sub, m) < N;
+        const T q = unit_t ? v[m] : div_by(v[m], t, rt);
+        vmax = in && q > vmax ? q : vmax; vmin = in && q < vmin ? q : vmin;
+        v[m] = in ? q : -Num<T>::inf();   // padding is never in the support
     }
-    vmax = warp_max(vmax); vmin = warp_min(vmin);
-    // Root of the non-increasing piecewise-linear phi(tau) = sum clip(v - tau, 0, u) - 1 by a
-    // bracketed Newton iteration: the Newton step is the exact solve for the current (free, capped)
-    // sets, so the iteration ends at a fixed point; a step that leaves the bracket or fails to
-    // halve the step before last is replaced by a bisection (the rtsafe rule).
-    T lo = vmin - u, hi = vmax;   // phi(lo) = N u - 1 >= 0 > phi(hi) = -1
-    T tau = vmax - (u < T(1) ? u : T(1));
-    if (tau < lo) tau = lo;
+    vmax = group_max<LPR>(vmax); vmin = group_min<LPR>(vmin);
+    // Root of the non-increasing piecewise-linear phi(tau) = sum clip(v - tau, 0, u) - 1 inside a bracket
+    // [lo, hi], phi(lo) >= 0 > phi(hi).  The Newton step is the exact solve for the current (free, capped) sets, so the
+    // iteration ends at a fixed point; a Newton step that leaves the bracket or fails to halve the step before last (the
+    // rtsafe rule) -- or does not exist because no asset is free at tau, the usual case when the cap binds and phi is a
+    // staircase of flats and short ramps -- is replaced by the secant of the bracket ends (Illinois rule: an end kept
+    // twice has its value halved), and by a bisection every other time once six steps have not been enough.
+    T lo = vmin - u, hi = vmax;
+    T flo = u * (T)N - T(1), fhi = T(-1);
+    // start: without a binding cap the top asset alone gives phi(vmax - 1) >= 0 and Newton climbs monotonically from
+    // there; with a cap, the secant of the initial bracket
+    T tau = u >= T(1) ? vmax - T(1) : lo + (hi - lo) * (flo / (flo - fhi));
+    if (!(tau >= lo)) tau = lo;
+    if (tau > hi) tau = hi;
     T dxold = hi - lo, dx = dxold;
+    int side = 0, nfall = 0;
+    bool done = false;
+    const auto ukey = inside_key(u);
+    T c[NREG];   // clip(v - tau, 0, u) of the last evaluation: the weights once the row is done
 #pragma unroll 1
     for (int it = 0; it < 200; ++it) {
-        T sumF = T(0);
-        int cntF = 0, cntU = 0;
+        T s0 = T(0), s1 = T(0);
+        int cntF = 0;   // assets strictly between the bounds = minus the slope of phi at tau
 #pragma unroll
         for (int m = 0; m < NREG; ++m) {
-            const T dlt = v[m] - tau;
-            if (dlt >= u) ++cntU;
-            else if (dlt > T(0)) { ++cntF; sumF += v[m]; }
+            c[m] = fminT(fmaxT(v[m] - tau, T(0)), u);
+            if (m & 1) s1 += c[m]; else s0 += c[m];
+            cntF += is_inside(c[m], ukey) ? 1 : 0;
         }
-        sumF = warp_sum(sumF);
-        cntF = warp_sum(cntF); cntU = warp_sum(cntU);
-        const T s = sumF - (T)cntF * tau + u * (T)cntU;
-        if (s > T(1)) lo = tau; else hi = tau;
-        bool ok = false;
-        T nt = tau;
-        if (cntF > 0) {
-            nt = (sumF + u * (T)cntU - T(1)) / (T)cntF;
-            if (nt == tau) break;
-            ok = nt >= lo && nt <= hi && absT(T(2) * (nt - tau)) <= absT(dxold);
-        } else if (absT(s - T(1)) <= T(4) * Num<T>::eps() * (T)N) break;
-        dxold = dx;
-        if (ok) dx = nt - tau;
-        else { dx = T(0.5) * (hi - lo); nt = lo + dx; }
-        if (nt == tau) break;
-        tau = nt;
+        const T ssum = group_sum<LPR>(s0 + s1);
+        cntF = group_sum<LPR>(cntF);
+        if (!done) {
+            const T f = ssum - T(1);
+            if (f > T(0)) { lo = tau; flo = f; if (side == 1) fhi *= T(0.5); side = 1; }
+            else { hi = tau; fhi = f; if (side == 2) flo *= T(0.5); side = 2; }
+            bool ok = false;
+            T nt = tau;
+            if (cntF > 0) {
+                nt = tau + step_div(f, (T)cntF);
+                if (nt == tau) done = true;
+                ok = nt > lo && nt < hi && absT(T(2) * (nt - tau)) <= absT(dxold);
+            } else if (absT(f) <= T(4) * Num<T>::eps() * (T)N) done = true;
+            if (!done) {
+                dxold = dx;
+                if (!ok) {
+                    const T den = flo - fhi;
+                    nt = lo + (hi - lo) * step_div(flo, den);
+                    const bool bisect = (it >= 6 && (nfall & 1)) || !(den > T(0)) || !(nt > lo && nt < hi);
+                    if (bisect) nt = lo + T(0.5) * (hi - lo);
+                    ++nfall;
+                    // no number left strictly inside the bracket: tau is within one rounding of the root
+                    if (!(nt > lo && nt < hi)) { done = true; nt = tau; }
+                }
+                dx = nt - tau;
+                tau = nt;
+            }
+        }
+        if (__all_sync(kFullMask, done)) break;
     }
-    T *w = p.out + row * N;
+    // Polish: the search steps above take phi from a sum of clipped values (rounding of order eps) and a hardware
+    // reciprocal; the last step is the exact solve for the sets found, tau = (sum_F v + u |U| - 1) / |F| with a true
+    // division, which lands exactly on a breakpoint when the solution sits on one (supports match the oracle's).
+    {
+        T sumF = T(0);
+        int cnt = 0;   // free count in the low half, capped count in the high half (n_assets <= 2048)
 #pragma unroll
-    for (int m = 0; m < NREG; ++m) {
-        const int i = lane + 32 * m;
-        if (i < N) w[i] = clampT(v[m] - tau, T(0), u);
+        for (int m = 0; m < NREG; ++m) {
+            const T cm = fminT(fmaxT(v[m] - tau, T(0)), u);
+            const bool fre = is_inside(cm, ukey);
+            sumF += fre ? v[m] : T(0);
+            cnt += fre ? 1 : (cm > T(0) ? (1 << 16) : 0);
+        }
+        sumF = group_sum<LPR>(sumF);
+        cnt = group_sum<LPR>(cnt);
+        const int cntF = cnt & 0xffff, cntU = cnt >> 16;
+        if (cntF > 0) {
+            const T tp = (sumF + (u * (T)cntU - T(1))) / (T)cntF;
+            if (absT(tp - tau) <= T(1e-3) * (absT(tau) + T(1))) tau = tp;
+        }
+#pragma unroll
+        for (int m = 0; m < NREG; ++m) c[m] = fminT(fmaxT(v[m] - tau, T(0)), u);
     }
+    if (live) row_store<T, NREG, LPR, kVec>(p.out + row * N, N, sub, c);
 }
 
 // d_inp = g - mean_F(g) on F = {0 < w < u}, 0 elsewhere; d_x = d_inp / t; d_t = -sum(d_inp x) / t^2
-template <typename T, int NREG>
+template <typename T, int NREG, int LPR, bool kVec>
 __global__ void __launch_bounds__(kRowWarps * 32) capped_simplex_bwd_kernel(RowParams<T> p) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-    if (row >= p.B) return;
+    long long row; int sub; bool live;
+    if (!row_of_group<LPR>(p.B, row, sub, live)) return;
     const int N = p.N;
     const T u = p.u;
     const T t = p.temperature ? p.temperature[row] : p.temperature_scalar;
-    const T *w = p.w + row * N, *g = p.grad_w + row * N, *x = p.x + row * N;
-    T gv[NREG];
+    T wv[NREG], gv[NREG];
+    row_load<T, NREG, LPR, kVec>(p.w + row * N, N, sub, wv, T(0));
+    row_load<T, NREG, LPR, kVec>(p.grad_w + row * N, N, sub, gv, T(0));
     bool fr[NREG];
     T sg = T(0);
     int cnt = 0;
 #pragma unroll
     for (int m = 0; m < NREG; ++m) {
-        const int i = lane + 32 * m;
-        fr[m] = false; gv[m] = T(0);
-        if (i < N) {
-            const T wi = w[i];
-            fr[m] = wi > T(0) && wi < u;
-            if (fr[m]) { gv[m] = g[i]; sg += gv[m]; ++cnt; }
-        }
+        fr[m] = row_elem<LPR, kVec>(sub, m) < N && wv[m] > T(0) && wv[m] < u;
+        gv[m] = fr[m] ? gv[m] : T(0);
+        sg += gv[m]; cnt += fr[m] ? 1 : 0;
     }
-    sg = warp_sum(sg); cnt = warp_sum(cnt);
+    sg = group_sum<LPR>(sg); cnt = group_sum<LPR>(cnt);
     const T mean = cnt > 0 ? sg / (T)cnt : T(0);
+    const bool unit_t = t == T(1);
+    const T rt = T(1) / t;
     T dt = T(0);
+    if (p.d_t) row_load<T, NREG, LPR, kVec>(p.x + row * N, N, sub, wv, T(0));   // w is not needed any more
 #pragma unroll
     for (int m = 0; m < NREG; ++m) {
-        const int i = lane + 32 * m;
-        if (i < N) {
-            const T di = fr[m] ? gv[m] - mean : T(0);
-            p.d_x[row * N + i] = di / t;
-            if (p.d_t) dt = fma(di, x[i], dt);
-        }
+        const T di = fr[m] ? gv[m] - mean : T(0);
+        if (p.d_t) dt = fma(di, wv[m], dt);
+        gv[m] = unit_t ? di : div_by(di, t, rt);
     }
+    if (live) row_store<T, NREG, LPR, kVec>(p.d_x + row * N, N, sub, gv);
     if (p.d_t) {
-        dt = warp_sum(dt);
-        if (lane == 0) p.d_t[row] = -dt / (t * t);
+        dt = group_sum<LPR>(dt);
+        if (live && sub == 0) p.d_t[row] = -dt / (t * t);
     }
 }
 
 // ---- capped softmax: w_i = min(u, exp(v_i - nu)), sum w = 1 ------------------------------------
-template <typename T, int NREG>
+template <typename T, int NREG, int LPR, bool kVec>
 __global__ void __launch_bounds__(kRowWarps * 32) capped_softmax_fwd_kernel(RowParams<T> p) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-    if (row >= p.B) return;
+    long long row; int sub; bool live;
+    if (!row_of_group<LPR>(p.B, row, sub, live)) return;
     const int N = p.N;
     const T u = p.u;
     const T t = p.temperature ? p.temperature[row] : p.temperature_scalar;
-    const T *x = p.x + row * N;
     T e[NREG];
+    row_load<T, NREG, LPR, kVec>(p.x + row * N, N, sub, e, T(0));
     T vmax = -Num<T>::inf();
+    const bool unit_t = t == T(1);
+    const T rt = T(1) / t;
 #pragma unroll
     for (int m = 0; m < NREG; ++m) {
-        const int i = lane + 32 * m;
-        e[m] = i < N ? x[i] / t : -Num<T>::inf();
+        const T q = unit_t ? e[m] : div_by(e[m], t, rt);
+        e[m] = row_elem<LPR, kVec>(sub, m) < N ? q : -Num<T>::inf();
         vmax = e[m] > vmax ? e[m] : vmax;
     }
-    vmax = warp_max(vmax);
+    vmax = group_max<LPR>(vmax);
 #pragma unroll
-    for (int m = 0; m < NREG; ++m) e[m] = (lane + 32 * m) < N ? expT(e[m] - vmax) : T(0);
-    unsigned long long capped = 0ull;   // bit m: slot m of this lane sits at the cap
-    int ncap = 0;
+    for (int m = 0; m < NREG; ++m) e[m] = row_elem<LPR, kVec>(sub, m) < N ? expT(e[m] - vmax) : T(0);
+    // The capped set only grows: rescale the rest to the remaining mass, cap what now exceeds u, repeat.  This is Newton on
+    // the concave piecewise-linear sum min(u, e s) = 1 in the scale s, from the left: monotone, ends after finitely many steps.
+    int ncap = 0;                      // a capped slot is marked by e = -1 (padding holds 0 and never exceeds the cap)
     T scale = T(0);
+    bool done = false;
+#pragma unroll 1
     for (int it = 0; it <= N; ++it) {
         T sF = T(0);
 #pragma unroll
-        for (int m = 0; m < NREG; ++m) sF += ((capped >> m) & 1ull) ? T(0) : e[m];
-        sF = warp_sum(sF);
+        for (int m = 0; m < NREG; ++m) sF += e[m] > T(0) ? e[m] : T(0);
+        sF = group_sum<LPR>(sF);
         const T mass = T(1) - u * (T)ncap;
-        if (!(sF > T(0)) || !(mass > T(0))) { scale = T(0); break; }
-        scale = mass / sF;
+        const bool empty = !(sF > T(0)) || !(mass > T(0));
+        if (!done) scale = empty ? T(0) : mass / sF;
         int nnew = 0;
 #pragma unroll
         for (int m = 0; m < NREG; ++m) {
-            if (!((capped >> m) & 1ull) && (lane + 32 * m) < N && e[m] * scale > u) { capped |= 1ull << m; ++nnew; }
+            const bool c = !done && e[m] * scale > u;
+            e[m] = c ? T(-1) : e[m];
+            nnew += c ? 1 : 0;
         }
-        nnew = warp_sum(nnew);
-        if (nnew == 0) break;
+        nnew = group_sum<LPR>(nnew);
+        if (nnew == 0) done = true;
         ncap += nnew;
+        if (__all_sync(kFullMask, done)) break;
     }
-    T *w = p.out + row * N;
 #pragma unroll
-    for (int m = 0; m < NREG; ++m) {
-        const int i = lane + 32 * m;
-        if (i < N) w[i] = ((capped >> m) & 1ull) ? u : e[m] * scale;
-    }
+    for (int m = 0; m < NREG; ++m) e[m] = e[m] < T(0) ? u : e[m] * scale;
+    if (live) row_store<T, NREG, LPR, kVec>(p.out + row * N, N, sub, e);
 }
 
 // d_inp = w_F * (g - sum_F(w g) / sum_F(w)) on F = {w < u}; 0 on the capped assets
-template <typename T, int NREG>
+template <typename T, int NREG, int LPR, bool kVec>
 __global__ void __launch_bounds__(kRowWarps * 32) capped_softmax_bwd_kernel(RowParams<T> p) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-    if (row >= p.B) return;
+    long long row; int sub; bool live;
+    if (!row_of_group<LPR>(p.B, row, sub, live)) return;
     const int N = p.N;
     const T u = p.u;
     const T t = p.temperature ? p.temperature[row] : p.temperature_scalar;
-    const T *w = p.w + row * N, *g = p.grad_w + row * N, *x = p.x + row * N;
     T wv[NREG], gv[NREG];
+    row_load<T, NREG, LPR, kVec>(p.w + row * N, N, sub, wv, u);          // fill = u: padding counts as capped
+    row_load<T, NREG, LPR, kVec>(p.grad_w + row * N, N, sub, gv, T(0));
     T sw = T(0), swg = T(0);
 #pragma unroll
     for (int m = 0; m < NREG; ++m) {
-        const int i = lane + 32 * m;
-        wv[m] = T(0); gv[m] = T(0);
-        if (i < N) {
-            const T wi = w[i];
-            if (wi < u) { wv[m] = wi; gv[m] = g[i]; sw += wi; swg = fma(wi, gv[m], swg); }
-        }
+        const bool fre = row_elem<LPR, kVec>(sub, m) < N && wv[m] < u;
+        wv[m] = fre ? wv[m] : T(0);
+        sw += wv[m]; swg = fma(wv[m], gv[m], swg);
     }
-    sw = warp_sum(sw); swg = warp_sum(swg);
+    sw = group_sum<LPR>(sw); swg = group_sum<LPR>(swg);
     const T mean = sw > T(0) ? swg / sw : T(0);
+    const bool unit_t = t == T(1);
+    const T rt = T(1) / t;
     T dt = T(0);
 #pragma unroll
-    for (int m = 0; m < NREG; ++m) {
-        const int i = lane + 32 * m;
-        if (i < N) {
-            const T di = wv[m] * (gv[m] - mean);
-            p.d_x[row * N + i] = di / t;
-            if (p.d_t) dt = fma(di, x[i], dt);
-        }
-    }
+    for (int m = 0; m < NREG; ++m) wv[m] = wv[m] * (gv[m] - mean);       // d_inp
     if (p.d_t) {
-        dt = warp_sum(dt);
-        if (lane == 0) p.d_t[row] = -dt / (t * t);
+        row_load<T, NREG, LPR, kVec>(p.x + row * N, N, sub, gv, T(0));   // g is not needed any more
+#pragma unroll
+        for (int m = 0; m < NREG; ++m) dt = fma(wv[m], gv[m], dt);
+    }
+#pragma unroll
+    for (int m = 0; m < NREG; ++m) wv[m] = unit_t ? wv[m] : div_by(wv[m], t, rt);
+    if (live) row_store<T, NREG, LPR, kVec>(p.d_x + row * N, N, sub, wv);
+    if (p.d_t) {
+        dt = group_sum<LPR>(dt);
+        if (live && sub == 0) p.d_t[row] = -dt / (t * t);
     }
 }
 
-template <typename T, template <typename, int> class K> struct Dummy {};
+static bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-#define DDW_ROW_DISPATCH(KERNEL)                                                              \
-    do {                                                                                      \
-        const unsigned grid = (unsigned)((p.B + kRowWarps - 1) / kRowWarps);                  \
-        if (p.N <= 32) KERNEL<T, 1><<<grid, kRowWarps * 32, 0, st>>>(p);                      \
-        else if (p.N <= 64) KERNEL<T, 2><<<grid, kRowWarps * 32, 0, st>>>(p);                 \
-        else if (p.N <= 128) KERNEL<T, 4><<<grid, kRowWarps * 32, 0, st>>>(p);                \
-        else if (p.N <= 256) KERNEL<T, 8><<<grid, kRowWarps * 32, 0, st>>>(p);                \
-        else if (p.N <= 512) KERNEL<T, 16><<<grid, kRowWarps * 32, 0, st>>>(p);               \
-        else if (p.N <= 1024) KERNEL<T, 32><<<grid, kRowWarps * 32, 0, st>>>(p);              \
-        else if (p.N <= 2048) KERNEL<T, 64><<<grid, kRowWarps * 32, 0, st>>>(p);              \
+// 16 values per lane and as many lanes per row as that takes (4 ... 32); longer rows keep the full warp and grow NREG
+#define DDW_ROW_LAUNCH(KERNEL, NREG, LPR, VEC)                                                            \
+    do {                                                                                                  \
+        const long long rows_per_block = (long long)kRowWarps * (32 / (LPR));                             \
+        const unsigned grid = (unsigned)((p.B + rows_per_block - 1) / rows_per_block);                    \
+        KERNEL<T, NREG, LPR, VEC><<<grid, kRowWarps * 32, 0, st>>>(p);                                    \
+    } while (0)
+#define DDW_ROW_SIZES(KERNEL, VEC)                                                                        \
+    do {                                                                                                  \
+        if (p.N <= 64) DDW_ROW_LAUNCH(KERNEL, 16, 4, VEC);                                                \
+        else if (p.N <= 128) DDW_ROW_LAUNCH(KERNEL, 16, 8, VEC);                                          \
+        else if (p.N <= 256) DDW_ROW_LAUNCH(KERNEL, 16, 16, VEC);                                         \
+        else if (p.N <= 512) DDW_ROW_LAUNCH(KERNEL, 16, 32, VEC);                                         \
+        else if (p.N <= 1024) DDW_ROW_LAUNCH(KERNEL, 32, 32, VEC);                                        \
+        else if (p.N <= 2048) DDW_ROW_LAUNCH(KERNEL, 64, 32, VEC);                                        \
         else { set_error(#KERNEL ": n_assets=%d > 2048 is not supported", p.N); return DDW_ERR_UNSUPPORTED; } \
-        return check_launch(#KERNEL);                                                         \
+    } while (0)
+#define DDW_ROW_DISPATCH(KERNEL)                                                                          \
+    do {                                                                                                  \
+        if (p.B <= 0) return 0;                                                                           \
+        /* vector layout: rows are multiples of 16 bytes and every array starts on one */                  \
+        const bool vec = (p.N % 4 == 0) && aligned16(p.x) && aligned16(p.grad_w) && aligned16(p.w) &&     \
+                         aligned16(p.out) && aligned16(p.d_x);                                            \
+        if (vec) DDW_ROW_SIZES(KERNEL, true); else DDW_ROW_SIZES(KERNEL, false);                          \
+        return check_launch(#KERNEL);                                                                     \
     } while (0)
 
 template <typename T> int capped_simplex_fwd_t(const RowParams<T> &p, cudaStream_t st) { DDW_ROW_DISPATCH(capped_simplex_fwd_kernel); }

@@ -298,7 +298,10 @@ def test_markowitz_config5_full_size_properties():
 # ------------------------------------------------------------------ sparsemax / softmax
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("B,N,u,scale", [(1024, 100, 1.0, 1.0), (1024, 100, 0.05, 10.0), (33, 5, 0.25, 1.0),
-                                         (7, 300, 0.013, 3.0), (5, 1000, 1.0, 1.0)])
+                                         (7, 300, 0.013, 3.0), (5, 1000, 1.0, 1.0),
+                                         # one case per (lanes per row, vector / scalar) layout of rowproj.cu, ragged batch ends
+                                         (37, 50, 0.1, 5.0), (1, 20, 0.2, 10.0), (130, 64, 0.03, 20.0), (19, 200, 0.05, 8.0),
+                                         (9, 130, 0.3, 4.0), (3, 2048, 0.001, 30.0), (11, 513, 1.0, 2.0)])
 def test_sparsemax_vs_oracle(dtype, B, N, u, scale):
     rng = np.random.default_rng(N)
     u = float(np.float32(u)) if dtype == torch.float32 else u   # the cap exactly as the kernel sees it
@@ -327,7 +330,9 @@ def test_sparsemax_vs_oracle(dtype, B, N, u, scale):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("B,N,u,scale", [(1024, 100, 1.0, 1.0), (1024, 100, 0.05, 10.0), (33, 5, 0.25, 1.0), (6, 700, 0.01, 3.0)])
+@pytest.mark.parametrize("B,N,u,scale", [(1024, 100, 1.0, 1.0), (1024, 100, 0.05, 10.0), (33, 5, 0.25, 1.0), (6, 700, 0.01, 3.0),
+                                         (37, 50, 0.1, 5.0), (1, 20, 0.2, 10.0), (130, 64, 0.03, 20.0), (19, 200, 0.05, 8.0),
+                                         (9, 130, 0.3, 4.0), (3, 2048, 0.001, 30.0), (11, 513, 1.0, 2.0)])
 def test_softmax_vs_oracle(dtype, B, N, u, scale):
     rng = np.random.default_rng(N + 1)
     u = float(np.float32(u)) if dtype == torch.float32 else u
@@ -404,13 +409,17 @@ def test_covariance_vs_reference_fixtures(dtype, golden_dir):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("B,L,N", [(64, 40, 20), (256, 40, 50), (16, 40, 100), (4, 60, 130), (2, 250, 200)])
+@pytest.mark.parametrize("B,L,N", [(64, 40, 20), (256, 40, 50), (16, 40, 100), (4, 60, 130), (2, 250, 200),
+                                   # odd shapes: no 16-byte alignment for the staged tile / the flat store of the plain kernel
+                                   (5, 7, 3), (3, 2, 9), (9, 33, 51), (300, 3, 1)])
 def test_covariance_vs_oracle_sizes(dtype, B, L, N):
     rng = np.random.default_rng(L + N)
     x = rng.standard_normal((B, L, N)) * 0.01
     xin = t(x, dtype).double().cpu().numpy()
-    for strategy in ["diagonal", "scaled_identity"]:
+    for strategy in ["diagonal", "scaled_identity", "identity", None]:
         for sqrt in [False, True]:
+            if sqrt and strategy in ("identity", None):
+                continue        # the square root of these is covered by the reference fixtures
             y = CovarianceMatrix(sqrt=sqrt, shrinkage_strategy=strategy)(t(x, dtype))
             ref = oracle.covariance_fwd(xin, 0.5, strategy, sqrt)
             tol = 3e-5 if dtype == torch.float32 else 1e-10

@@ -473,29 +473,33 @@ __global__ void __launch_bounds__(kPlainThreads) covariance_plain_kernel(CovPara
         for (int e = tid; e < L * N; e += kPlainThreads) X[e] = xb[e];
         __syncthreads();
     }
-    // column means: kPlainParts row slices per column, combined in the centring pass
-    for (int e = tid; e < kPlainParts * N; e += kPlainThreads) {
-        const int q = e / N, i = e - q * N;
-        T acc = T(0);
-        for (int l = q; l < L; l += kPlainParts) acc += X[l * N + i];
-        part[q * round_up(N, 4) + i] = acc;
-    }
-    __syncthreads();
+    // column means and centring with a fixed (column, row slice) per thread: the mean stays in a register and the loops
+    // carry no index arithmetic.  P = row slices (as many as fit 128 threads; 1 and a column loop when XS > 128).
     {
-        const T invL = T(1) / (T)L;
-        int l = tid / XS, i = tid - l * XS;
-        const int dl = kPlainThreads / XS, di = kPlainThreads % XS;
-        for (int e = tid; e < L * XS; e += kPlainThreads) {
-            T v = T(0);
-            if (i < N) {
-                T m = T(0);
-#pragma unroll
-                for (int q = 0; q < kPlainParts; ++q) m += part[q * round_up(N, 4) + i];
-                v = X[l * N + i] - m * invL;
+        const int P = XS <= kPlainThreads ? min(kPlainParts, kPlainThreads / XS) : 1;
+        const int q = XS <= kPlainThreads ? tid / XS : 0;
+        const int i0 = XS <= kPlainThreads ? tid - q * XS : tid;
+        const int PS = round_up(N, 4);
+        const bool active = q < P;
+        if (active)
+            for (int i = i0; i < N; i += kPlainThreads) {
+                T acc = T(0);
+                for (int l = q; l < L; l += P) acc += X[l * N + i];
+                part[q * PS + i] = acc;
             }
-            Xc[e] = v;
-            i += di; l += dl;
-            if (i >= XS) { i -= XS; ++l; }
+        __syncthreads();
+        if (active) {
+            const T invL = T(1) / (T)L;
+            for (int i = i0; i < XS; i += kPlainThreads) {
+                if (i < N) {
+                    T m = T(0);
+                    for (int r = 0; r < P; ++r) m += part[r * PS + i];
+                    m *= invL;
+                    for (int l = q; l < L; l += P) Xc[l * XS + i] = X[l * N + i] - m;
+                } else {
+                    for (int l = q; l < L; l += P) Xc[l * XS + i] = T(0);
+                }
+            }
         }
     }
     __syncthreads();
@@ -512,6 +516,10 @@ __global__ void __launch_bounds__(kPlainThreads) covariance_plain_kernel(CovPara
         }
         tr = block_sum<T, kPlainThreads>(loc, red) * fact / (T)N;
     }
+    // S_ij = fact * acc * (c off the diagonal | shrinkage weight on it) + the target's diagonal (misc.py:149-166)
+    const T woff = fact * c;
+    const T wdiag = strategy == DDW_SHRINK_DIAGONAL ? fact * (c + (T(1) - c)) : woff;
+    const T dadd = strategy == DDW_SHRINK_IDENTITY ? T(1) - c : (strategy == DDW_SHRINK_SCALED_IDENTITY ? (T(1) - c) * tr : T(0));
     const int NT = XS >> 2, ntiles = NT * (NT + 1) / 2;
     for (int t = tid; t < ntiles; t += kPlainThreads) {
         int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
@@ -539,11 +547,7 @@ __global__ void __launch_bounds__(kPlainThreads) covariance_plain_kernel(CovPara
             for (int y = 0; y < 4; ++y) {
                 const int j = 4 * tj + y;
                 if (i < N && j < N) {
-                    const T sij = acc[x][y] * fact;
-                    T v = sij;
-                    if (strategy == DDW_SHRINK_DIAGONAL) v = i == j ? c * sij + (T(1) - c) * sij : c * sij;
-                    else if (strategy == DDW_SHRINK_IDENTITY) v = c * sij + (i == j ? (T(1) - c) : T(0));
-                    else if (strategy == DDW_SHRINK_SCALED_IDENTITY) v = c * sij + (i == j ? (T(1) - c) * tr : T(0));
+                    const T v = i == j ? fma(acc[x][y], wdiag, dadd) : acc[x][y] * woff;
                     S[i * N + j] = v;
                     S[j * N + i] = v;
                 }

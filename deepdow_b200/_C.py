@@ -39,6 +39,7 @@ SIGNATURES = {
                                        _vp, _sz, _vp]),
     "ddw_capped_simplex_fwd": (_i32, [_vp, _vp, _dbl, _dbl, _i64, _i64, _i32, _vp, _vp]),
     "ddw_capped_simplex_bwd": (_i32, [_vp, _vp, _vp, _vp, _dbl, _dbl, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "ddw_capped_argmax_fwd": (_i32, [_vp, _dbl, _i64, _i64, _i32, _vp, _vp]),
     "ddw_capped_softmax_fwd": (_i32, [_vp, _vp, _dbl, _dbl, _i64, _i64, _i32, _vp, _vp]),
     "ddw_capped_softmax_bwd": (_i32, [_vp, _vp, _vp, _vp, _dbl, _dbl, _i64, _i64, _i32, _vp, _vp, _vp]),
     "ddw_covariance_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),

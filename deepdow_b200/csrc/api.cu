@@ -151,6 +151,15 @@ int ddw_capped_simplex_bwd(const void *grad_w, const void *w, const void *x, con
     return row_call("ddw_capped_simplex_bwd", 1, x, temperature, temperature_scalar, max_weight, B, N, dtype, grad_w, w, nullptr, d_x, d_temperature, stream);
 }
 
+int ddw_capped_argmax_fwd(const void *x, double max_weight, int64_t B, int64_t N, int dtype, void *w, void *stream) {
+    if (!w) { set_error("ddw_capped_argmax_fwd: null output"); return DDW_ERR_ARG; }
+    if (!(max_weight > 0.0) || (double)N * max_weight < 1.0 - 1e-12) {
+        set_error("ddw_capped_argmax_fwd: n_assets * max_weight < 1, no fully invested portfolio exists");
+        return DDW_ERR_ARG;
+    }
+    return row_call("ddw_capped_argmax_fwd", 4, x, nullptr, 1.0, max_weight, B, N, dtype, nullptr, nullptr, w, nullptr, nullptr, stream);
+}
+
 int ddw_capped_softmax_fwd(const void *x, const void *temperature, double temperature_scalar, double max_weight,
                            int64_t B, int64_t N, int dtype, void *w, void *stream) {
     if (!w) { set_error("ddw_capped_softmax_fwd: null output"); return DDW_ERR_ARG; }

@@ -386,6 +386,80 @@ template <typename T> int capped_simplex_bwd_t(const RowParams<T> &p, cudaStream
 template <typename T> int capped_softmax_fwd_t(const RowParams<T> &p, cudaStream_t st) { DDW_ROW_DISPATCH(capped_softmax_fwd_kernel); }
 template <typename T> int capped_softmax_bwd_t(const RowParams<T> &p, cudaStream_t st) { DDW_ROW_DISPATCH(capped_softmax_bwd_kernel); }
 
+
+// ---- box-simplex LP: argmax x'w, sum w = 1, 0 <= w <= u (MaximumReturn, deepdow/benchmarks.py:114-125,160) -------------
+// The optimum fills the cap greedily from the largest entry down: floor(1/u) assets at u, the next one takes the rest.
+// One selection round per funded asset: group-wide (value, index) arg-max, ties to the smaller index.
+template <typename T, int NREG, int LPR, bool kVec>
+__global__ void __launch_bounds__(kRowWarps * 32) capped_argmax_kernel(RowParams<T> p, int kfull, T rem) {
+    long long row; int sub; bool live;
+    if (!row_of_group<LPR>(p.B, row, sub, live)) return;
+    const int N = p.N;
+    T v[NREG], w[NREG];
+    row_load<T, NREG, LPR, kVec>(p.x + row * N, N, sub, v, T(0));
+#pragma unroll
+    for (int m = 0; m < NREG; ++m) {
+        w[m] = T(0);
+        if (row_elem<LPR, kVec>(sub, m) >= N) v[m] = -Num<T>::inf();
+        else if (!(v[m] == v[m])) v[m] = -Num<T>::inf();      // NaN never wins a round
+    }
+    const int rounds = kfull + (rem > T(0) ? 1 : 0);
+#pragma unroll 1
+    for (int r = 0; r < rounds && r < N; ++r) {
+        T best = -Num<T>::inf();
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int m = 0; m < NREG; ++m) {
+            const int i = row_elem<LPR, kVec>(sub, m);
+            const bool open = i < N && w[m] == T(0);
+            if (open && (v[m] > best || (v[m] == best && i < bi))) { best = v[m]; bi = i; }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            const T ob = __shfl_xor_sync(kFullMask, best, o);
+            const int oi = __shfl_xor_sync(kFullMask, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        const T give = r < kfull ? p.u : rem;
+#pragma unroll
+        for (int m = 0; m < NREG; ++m)
+            if (row_elem<LPR, kVec>(sub, m) == bi) w[m] = give;
+    }
+    if (live) row_store<T, NREG, LPR, kVec>(p.out + row * N, N, sub, w);
+}
+
+template <typename T> int capped_argmax_t(const RowParams<T> &p, cudaStream_t st) {
+    // funded assets at the cap, and what is left for the next one (computed in double on the host)
+    const double u = (double)p.u;
+    int kfull = (int)floor(1.0 / u + 1e-9);
+    if (kfull > p.N) kfull = p.N;
+    double remd = 1.0 - kfull * u;
+    if (remd < 1e-12 || kfull >= p.N) remd = 0.0;
+    const T rem = (T)remd;
+#define DDW_ARGMAX_LAUNCH(NREG, LPR, VEC)                                                                 \
+    do {                                                                                                  \
+        const long long rows_per_block = (long long)kRowWarps * (32 / (LPR));                             \
+        const unsigned grid = (unsigned)((p.B + rows_per_block - 1) / rows_per_block);                    \
+        capped_argmax_kernel<T, NREG, LPR, VEC><<<grid, kRowWarps * 32, 0, st>>>(p, kfull, rem);          \
+    } while (0)
+#define DDW_ARGMAX_SIZES(VEC)                                                                             \
+    do {                                                                                                  \
+        if (p.N <= 64) DDW_ARGMAX_LAUNCH(16, 4, VEC);                                                     \
+        else if (p.N <= 128) DDW_ARGMAX_LAUNCH(16, 8, VEC);                                               \
+        else if (p.N <= 256) DDW_ARGMAX_LAUNCH(16, 16, VEC);                                              \
+        else if (p.N <= 512) DDW_ARGMAX_LAUNCH(16, 32, VEC);                                              \
+        else if (p.N <= 1024) DDW_ARGMAX_LAUNCH(32, 32, VEC);                                             \
+        else if (p.N <= 2048) DDW_ARGMAX_LAUNCH(64, 32, VEC);                                             \
+        else { set_error("capped_argmax_kernel: n_assets=%d > 2048 is not supported", p.N); return DDW_ERR_UNSUPPORTED; } \
+    } while (0)
+    if (p.B <= 0) return 0;
+    const bool vec = (p.N % 4 == 0) && aligned16(p.x) && aligned16(p.out);
+    if (vec) DDW_ARGMAX_SIZES(true); else DDW_ARGMAX_SIZES(false);
+    return check_launch("capped_argmax_kernel");
+#undef DDW_ARGMAX_SIZES
+#undef DDW_ARGMAX_LAUNCH
+}
+
 template <typename T>
 int row_op_t(int which, const void *x, const void *temperature, double tscalar, double u, long long B, int N,
              const void *grad_w, const void *w, void *out, void *d_x, void *d_t, cudaStream_t st) {
@@ -397,6 +471,7 @@ int row_op_t(int which, const void *x, const void *temperature, double tscalar, 
         case 0: return capped_simplex_fwd_t<T>(p, st);
         case 1: return capped_simplex_bwd_t<T>(p, st);
         case 2: return capped_softmax_fwd_t<T>(p, st);
+        case 4: return capped_argmax_t<T>(p, st);
         default: return capped_softmax_bwd_t<T>(p, st);
     }
 }

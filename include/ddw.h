@@ -155,6 +155,14 @@ int ddw_capped_softmax_bwd(const void *grad_w, const void *w, const void *x, con
                            void *d_x, void *d_temperature, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * MaximumReturn benchmark -- replaces self.optlayer(rets_estimate)[0] (deepdow/benchmarks.py:114-125, :160):
+ * argmax x'w  s.t. sum = 1, 0 <= w <= max_weight.  The linear program's vertex solution: floor(1/max_weight) largest
+ * entries at the cap, the next one takes the remainder; ties go to the smaller index.  Inference only (benchmarks are
+ * not trainable, benchmarks.py:13-15).  DDW_ERR_ARG when N * max_weight < 1.
+ * ------------------------------------------------------------------------------------------- */
+int ddw_capped_argmax_fwd(const void *x, double max_weight, int64_t B, int64_t N, int dtype, void *w, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * CovarianceMatrix -- replaces the python loop of misc.py:107-119.
  * x (B,L,N) observations; coef (B) shrinkage coefficient per sample (ignored for DDW_SHRINK_NONE);
  * out (B,N,N): shrunk sample covariance, or its symmetric PSD square root when do_sqrt != 0.

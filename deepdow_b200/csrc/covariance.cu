@@ -481,23 +481,32 @@ __global__ void __launch_bounds__(kPlainThreads) covariance_plain_kernel(CovPara
         const int i0 = XS <= kPlainThreads ? tid - q * XS : tid;
         const int PS = round_up(N, 4);
         const bool active = q < P;
+        // pointer-stepped loops: with run-time strides the compiler spent ~25 instructions per element on index arithmetic
+        const int rows = active ? (L - q + P - 1) / P : 0;       // rows q, q + P, ... of this thread
+        const int xstep = P * N, cstep = P * XS;
         if (active)
             for (int i = i0; i < N; i += kPlainThreads) {
-                T acc = T(0);
-                for (int l = q; l < L; l += P) acc += X[l * N + i];
-                part[q * PS + i] = acc;
+                const T *px = X + q * N + i;
+                T a0 = T(0), a1 = T(0);
+                int r = 0;
+                for (; r + 1 < rows; r += 2) { a0 += px[0]; a1 += px[xstep]; px += 2 * xstep; }
+                if (r < rows) a0 += px[0];
+                part[q * PS + i] = a0 + a1;
             }
         __syncthreads();
         if (active) {
             const T invL = T(1) / (T)L;
             for (int i = i0; i < XS; i += kPlainThreads) {
+                T *pc = Xc + q * XS + i;
                 if (i < N) {
                     T m = T(0);
                     for (int r = 0; r < P; ++r) m += part[r * PS + i];
                     m *= invL;
-                    for (int l = q; l < L; l += P) Xc[l * XS + i] = X[l * N + i] - m;
+                    const T *px = X + q * N + i;
+#pragma unroll 4
+                    for (int r = 0; r < rows; ++r) { *pc = *px - m; px += xstep; pc += cstep; }
                 } else {
-                    for (int l = q; l < L; l += P) Xc[l * XS + i] = T(0);
+                    for (int r = 0; r < rows; ++r) { *pc = T(0); pc += cstep; }
                 }
             }
         }
@@ -534,22 +543,36 @@ __global__ void __launch_bounds__(kPlainThreads) covariance_plain_kernel(CovPara
         const T *pa = Xc + 4 * ti, *pb = Xc + 4 * tj;
 #pragma unroll 4
         for (int l = 0; l < L; ++l) {
-            const Vec4<T> a = ld4(pa + l * XS), bb = ld4(pb + l * XS);
+            const Vec4<T> a = ld4(pa), bb = ld4(pb);
+            pa += XS; pb += XS;
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) acc[x][y] = fma(a.v[x], bb.v[y], acc[x][y]);
         }
+        const int i0t = 4 * ti, j0t = 4 * tj;
+        T *srow = S + i0t * N + j0t, *scol = S + j0t * N + i0t;      // the tile and its mirror image
+        if (i0t + 3 < N && ti != tj) {                               // interior off-diagonal tile: no bounds, no diagonal
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            const int i = 4 * ti + x;
+            for (int x = 0; x < 4; ++x)
 #pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const int j = 4 * tj + y;
-                if (i < N && j < N) {
-                    const T v = i == j ? fma(acc[x][y], wdiag, dadd) : acc[x][y] * woff;
-                    S[i * N + j] = v;
-                    S[j * N + i] = v;
+                for (int y = 0; y < 4; ++y) {
+                    const T v = acc[x][y] * woff;
+                    srow[x * N + y] = v;
+                    scol[y * N + x] = v;
+                }
+        } else {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int i = i0t + x;
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int j = j0t + y;
+                    if (i < N && j < N) {
+                        const T v = i == j ? fma(acc[x][y], wdiag, dadd) : acc[x][y] * woff;
+                        srow[x * N + y] = v;
+                        scol[y * N + x] = v;
+                    }
                 }
             }
         }

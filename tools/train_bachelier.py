@@ -48,11 +48,14 @@ def main():
     ap.add_argument("--lookback", type=int, default=40)
     ap.add_argument("--horizon", type=int, default=10)
     ap.add_argument("--loop", action="store_true")
+    ap.add_argument("--no-cudnn", action="store_true", help="run the recurrent cell on ATen's own kernels instead of cuDNN")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if a.no_cudnn:
+        torch.backends.cudnn.enabled = False
     dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
@@ -96,7 +99,8 @@ def main():
         print(json.dumps({"metric": "BachelierNet training samples/s", "value": world * a.batch / (per * 1e-3), "unit": "samples/s",
                           "n_gpus": world, "ms_per_step": per, "steps": a.steps, "scaling": "weak",
                           "config": {"n_assets": a.n_assets, "lookback": a.lookback, "horizon": a.horizon, "batch_per_gpu": a.batch,
-                                     "callers": "python loop over samples (reference formulation)" if a.loop else "batched RNN / attention"},
+                                     "callers": "python loop over samples (reference formulation)" if a.loop else "batched RNN / attention",
+                                     "cudnn": not a.no_cudnn},
                           "final_loss": float(loss.detach())}))
     if world > 1:
         dist.destroy_process_group()

@@ -268,22 +268,25 @@ __global__ void __launch_bounds__(kRowWarps * 32) capped_softmax_fwd_kernel(RowP
     const int N = p.N;
     const T u = p.u;
     const T t = p.temperature ? p.temperature[row] : p.temperature_scalar;
-    T e[NREG];
-    row_load<T, NREG, LPR, kVec>(p.x + row * N, N, sub, e, T(0));
+    T v[NREG], e[NREG];
+    row_load<T, NREG, LPR, kVec>(p.x + row * N, N, sub, v, T(0));
     T vmax = -Num<T>::inf();
     const bool unit_t = t == T(1);
     const T rt = T(1) / t;
 #pragma unroll
     for (int m = 0; m < NREG; ++m) {
-        const T q = unit_t ? e[m] : div_by(e[m], t, rt);
-        e[m] = row_elem<LPR, kVec>(sub, m) < N ? q : -Num<T>::inf();
-        vmax = e[m] > vmax ? e[m] : vmax;
+        const T q = unit_t ? v[m] : div_by(v[m], t, rt);
+        v[m] = row_elem<LPR, kVec>(sub, m) < N ? q : -Num<T>::inf();
+        vmax = v[m] > vmax ? v[m] : vmax;
     }
     vmax = group_max<LPR>(vmax);
 #pragma unroll
-    for (int m = 0; m < NREG; ++m) e[m] = row_elem<LPR, kVec>(sub, m) < N ? expT(e[m] - vmax) : T(0);
+    for (int m = 0; m < NREG; ++m) e[m] = row_elem<LPR, kVec>(sub, m) < N ? expT(v[m] - vmax) : T(0);
     // The capped set only grows: rescale the rest to the remaining mass, cap what now exceeds u, repeat.  This is Newton on
     // the concave piecewise-linear sum min(u, e s) = 1 in the scale s, from the left: monotone, ends after finitely many steps.
+    // When the logits are spread wider than the exponent range and the cap pushes mass far down the row, the exponentials
+    // of the assets still free underflow against the row maximum: they are then re-based on the largest free logit.
+    const T tiny_sum = sizeof(T) == 4 ? T(1e-30) : T(1e-290);
     int ncap = 0;                      // a capped slot is marked by e = -1 (padding holds 0 and never exceeds the cap)
     T scale = T(0);
     bool done = false;
@@ -293,6 +296,20 @@ __global__ void __launch_bounds__(kRowWarps * 32) capped_softmax_fwd_kernel(RowP
 #pragma unroll
         for (int m = 0; m < NREG; ++m) sF += e[m] > T(0) ? e[m] : T(0);
         sF = group_sum<LPR>(sF);
+        const bool rebase = !done && sF < tiny_sum && ncap < N;
+        if (__any_sync(kFullMask, rebase)) {
+            T vm = -Num<T>::inf();
+#pragma unroll
+            for (int m = 0; m < NREG; ++m) vm = (e[m] >= T(0) && v[m] > vm) ? v[m] : vm;
+            vm = group_max<LPR>(vm);
+            T s2 = T(0);
+#pragma unroll
+            for (int m = 0; m < NREG; ++m) {
+                if (rebase && e[m] >= T(0)) e[m] = expT(v[m] - vm);      // padding: exp(-inf) = 0
+                s2 += e[m] > T(0) ? e[m] : T(0);
+            }
+            sF = group_sum<LPR>(s2);
+        }
         const T mass = T(1) - u * (T)ncap;
         const bool empty = !(sF > T(0)) || !(mass > T(0));
         if (!done) scale = empty ? T(0) : mass / sF;

@@ -469,3 +469,35 @@ def test_compute_sqrt_static(dtype):
         assert rel_err(r @ r, Min) < (5e-5 if dtype == torch.float32 else 1e-10)
         (r * t(G, dtype)).sum().backward()
         assert rel_err(m.grad, oracle.psd_sqrt_bwd(G[None], Min[None])[0]) < (2e-3 if dtype == torch.float32 else 1e-7)
+
+
+# ------------------------------------------------------------------ row allocators: randomized sweep over every layout
+@pytest.mark.parametrize("seed", range(6))
+def test_row_allocators_random_shapes(seed):
+    """Random (n_samples, n_assets, cap, scale) per seed: every lanes-per-row / vector / scalar variant of rowproj.cu, ragged batch
+    ends, caps from barely feasible to loose, logits from nearly flat to widely spread; sparsemax, capped softmax and the greedy LP."""
+    from deepdow_b200.benchmarks import MaximumReturn
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(12):
+        N = int(rng.choice([2, 3, 4, 7, 16, 31, 64, 65, 100, 128, 129, 200, 256, 257, 500, 512, 600, 1024, 1500]))
+        B = int(rng.integers(1, 70))
+        slack = float(rng.choice([1.0 + 1e-3, 1.3, 2.0, 7.7, N]))          # n_assets * cap
+        u = min(1.0, slack / N)
+        if N * float(np.float32(u)) < 1:
+            u = min(1.0, 1.01 * slack / N)
+        scale = float(rng.choice([1e-3, 0.3, 3.0, 40.0]))
+        dtype = torch.float32 if rng.random() < 0.6 else torch.float64
+        uk = float(np.float32(u)) if dtype == torch.float32 else u
+        x = rng.standard_normal((B, N)) * scale
+        xin = t(x, dtype).double().cpu().numpy()
+        tag = (N, B, u, scale, str(dtype))
+        w = SparsemaxAllocator(N, temperature=1, max_weight=uk)(t(x, dtype)).double().cpu().numpy()
+        ref = oracle.capped_simplex_fwd(xin, np.ones(B), uk)
+        assert np.abs(w - ref).max() < W_ATOL[dtype] * max(1.0, scale / 3), ("sparsemax",) + tag
+        assert np.abs(w.sum(1) - 1).max() < 1e-5 and w.min() >= 0 and w.max() <= uk * (1 + 1e-6), ("sparsemax",) + tag
+        w = SoftmaxAllocator(temperature=1, formulation="variational", n_assets=N, max_weight=uk)(t(x, dtype)).double().cpu().numpy()
+        ref = oracle.capped_softmax_fwd(xin, np.ones(B), uk)
+        assert np.abs(w - ref).max() < W_ATOL[dtype] * max(1.0, scale / 3), ("softmax",) + tag
+        w = MaximumReturn(max_weight=uk)(t(x, dtype)[:, None, None, :]).double().cpu().numpy()
+        ref = oracle.capped_argmax_fwd(xin, uk)
+        assert np.abs(w - ref).max() < (2e-6 if dtype == torch.float32 else 1e-12), ("argmax",) + tag

@@ -544,3 +544,41 @@ def test_markowitz_random_shapes(seed):
             w32 = NumericalMarkowitz(N, float(np.float32(u)) if N * float(np.float32(u)) >= 1 else u)(
                 t(rets, torch.float32), t(C, torch.float32), t(g, torch.float32), t(a, torch.float32))
             assert np.abs(w32.double().cpu().numpy() - w_ref).max() < 3e-5 * max(1.0, rscale), tag
+
+
+# ------------------------------------------------------------------ CovarianceMatrix: randomized sweep
+@pytest.mark.parametrize("seed", range(4))
+def test_covariance_random_shapes(seed):
+    """Random (batch, lookback, n_assets, strategy, sqrt, per-sample coefficient, data scale) per seed against the oracle: float64
+    forward and gradients (x and shrinkage_coef), float32 forward.  Crosses the plain-kernel / general-kernel boundary (75 KB of
+    shared memory), aligned and unaligned tile sizes, lookbacks shorter and longer than the asset count."""
+    rng = np.random.default_rng(900 + seed)
+    for _ in range(8):
+        N = int(rng.choice([1, 2, 3, 5, 8, 13, 20, 32, 50, 51, 64, 100, 101, 130]))
+        L = int(rng.choice([2, 3, 7, 16, 40, 41, 60, 120]))
+        B = int(rng.integers(1, 12 if N < 100 else 4))
+        strategy = [None, "diagonal", "identity", "scaled_identity"][int(rng.integers(0, 4))]
+        sqrt = bool(rng.integers(0, 2))
+        scale = float(rng.choice([0.01, 1.0, 30.0]))
+        x = rng.standard_normal((B, L, N)) * scale + rng.standard_normal((1, 1, N)) * scale   # non-zero column means
+        coef = rng.uniform(0.2, 0.9, B)
+        G = rng.standard_normal((B, N, N))
+        tag = (N, L, B, strategy, sqrt, scale)
+        ref = oracle.covariance_fwd(x, coef, strategy, sqrt)
+        layer = CovarianceMatrix(sqrt=sqrt, shrinkage_strategy=strategy, shrinkage_coef=None if strategy is not None else 0.5)
+        tx = t(x, torch.float64, True)
+        tc = t(coef, torch.float64, True) if strategy is not None else None
+        y = layer(tx, tc) if strategy is not None else layer(tx)
+        assert rel_err(y, ref) < 1e-9, tag
+        # gradients: only where the square root is smooth (full-rank shrunk covariance) or no square root is taken
+        full_rank = strategy in ("diagonal", "identity", "scaled_identity") or L - 1 >= N
+        if not sqrt or (full_rank and strategy is not None):
+            (y * t(G, torch.float64)).sum().backward()
+            dx_ref, dc_ref = oracle.covariance_bwd(G, x, coef, strategy, sqrt)
+            assert rel_err(tx.grad, dx_ref) < 1e-6, ("dx", rel_err(tx.grad, dx_ref)) + tag
+            if strategy is not None:
+                assert rel_err(tc.grad, dc_ref) < 1e-6, ("dcoef", rel_err(tc.grad, dc_ref)) + tag
+        x32 = t(x, torch.float32)
+        ref32 = oracle.covariance_fwd(x32.double().cpu().numpy(), coef.astype(np.float32).astype(np.float64), strategy, sqrt)
+        y32 = layer(x32, t(coef, torch.float32)) if strategy is not None else layer(x32)
+        assert rel_err(y32, ref32) < (1e-4 if sqrt else 3e-5), ("f32", rel_err(y32, ref32)) + tag

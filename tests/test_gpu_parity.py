@@ -579,6 +579,12 @@ def test_covariance_random_shapes(seed):
             if strategy is not None:
                 assert rel_err(tc.grad, dc_ref) < 1e-6, ("dcoef", rel_err(tc.grad, dc_ref)) + tag
         x32 = t(x, torch.float32)
+        if sqrt:
+            # the reference drops singular values below s.max * n * eps OF THE INPUT DTYPE (misc.py:185-187): a spectrum that
+            # reaches down to the float32 threshold is cut differently in float32 and in the float64 oracle -- not comparable
+            lam = np.abs(np.linalg.eigvalsh(oracle.covariance_fwd(x, coef, strategy, False)))
+            if (lam.min(1) < 1e3 * lam.max(1) * N * np.finfo(np.float32).eps).any():
+                continue
         ref32 = oracle.covariance_fwd(x32.double().cpu().numpy(), coef.astype(np.float32).astype(np.float64), strategy, sqrt)
         y32 = layer(x32, t(coef, torch.float32)) if strategy is not None else layer(x32)
         assert rel_err(y32, ref32) < (1e-4 if sqrt else 3e-5), ("f32", rel_err(y32, ref32)) + tag

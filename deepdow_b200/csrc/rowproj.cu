@@ -2,9 +2,9 @@
 // deepdow/layers/allocate.py:554-560,580-595) and capped softmax (variational SoftmaxAllocator,
 // allocate.py:470-475,495-514), forward and backward.
 //
-// A row is owned by a GROUP of LPR lanes (4, 8, 16 or 32) holding NREG = 16+ values each, so a warp works on
-// 32 / LPR rows at once: a row of 100 is 8 lanes x 16 values, and a reduction over the row is 3 shuffle steps shared by
-// four rows instead of 5 for one (the kernels were bound by the SM's shuffle rate with one warp per row).  Integer counts
+// A row is owned by a GROUP of LPR lanes (4, 16 or 32) holding NREG = 16+ values each, so a warp works on
+// 32 / LPR rows at once: a row of 100 is 4 lanes x 32 values, and a reduction over the row is 2 shuffle steps shared by
+// eight rows instead of 5 for one (the kernels were bound by the SM's shuffle rate with one warp per row).  Integer counts
 // travel packed in one word.  A row costs one coalesced read of x and one coalesced write of w: (2N+1) elements of HBM
 // traffic forward, 3N backward.  Rows whose length is a multiple of 4 move as 16-byte vectors (row_load / row_store).
 #include "common.cuh"
@@ -381,7 +381,7 @@ static bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 
 #define DDW_ROW_SIZES(KERNEL, VEC)                                                                        \
     do {                                                                                                  \
         if (p.N <= 64) DDW_ROW_LAUNCH(KERNEL, 16, 4, VEC);                                                \
-        else if (p.N <= 128) DDW_ROW_LAUNCH(KERNEL, 16, 8, VEC);                                          \
+        else if (p.N <= 128) DDW_ROW_LAUNCH(KERNEL, 32, 4, VEC);                                          \
         else if (p.N <= 256) DDW_ROW_LAUNCH(KERNEL, 16, 16, VEC);                                         \
         else if (p.N <= 512) DDW_ROW_LAUNCH(KERNEL, 16, 32, VEC);                                         \
         else if (p.N <= 1024) DDW_ROW_LAUNCH(KERNEL, 32, 32, VEC);                                        \

@@ -268,25 +268,98 @@ __host__ __device__ __forceinline__ int gram_tiles_per_thread(int n, int threads
 // ------------------------------------------------------------------------------------------------
 // In-place unscaled LDL' of the n x n lower triangle stored column-major at Lb (element (i,k) at
 // Lb[k*ld + i]) with `nrhs` extra rows n .. n+nrhs-1 that undergo the same elimination (so row
-// n+q ends up holding D * L^-1 * rhs_q).  dinv[k] = 1 / pivot_k.  One barrier per column.
+// n+q ends up holding D * L^-1 * rhs_q).  dinv[k] = 1 / pivot_k.
 // Returns nonzero when a pivot had to be lifted.
 // ------------------------------------------------------------------------------------------------
+// Blocked right-looking form, panels of kLdlNb columns, three block barriers per panel:
+//   panel     every thread factors the kLdlNb x kLdlNb diagonal block redundantly in registers (85 FMAs), then eliminates
+//             its own row(s) below the block against it -- no barrier inside the panel;
+//   trailing  warps take blocks of 4 columns, lanes take rows: the panel's entries of a row are loaded once and used for
+//             all 4 columns, the 4 x kLdlNb multipliers live in registers (1.5 instructions per FMA).
+// The column-at-a-time form this replaces (one barrier and one short row loop per (k, j) pair) spent 19 instructions per
+// FMA at n = 86: 80% of the dense forward kernel's instructions (ncu, profiles/r01_final/dense_regime.txt).
+constexpr int kLdlNb = 8;
+
 template <typename T, int kThreads>
 __device__ __forceinline__ int factor_ldl(T *Lb, int ld, int n, int nrhs, T *dinv, T dmin) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NB = kLdlNb, JB = 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kThreads / 32;
     int lifted = 0;
     const int rows = n + nrhs;
-    for (int k = 0; k < n; ++k) {
-        const T *colk = Lb + k * ld;
-        T d = colk[k];
-        if (!(d > dmin)) { d = dmin; lifted = 1; }
-        const T invd = T(1) / d;
-        if (threadIdx.x == 0) dinv[k] = invd;
-        for (int j = k + 1 + warp; j < n; j += kWarps) {
-            const T cj = colk[j] * invd;
-            T *colj = Lb + j * ld;
-            for (int i = j + lane; i < rows; i += 32) colj[i] = fma(-colk[i], cj, colj[i]);
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int kb = min(NB, n - k0);
+        // ---- panel: diagonal block in registers (lower triangle, element (a, c) of the block at Bd[a][c], c <= a)
+        T Bd[NB][NB], inv[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+#pragma unroll
+            for (int a2 = c; a2 < NB; ++a2) Bd[a2][c] = (a2 < kb) ? Lb[(k0 + c) * ld + k0 + a2] : T(0);
+        __syncthreads();                     // every thread holds the block before its owners write the factored rows back
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            T d = Bd[c][c];
+            if (c < kb && !(d > dmin)) { d = dmin; lifted = 1; }
+            inv[c] = c < kb ? T(1) / d : T(0);
+#pragma unroll
+            for (int j = c + 1; j < NB; ++j) {
+                const T cj = Bd[j][c] * inv[c];
+#pragma unroll
+                for (int a2 = j; a2 < NB; ++a2) Bd[a2][j] = fma(-Bd[a2][c], cj, Bd[a2][j]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+            if (tid == c && c < kb) dinv[k0 + c] = inv[c];
+        // rows of the block itself: thread t < kb writes row t back; rows below: one row per thread and pass
+        for (int i = k0 + tid; i < rows; i += kThreads) {
+            const int t = i - k0;
+            if (t < kb) {
+#pragma unroll
+                for (int a2 = 0; a2 < NB; ++a2)
+                    if (a2 == t) {
+#pragma unroll
+                        for (int c = 0; c <= a2; ++c) Lb[(k0 + c) * ld + i] = Bd[a2][c];
+                    }
+            } else {
+                T v[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) v[c] = c < kb ? Lb[(k0 + c) * ld + i] : T(0);
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    const T vc = v[c] * inv[c];
+#pragma unroll
+                    for (int j = c + 1; j < NB; ++j) v[j] = fma(-vc, Bd[j][c], v[j]);
+                }
+#pragma unroll
+                for (int c = 1; c < NB; ++c)
+                    if (c < kb) Lb[(k0 + c) * ld + i] = v[c];
+            }
+        }
+        __syncthreads();
+        // ---- trailing update: col_j[i] -= sum_c col_c[i] * col_c[j] / d_c, c over the panel, j >= k0 + kb, i >= j
+        const int j0 = k0 + kb;
+        for (int jb = j0 + JB * warp; jb < n; jb += JB * kWarps) {
+            T cf[JB][NB];
+#pragma unroll
+            for (int q = 0; q < JB; ++q)
+#pragma unroll
+                for (int c = 0; c < NB; ++c) cf[q][c] = (jb + q < n && c < kb) ? Lb[(k0 + c) * ld + jb + q] * inv[c] : T(0);
+            for (int i = jb + lane; i < rows; i += 32) {
+                T av[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) av[c] = c < kb ? Lb[(k0 + c) * ld + i] : T(0);
+#pragma unroll
+                for (int q = 0; q < JB; ++q) {
+                    if (jb + q < n && i >= jb + q) {
+                        T *pe = Lb + (jb + q) * ld + i;
+                        T acc = *pe;
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) acc = fma(-av[c], cf[q][c], acc);
+                        *pe = acc;
+                    }
+                }
+            }
         }
         __syncthreads();
     }

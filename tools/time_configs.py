@@ -42,3 +42,21 @@ t_f = timeit(lambda: l(*[t.detach() for t in ins]), 2)
 t_fb = timeit(lambda: torch.autograd.grad(l(*ins), ins, G), 2)
 w = l(*ins); nf = ((w > 0) & (w < 0.05)).sum(1).float().mean().item()
 print(f"C5  N=500 L=250 B=1024: covariance(sqrt) {t_cov:.1f} ms, markowitz fwd {t_f:.1f} ms, fwd+bwd {t_fb:.1f} ms (mean free {nf:.1f})")
+# C4 as BASELINE.json states it: ThorpNet(n_assets=100, max_weight=0.2), batch 4096 (identical problems; solved one by one, not deduplicated)
+from deepdow_b200 import nn as dnn
+net = dnn.ThorpNet(100, max_weight=0.2).to(dev)
+with torch.no_grad():
+    net.exp_returns.normal_(0, 0.1); net.matrix.add_(0.05 * torch.randn(100, 100, device=dev))
+opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+X4 = torch.randn(4096, 1, 5, 100, device=dev); y4 = torch.randn(4096, 1, 10, 100, device=dev) * 0.01
+def thorp_step():
+    loss = dnn.sharpe_ratio_loss(net(X4), y4).mean()
+    opt.zero_grad(set_to_none=True); loss.backward(); opt.step()
+print(f"C4  ThorpNet N=100 B=4096 max_weight=0.2: training step {timeit(thorp_step, 10):.3f} ms")
+# C2 as BASELINE.json states it: BachelierNet training (tools/train_bachelier.py has the multi-GPU form)
+bn = dnn.BachelierNet(1, 50, hidden_size=32).to(dev); ob = torch.optim.Adam(bn.parameters(), lr=1e-2)
+X2 = torch.randn(256, 1, 40, 50, device=dev) * 0.01; y2 = torch.randn(256, 1, 10, 50, device=dev) * 0.01
+def bach_step():
+    loss = dnn.sharpe_ratio_loss(bn(X2), y2).mean()
+    ob.zero_grad(set_to_none=True); loss.backward(); ob.step()
+print(f"C2  BachelierNet N=50 L=40 H=10 B=256: training step {timeit(bach_step, 10):.3f} ms")

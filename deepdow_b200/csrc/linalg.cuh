@@ -341,6 +341,29 @@ __device__ __forceinline__ int factor_ldl(T *Lb, int ld, int n, int nrhs, T *din
         const int j0 = k0 + kb;
         for (int jb = j0 + JB * warp; jb < n; jb += JB * kWarps) {
             T cf[JB][NB];
+            if (kb == NB && jb + JB <= n) {
+                // full panel, full column block: no bounds tests; only the rows inside the block's own triangle are masked
+#pragma unroll
+                for (int q = 0; q < JB; ++q)
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) cf[q][c] = Lb[(k0 + c) * ld + jb + q] * inv[c];
+                for (int i = jb + lane; i < rows; i += 32) {
+                    T av[NB];
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) av[c] = Lb[(k0 + c) * ld + i];
+                    T *pe = Lb + jb * ld + i;
+#pragma unroll
+                    for (int q = 0; q < JB; ++q) {
+                        if (i >= jb + q) {
+                            T acc = pe[q * ld];
+#pragma unroll
+                            for (int c = 0; c < NB; ++c) acc = fma(-av[c], cf[q][c], acc);
+                            pe[q * ld] = acc;
+                        }
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int q = 0; q < JB; ++q)
 #pragma unroll

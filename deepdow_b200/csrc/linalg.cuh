@@ -291,10 +291,18 @@ __device__ __forceinline__ int factor_ldl(T *Lb, int ld, int n, int nrhs, T *din
         const int kb = min(NB, n - k0);
         // ---- panel: diagonal block in registers (lower triangle, element (a, c) of the block at Bd[a][c], c <= a)
         T Bd[NB][NB], inv[NB];
+        const bool fullp = kb == NB;         // full panel: no bounds tests anywhere below (they cost as much as the arithmetic)
+        if (fullp) {
 #pragma unroll
-        for (int c = 0; c < NB; ++c)
+            for (int c = 0; c < NB; ++c)
 #pragma unroll
-            for (int a2 = c; a2 < NB; ++a2) Bd[a2][c] = (a2 < kb) ? Lb[(k0 + c) * ld + k0 + a2] : T(0);
+                for (int a2 = c; a2 < NB; ++a2) Bd[a2][c] = Lb[(k0 + c) * ld + k0 + a2];
+        } else {
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+#pragma unroll
+                for (int a2 = c; a2 < NB; ++a2) Bd[a2][c] = (a2 < kb) ? Lb[(k0 + c) * ld + k0 + a2] : T(0);
+        }
         __syncthreads();                     // every thread holds the block before its owners write the factored rows back
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
@@ -323,17 +331,28 @@ __device__ __forceinline__ int factor_ldl(T *Lb, int ld, int n, int nrhs, T *din
                     }
             } else {
                 T v[NB];
+                T *pr = Lb + k0 * ld + i;
+                if (fullp) {
 #pragma unroll
-                for (int c = 0; c < NB; ++c) v[c] = c < kb ? Lb[(k0 + c) * ld + i] : T(0);
+                    for (int c = 0; c < NB; ++c) v[c] = pr[c * ld];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) v[c] = c < kb ? pr[c * ld] : T(0);
+                }
 #pragma unroll
                 for (int c = 0; c < NB; ++c) {
                     const T vc = v[c] * inv[c];
 #pragma unroll
                     for (int j = c + 1; j < NB; ++j) v[j] = fma(-vc, Bd[j][c], v[j]);
                 }
+                if (fullp) {
 #pragma unroll
-                for (int c = 1; c < NB; ++c)
-                    if (c < kb) Lb[(k0 + c) * ld + i] = v[c];
+                    for (int c = 1; c < NB; ++c) pr[c * ld] = v[c];
+                } else {
+#pragma unroll
+                    for (int c = 1; c < NB; ++c)
+                        if (c < kb) pr[c * ld] = v[c];
+                }
             }
         }
         __syncthreads();

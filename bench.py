@@ -321,6 +321,34 @@ def main():
     barrier()
     fwd_only_ms = f0.elapsed_time(f1)
 
+    # side measurement (rank-local, not part of `value`): the same matrices with expected returns scaled down 25x, so that
+    # ~86 of the 100 assets end up free -- the diversified regime BachelierNet / ThorpNet train in, which runs through the
+    # dense kernels (profiles/r01_final/dense_regime.txt)
+    dense_info = None
+    try:
+        d_in = [(rets.detach() * 0.04).requires_grad_()] + [t.detach().clone().requires_grad_() for t in (C, gam, alp)]
+        d0, d1, d2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        n_dense = 5
+        for _ in range(2):
+            torch.autograd.grad(layer(*d_in), d_in, G)
+        with torch.no_grad():
+            d0.record()
+            for _ in range(n_dense):
+                wd = layer(*d_in)
+            d1.record()
+        for _ in range(n_dense):
+            torch.autograd.grad(layer(*d_in), d_in, G)
+        d2.record()
+        torch.cuda.synchronize()
+        dense_info = {"workload": "same covmat_sqrt, rets~N(0,0.02^2): diversified optimum",
+                      "mean_free": float(((wd > 0) & (wd < u)).sum(1).float().mean()),
+                      "fwd_only": {"value": B * n_dense / (d0.elapsed_time(d1) * 1e-3), "unit": UNIT + " per GPU"},
+                      "fwd_bwd": {"value": B * n_dense / (d1.elapsed_time(d2) * 1e-3), "unit": UNIT + " per GPU"}}
+        del d_in, wd
+    except Exception as exc:                      # never let the side measurement take the bench line down
+        dense_info = {"error": f"{type(exc).__name__}: {exc}"}
+    barrier()
+
     # ---- timed region 2: end to end from pinned host buffers -----------------------------------
     # (a) the host-buffer C-ABI call (ddw_markowitz_host_step through MarkowitzHostPipeline): chunks flow through
     #     H2D / kernels / D2H streams; every input comes from and every output lands in pinned host memory
@@ -428,6 +456,7 @@ def main():
                                  "markowitz_ipm_kernel (fallback list, empty here)", "markowitz_bwd_sparse_kernel",
                                  "markowitz_bwd_kernel (dense work list)", "markowitz_gamma_kernel"],
             "fwd_only": {"value": world * B * steps_total / (fwd_only_ms * 1e-3), "unit": UNIT},
+            "dense_regime": dense_info,
             "phase_ms": {"fwd": fwd_ms, "bwd": bwd_ms, "host_enqueue": cpu_enqueue_ms,
                          "source": "CUDA-graph replays (forward alone; step minus forward)" if graph_ms is not None
                          else "CUDA events around the eager layer calls"},

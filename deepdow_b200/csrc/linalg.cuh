@@ -271,7 +271,7 @@ __host__ __device__ __forceinline__ int gram_tiles_per_thread(int n, int threads
 // n+q ends up holding D * L^-1 * rhs_q).  dinv[k] = 1 / pivot_k.
 // Returns nonzero when a pivot had to be lifted.
 // ------------------------------------------------------------------------------------------------
-// Blocked right-looking form, panels of kLdlNb columns, three block barriers per panel:
+// Blocked right-looking form, panels of kLdlNb columns, two block barriers per panel:
 //   panel     every thread factors the kLdlNb x kLdlNb diagonal block redundantly in registers (85 FMAs), then eliminates
 //             its own row(s) below the block against it -- no barrier inside the panel;
 //   trailing  warps take blocks of 4 columns, lanes take rows: the panel's entries of a row are loaded once and used for
@@ -303,7 +303,6 @@ __device__ __forceinline__ int factor_ldl(T *Lb, int ld, int n, int nrhs, T *din
 #pragma unroll
                 for (int a2 = c; a2 < NB; ++a2) Bd[a2][c] = (a2 < kb) ? Lb[(k0 + c) * ld + k0 + a2] : T(0);
         }
-        __syncthreads();                     // every thread holds the block before its owners write the factored rows back
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
             T d = Bd[c][c];
@@ -319,17 +318,10 @@ __device__ __forceinline__ int factor_ldl(T *Lb, int ld, int n, int nrhs, T *din
 #pragma unroll
         for (int c = 0; c < NB; ++c)
             if (tid == c && c < kb) dinv[k0 + c] = inv[c];
-        // rows of the block itself: thread t < kb writes row t back; rows below: one row per thread and pass
+        // rows below the block: one row per thread and pass, eliminated against the block held in registers
         for (int i = k0 + tid; i < rows; i += kThreads) {
             const int t = i - k0;
-            if (t < kb) {
-#pragma unroll
-                for (int a2 = 0; a2 < NB; ++a2)
-                    if (a2 == t) {
-#pragma unroll
-                        for (int c = 0; c <= a2; ++c) Lb[(k0 + c) * ld + i] = Bd[a2][c];
-                    }
-            } else {
+            if (t >= kb) {
                 T v[NB];
                 T *pr = Lb + k0 * ld + i;
                 if (fullp) {
@@ -356,6 +348,16 @@ __device__ __forceinline__ int factor_ldl(T *Lb, int ld, int n, int nrhs, T *din
             }
         }
         __syncthreads();
+        // the factored rows of the diagonal block go back only now: during the panel every thread was still reading the
+        // block, and nothing below reads these entries (the trailing update takes rows >= k0 + kb of the panel columns)
+        if (tid < kb) {
+#pragma unroll
+            for (int a2 = 0; a2 < NB; ++a2)
+                if (a2 == tid) {
+#pragma unroll
+                    for (int c = 0; c <= a2; ++c) Lb[(k0 + c) * ld + k0 + tid] = Bd[a2][c];
+                }
+        }
         // ---- trailing update: col_j[i] -= sum_c col_c[i] * col_c[j] / d_c, c over the panel, j >= k0 + kb, i >= j
         const int j0 = k0 + kb;
         for (int jb = j0 + JB * warp; jb < n; jb += JB * kWarps) {

@@ -307,7 +307,7 @@ __device__ __forceinline__ int factor_ldl(T *Lb, int ld, int n, int nrhs, T *din
         for (int c = 0; c < NB; ++c) {
             T d = Bd[c][c];
             if (c < kb && !(d > dmin)) { d = dmin; lifted = 1; }
-            inv[c] = c < kb ? T(1) / d : T(0);
+            inv[c] = c < kb ? recipFastT(d) : T(0);     // d > dmin > 0: the hardware reciprocal + one Newton step is within 1 ulp
 #pragma unroll
             for (int j = c + 1; j < NB; ++j) {
                 const T cj = Bd[j][c] * inv[c];

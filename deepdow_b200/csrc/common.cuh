@@ -134,4 +134,33 @@ __host__ __device__ __forceinline__ int round_up(int v, int m) { return (v + m -
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);
 
+// ---- per-device launch configuration ------------------------------------------------------------------------------
+// cudaFuncSetAttribute (the > 48 KB dynamic shared-memory opt-in) and the opt-in limit itself belong to a DEVICE: a
+// process that drives several GPUs (DataParallel threads, a model moved to cuda:1) must configure every kernel once
+// per device it launches on.  DeviceOnce is a per-kernel-instance table of "configured on device d" flags; setting the
+// attribute twice is harmless, so plain relaxed atomics are enough for thread safety.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+struct DeviceOnce {
+    volatile unsigned char done[kMaxDevices];
+    bool needs(int dev) const { return !done[dev]; }
+    void mark(int dev) { done[dev] = 1; }
+};
+// the device's opt-in shared-memory limit per block, cached per device
+inline int device_smem_limit() {
+    static volatile int lim[kMaxDevices];
+    const int dev = current_device();
+    int v = lim[dev];
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) v = 48 * 1024;
+        cudaGetLastError();
+        lim[dev] = v;
+    }
+    return v;
+}
+
 }  // namespace ddw

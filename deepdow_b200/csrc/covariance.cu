@@ -601,16 +601,7 @@ struct CovPlan {
     size_t smem, per_sample_ws;
 };
 
-static int cov_smem_limit() {
-    static int lim = -1;
-    if (lim < 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) lim = 48 * 1024;
-        cudaGetLastError();
-    }
-    return lim;
-}
+static int cov_smem_limit() { return device_smem_limit(); }   // of the current device
 
 static CovPlan cov_plan_fwd(int L, int N, int tsize, int do_sqrt) {
     CovPlan pl;
@@ -655,9 +646,16 @@ static CovPlan cov_plan_bwd(int L, int N, int tsize, int do_sqrt) {
     return pl;
 }
 
+// eig_block.cu: float32 forward for matrices beyond shared memory (tensor-core Gram + blocked Jacobi)
+size_t eig_block_workspace_bytes(long long B, int N);
+int covariance_fwd_large_f32(const float *x, const float *coef, int strategy, int do_sqrt, long long B, int L, int N, float *out,
+                             float *eigvec, float *eigval, int32_t *sweeps, void *ws, size_t ws_bytes, cudaStream_t st);
+
 size_t covariance_workspace_bytes(long long B, int L, int N, int tsize, int do_sqrt) {
     const CovPlan pf = cov_plan_fwd(L, N, tsize, do_sqrt), pb = cov_plan_bwd(L, N, tsize, do_sqrt);
-    return (size_t)B * max(pf.per_sample_ws, pb.per_sample_ws);
+    size_t fwd = (size_t)B * pf.per_sample_ws;
+    if (pf.global_m && tsize == 4) fwd = eig_block_workspace_bytes(B, N);
+    return max(fwd, (size_t)B * pb.per_sample_ws);
 }
 
 template <typename T>
@@ -669,17 +667,20 @@ int covariance_fwd_t(const void *x, const void *coef, int strategy, int do_sqrt,
         q.x = (const T *)x; q.coef = (const T *)coef; q.strategy = strategy; q.B = B; q.L = L; q.N = N;
         q.AS = round_up(N, 4); q.out = (T *)out;
         const size_t smem = cov_plain_smem(L, N, sizeof(T));
-        static size_t attr_set[2] = {0, 0};   // largest dynamic size already granted per dtype (the attribute is per function)
-        size_t &granted = attr_set[sizeof(T) == 8];
-        if (smem > 48 * 1024 && smem > granted) {
-            if (cudaFuncSetAttribute(covariance_plain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        static DeviceOnce configured;     // per dtype instance and per device: opt in to the plain kernel's ceiling once
+        const int dev = current_device();
+        if (smem > 48 * 1024 && configured.needs(dev)) {
+            if (cudaFuncSetAttribute(covariance_plain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024) != cudaSuccess)
                 return check_launch("cudaFuncSetAttribute(covariance_plain_kernel)");
-            granted = smem;
+            configured.mark(dev);
         }
         covariance_plain_kernel<T><<<(unsigned)B, kPlainThreads, smem, st>>>(q);
         return check_launch("covariance_plain_kernel");
     }
     const CovPlan pl = cov_plan_fwd(L, N, sizeof(T), do_sqrt);
+    if (pl.global_m && sizeof(T) == 4)     // beyond shared memory: tensor-core Gram + blocked Jacobi (eig_block.cu)
+        return covariance_fwd_large_f32((const float *)x, (const float *)coef, strategy, do_sqrt, B, L, N, (float *)out, (float *)eigvec,
+                                        (float *)eigval, sweeps, ws, ws_bytes, st);
     if (pl.global_m && (ws_bytes < (size_t)B * pl.per_sample_ws || !ws)) { set_error("ddw_covariance_fwd: workspace too small"); return DDW_ERR_WORKSPACE; }
     if (pl.smem > (size_t)cov_smem_limit()) { set_error("ddw_covariance_fwd: n_assets=%d needs %zu B of shared memory", N, pl.smem); return DDW_ERR_UNSUPPORTED; }
     CovParams<T> p;

@@ -225,14 +225,12 @@ namespace ddw {
 
 template <typename T> int launch_bwd_sparse(const MkBwdParams<T> &p, cudaStream_t st) {
     auto kb = markowitz_bwd_sparse_kernel<T, 128>;
-    static bool configured = false;
-    if (!configured) {
-        int dev = 0, lim = 48 * 1024;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess)
+    static DeviceOnce configured;     // per template instance and per device
+    const int dev = current_device();
+    if (configured.needs(dev)) {
+        if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, device_smem_limit()) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(markowitz_bwd_sparse)");
-        configured = true;
+        configured.mark(dev);
     }
     kb<<<(unsigned)p.B, 128, bs_smem_bytes(p.N, sizeof(T)), st>>>(p);
     return check_launch("markowitz_bwd_sparse_kernel");

@@ -658,16 +658,7 @@ struct MkPlan {
     size_t smem;
 };
 
-static int smem_limit() {
-    static int lim = -1;
-    if (lim < 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) lim = 48 * 1024;
-        cudaGetLastError();
-    }
-    return lim;
-}
+static int smem_limit() { return device_smem_limit(); }   // of the CURRENT device
 
 static MkPlan plan_fwd(int N, int tsize) {
     MkPlan pl;
@@ -745,13 +736,14 @@ template <typename T, int kThreads, int NREG, bool kGlobal, int MAXT>
 static int launch_fwd_variant(MkFwdParams<T> p, const MkPlan &pl, T *ipm_ws, bool sparse_first, cudaStream_t st) {
     auto kf = markowitz_fwd_kernel<T, kThreads, NREG, kGlobal, MAXT>;
     auto ki = markowitz_ipm_kernel<T, kThreads, NREG, kGlobal>;
-    static bool configured = false;   // per template instance
-    if (!configured) {
-        // opt in to the device maximum once: the same instance serves several n_assets
+    static DeviceOnce configured;     // per template instance and per device
+    const int dev = current_device();
+    if (configured.needs(dev)) {
+        // opt in to the device maximum once per device: the same instance serves several n_assets
         if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess ||
             cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(markowitz_fwd)");
-        configured = true;
+        configured.mark(dev);
     }
     cudaMemsetAsync(p.fail_count, 0, 4 * sizeof(int), st);
     int rc;
@@ -809,11 +801,12 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
 template <typename T, int kThreads, int NREG, bool kGlobal>
 static int launch_bwd_variant(const MkBwdParams<T> &p, const MkPlan &pl, cudaStream_t st) {
     auto kb = markowitz_bwd_kernel<T, kThreads, NREG, kGlobal>;
-    static bool configured = false;   // per template instance; opt in to the device maximum once
-    if (!configured) {
+    static DeviceOnce configured;     // per template instance and per device
+    const int dev = current_device();
+    if (configured.needs(dev)) {
         if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(markowitz_bwd)");
-        configured = true;
+        configured.mark(dev);
     }
     kb<<<(unsigned)p.B, kThreads, pl.smem, st>>>(p);
     return check_launch("markowitz_bwd_kernel");

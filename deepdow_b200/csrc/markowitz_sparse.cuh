@@ -340,14 +340,12 @@ namespace ddw {
 
 template <typename T> int launch_fwd_sparse(const MkFwdParams<T> &p, cudaStream_t st) {
     auto ks = markowitz_fwd_sparse_kernel<T, 128, 4>;
-    static bool configured = false;
-    if (!configured) {
-        int dev = 0, lim = 48 * 1024;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess)
+    static DeviceOnce configured;     // per template instance AND per device (the attribute belongs to the device)
+    const int dev = current_device();
+    if (configured.needs(dev)) {
+        if (cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, device_smem_limit()) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(markowitz_fwd_sparse)");
-        configured = true;
+        configured.mark(dev);
     }
     size_t smem = sp_smem_bytes(p.N, sizeof(T));
 #ifdef DDW_PHASE_TIMING

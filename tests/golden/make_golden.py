@@ -116,6 +116,45 @@ def markowitz():
     print("markowitz cases:", case)
 
 
+def markowitz_large():
+    """Independent third-party fixtures at n_assets = 50 and 100 (SLSQP refined by trust-constr), including the diversified
+    ("dense": most assets free) and the cap-bound regimes of BASELINE configs 2 / 4.  Written to their own file so that
+    markowitz_slsqp.npz keeps its bytes."""
+    rng = np.random.default_rng(4048)
+    out = {}
+    case = 0
+    for (B, N, u, rscale, gam) in [(3, 50, 1.0, 0.5, "rand"), (3, 50, 0.1, 0.02, "ones"), (2, 100, 0.2, 0.5, "ones"),
+                                   (2, 100, 0.2, 0.02, "ones"), (2, 100, 0.05, 3.0, "rand")]:
+        rets = rng.standard_normal((B, N)) * rscale
+        R = rng.standard_normal((B, N, N))
+        C = R @ R.transpose(0, 2, 1) / N + 0.1 * np.eye(N)
+        gamma = rng.uniform(0.5, 2.0, B) if gam == "rand" else np.ones(B)
+        alpha = rng.uniform(0.5, 1.5, B) * rng.choice([-1.0, 1.0], B)
+        gamma_ = torch.from_numpy(gamma).repeat((1, N * N)).view(B, N, N).numpy()     # allocate.py:268-270
+        A = gamma_ * C
+        W = np.empty((B, N))
+        for b in range(B):
+            Ab, rb, ab = A[b], rets[b], abs(alpha[b])
+            H = 2 * (Ab.T @ Ab + ab * np.eye(N))
+            f = lambda w: -(rb @ w) + 0.5 * w @ H @ w
+            df = lambda w: -rb + H @ w
+            x0 = np.clip(np.full(N, 1.0 / N), 0, u); x0 /= x0.sum()
+            res = so.minimize(f, x0, jac=df, method="SLSQP", bounds=[(0, u)] * N,
+                              constraints=[{"type": "eq", "fun": lambda w: w.sum() - 1, "jac": lambda w: np.ones(N)}],
+                              options={"ftol": 1e-16, "maxiter": 2000})
+            res2 = so.minimize(f, res.x, jac=df, hess=lambda w: H, method="trust-constr", bounds=so.Bounds(0, u),
+                               constraints=[so.LinearConstraint(np.ones((1, N)), 1, 1)],
+                               options={"gtol": 1e-13, "xtol": 1e-15, "barrier_tol": 1e-14, "maxiter": 5000})
+            W[b] = res2.x if res2.fun <= res.fun else res.x
+        k = f"m{case}"
+        out[k + "_rets"] = rets; out[k + "_C"] = C; out[k + "_gamma"] = gamma; out[k + "_alpha"] = alpha
+        out[k + "_u"] = np.array(u); out[k + "_w"] = W
+        case += 1
+    out["n_cases"] = np.array(case)
+    np.savez_compressed(os.path.join(HERE, "markowitz_scipy_large.npz"), **out)
+    print("markowitz large cases:", case)
+
+
 def reference_vectors():
     out = dict(
         # tests/test_layers.py:821-838 (atol 1e-3)
@@ -134,6 +173,11 @@ def reference_vectors():
 
 
 if __name__ == "__main__":
-    covariance()
-    markowitz()
-    reference_vectors()
+    import sys
+    if "--large-only" in sys.argv:
+        markowitz_large()
+    else:
+        covariance()
+        markowitz()
+        markowitz_large()
+        reference_vectors()

@@ -410,6 +410,8 @@ def test_covariance_vs_reference_fixtures(dtype, golden_dir):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("B,L,N", [(64, 40, 20), (256, 40, 50), (16, 40, 100), (4, 60, 130), (2, 250, 200),
+                                   # beyond shared memory: tensor-core Gram + blocked Jacobi in float32 (eig_block.cu), padded blocks
+                                   (3, 300, 260), (2, 250, 500), (2, 40, 385),
                                    # odd shapes: no 16-byte alignment for the staged tile / the flat store of the plain kernel
                                    (5, 7, 3), (3, 2, 9), (9, 33, 51), (300, 3, 1)])
 def test_covariance_vs_oracle_sizes(dtype, B, L, N):
@@ -458,7 +460,7 @@ def test_covariance_reference_behaviour(golden_dir):
 def test_compute_sqrt_static(dtype):
     """CovarianceMatrix.compute_sqrt (misc.py:168-201) on a given matrix, forward and gradient."""
     rng = np.random.default_rng(21)
-    for N in (5, 40, 110):
+    for N in (5, 40, 110, 300):
         R = rng.standard_normal((N, N))
         M = R @ R.T / N + 0.05 * np.eye(N)
         G = rng.standard_normal((N, N))

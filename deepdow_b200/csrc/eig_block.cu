@@ -10,8 +10,8 @@
 // that rotate the 32 x 32 cross pairs.  Per round and sample:
 //   bj_local_kernel      one CTA per block pair: the 64 x 64 pivot block in shared memory, 32 (63) parallel steps of 32 disjoint
 //                        Rutishauser rotations, accumulated into U; writes E = U - I
-//   bj_update_kernel<0>  W[IJ, :] = U' S[IJ, :] and VT[IJ, :] = U' VT[IJ, :]   (128 x 64 x 64 tiles on tcgen05)
-//   bj_update_kernel<1>  S[IJ, :] = U' W'[IJ, :]                                (S stays symmetric: rows IJ of S' = columns IJ of S)
+//   bj_update_kernel<0>  Z[:, IJ] = (U' S[IJ, :])' and VT[IJ, :] = U' VT[IJ, :]   (128 x 64 x 64 tiles on tcgen05; Z lives in `W`)
+//   bj_update_kernel<1>  S[IJ, :] = U' Z[IJ, :]                                   (= rows IJ of U' S U, which is symmetric)
 // The updates run in "delta" form X + X E: the tensor core only forms the correction, which vanishes as the sweeps converge,
 // and the base term is added back exactly in FP32 (numerical model: tools/models/block_jacobi_model.py).
 // All samples of the batch advance together (grid = pairs x batch); a sample whose last sweep made no significant rotation is
@@ -23,7 +23,8 @@ namespace ddw {
 
 constexpr int kBjB = 32;              // block width
 constexpr int kBjW = 2 * kBjB;        // width of a block pair = K and N of the update GEMMs
-constexpr int kBjMaxSweeps = 24;
+constexpr int kBjMaxSweeps = 20;
+constexpr float kBjSigRel = 1e-4f;    // a rotation is "significant" (another sweep is needed) above this relative size
 constexpr int kLocalThreads = 128;
 
 struct BjArgs {
@@ -31,7 +32,8 @@ struct BjArgs {
     long long B;
     float *S, *W, *VT, *ET;           // (B, NP, NP) x 3, (B, nb/2, 64, 64)
     float *mean, *rs, *trace;         // (B, NP), (B, NP), (B)
-    int *state;                       // (B, 4): [0] significant rotations of the running sweep, [1] done, [2] sweeps used
+    int *state;                       // (B, 4): [0] significant rotations of the running sweep, [1] done, [2] sweeps used,
+                                      //         [3] max |diag| of the input as float bits
 };
 
 __host__ __device__ inline int bj_padded(int N) { return (N + 127) / 128 * 128; }
@@ -149,10 +151,23 @@ __global__ void __launch_bounds__(256) sym_pad_kernel(const float *m, int N, int
 }
 
 __global__ void __launch_bounds__(256) bj_init_kernel(BjArgs a) {
+    __shared__ float red[8];
     const long long b = blockIdx.x;
     float *VT = a.VT + b * (long long)a.NP * a.NP;
-    for (int i = threadIdx.x; i < a.NP; i += 256) VT[(long long)i * a.NP + i] = 1.f;
-    if (threadIdx.x < 4) a.state[4 * b + threadIdx.x] = 0;
+    const float *S = a.S + b * (long long)a.NP * a.NP;
+    float smax = 0.f;
+    for (int i = threadIdx.x; i < a.NP; i += 256) {
+        VT[(long long)i * a.NP + i] = 1.f;
+        smax = fmaxf(smax, fabsf(S[(long long)i * a.NP + i]));
+    }
+    smax = warp_max(smax);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = smax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) smax = fmaxf(smax, red[i]);
+        a.state[4 * b + 0] = 0; a.state[4 * b + 1] = 0; a.state[4 * b + 2] = 0;
+        a.state[4 * b + 3] = __float_as_int(smax);      // scale of the matrix: |trace| / N <= max |diag| for a PSD matrix
+    }
 }
 
 // start of sweep `sweep` (or, with last != 0, the closing check): a sample whose previous sweep made no significant
@@ -169,13 +184,16 @@ __global__ void __launch_bounds__(256) bj_sweep_begin_kernel(BjArgs a, int sweep
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// local rotations of one block pair: P = S[IJ, IJ] (64 x 64) in shared memory, U accumulated as rows of UT
+// local rotations of one block pair: P = S[IJ, IJ] (64 x 64) in shared memory, U accumulated as rows of UT.
+// A step applies 32 disjoint rotations J_k at once.  Indices split into the 32 pairs, so P splits into 32 x 32 blocks of
+// 2 x 2 and the two-sided update is  P_kl <- J_k' P_kl J_l : one pass over P per step (lane = l, warps walk k), the lane's own
+// (s_l, tau_l) in registers, (s_k, tau_k) broadcast from shared memory -- instead of a column pass and a row pass with a
+// barrier between them.  Rotations use Rutishauser's form a' = a - s (b + tau a), b' = b + s (a - tau b).
 __global__ void __launch_bounds__(kLocalThreads) bj_local_kernel(BjArgs a, int round) {
     __shared__ float P[kBjW][kBjW + 1];
-    __shared__ float UT[kBjW][kBjW + 1];
+    __shared__ __align__(8) float UT[kBjW][kBjW + 2];
     __shared__ float cs[kBjB], sn[kBjB];
     __shared__ int pp[kBjB], pq[kBjB];
-    __shared__ int nsig;
     const long long b = blockIdx.y;
     if (a.state[4 * b + 1]) return;
     int bi, bj;
@@ -191,13 +209,14 @@ __global__ void __launch_bounds__(kLocalThreads) bj_local_kernel(BjArgs a, int r
         P[i][j] = S[(long long)gi * NP + gj];
         UT[i][j] = i == j ? 1.f : 0.f;
     }
-    if (tid == 0) nsig = 0;
     __syncthreads();
     const bool full = round < 0;
     const int nsteps = full ? kBjW - 1 : kBjB;
     const float tol = Num<float>::eps();
+    const float floor_abs = tol * __int_as_float(a.state[4 * b + 3]);   // eps * max |diag|: below it an entry is rounding noise
     int mysig = 0;
     for (int t = 0; t < nsteps; ++t) {
+        int active = 0;
         if (tid < kBjB) {
             const int k = tid;
             int p, q;
@@ -210,97 +229,80 @@ __global__ void __launch_bounds__(kLocalThreads) bj_local_kernel(BjArgs a, int r
             const float spq = P[p][q], spp = P[p][p], sqq = P[q][q];
             const float aq = fabsf(spq), ref = sqrtf(fabsf(spp * sqq));
             float cc = 1.f, ss = 0.f;
-            if (aq > tol * ref && aq > Num<float>::tiny()) {
+            if (aq > tol * ref && aq > floor_abs) {
                 const float tau = (sqq - spp) / (2.f * spq);
                 const float tt = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
                 cc = 1.f / sqrtf(1.f + tt * tt);      // correctly rounded (see covariance.cu: rsqrt's bias would shrink V)
                 ss = tt * cc;
-                if (aq > 8.f * tol * ref) ++mysig;
+                active = 1;
+                // Jacobi converges quadratically: once every rotated entry of a sweep is below kBjSigRel of its diagonal
+                // scale, what is left after the sweep is below rounding and no further sweep is needed
+                if (aq > kBjSigRel * ref) ++mysig;
             }
             pp[k] = p; pq[k] = q; cs[k] = ss / (1.f + cc); sn[k] = ss;
         }
-        __syncthreads();
-        // columns p, q of P and rows p, q of UT: Rutishauser's form a' = a - s (b + tau a), b' = b + s (a - tau b)
-        for (int k = warp; k < kBjB; k += kLocalThreads / 32) {
-            const float ss = sn[k];
-            if (ss == 0.f) continue;
-            const float tt = cs[k];
-            const int p = pp[k], q = pq[k];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = lane + 32 * h;
-                const float x = P[i][p], y = P[i][q];
-                P[i][p] = fmaf(-ss, fmaf(x, tt, y), x);
-                P[i][q] = fmaf(ss, fmaf(-y, tt, x), y);
-                const float ux = UT[p][i], uy = UT[q][i];
-                UT[p][i] = fmaf(-ss, fmaf(ux, tt, uy), ux);
-                UT[q][i] = fmaf(ss, fmaf(-uy, tt, ux), uy);
-            }
-        }
-        __syncthreads();
-        for (int k = warp; k < kBjB; k += kLocalThreads / 32) {
-            const float ss = sn[k];
-            if (ss == 0.f) continue;
-            const float tt = cs[k];
-            const int p = pp[k], q = pq[k];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = lane + 32 * h;
-                const float x = P[p][j], y = P[q][j];
-                P[p][j] = fmaf(-ss, fmaf(x, tt, y), x);
-                P[q][j] = fmaf(ss, fmaf(-y, tt, x), y);
+        if (!__syncthreads_or(active)) continue;       // no rotation in this step (late sweeps): nothing to apply
+        {
+            const int pl = pp[lane], ql = pq[lane];
+            const float sl = sn[lane], tl = cs[lane];
+#pragma unroll 2
+            for (int k = warp; k < kBjB; k += kLocalThreads / 32) {
+                const int pk = pp[k], qk = pq[k];
+                const float sk = sn[k], tk = cs[k];
+                float x00 = P[pk][pl], x01 = P[pk][ql], x10 = P[qk][pl], x11 = P[qk][ql];
+                // columns (J_l)
+                float y00 = fmaf(-sl, fmaf(x00, tl, x01), x00), y01 = fmaf(sl, fmaf(-x01, tl, x00), x01);
+                float y10 = fmaf(-sl, fmaf(x10, tl, x11), x10), y11 = fmaf(sl, fmaf(-x11, tl, x10), x11);
+                // rows (J_k')
+                P[pk][pl] = fmaf(-sk, fmaf(y00, tk, y10), y00); P[qk][pl] = fmaf(sk, fmaf(-y10, tk, y00), y10);
+                P[pk][ql] = fmaf(-sk, fmaf(y01, tk, y11), y01); P[qk][ql] = fmaf(sk, fmaf(-y11, tk, y01), y11);
+                // rows pk, qk of UT: two columns per lane
+                if (sk != 0.f) {
+                    float2 u = *reinterpret_cast<float2 *>(&UT[pk][2 * lane]), v = *reinterpret_cast<float2 *>(&UT[qk][2 * lane]);
+                    float2 un, vn;
+                    un.x = fmaf(-sk, fmaf(u.x, tk, v.x), u.x); vn.x = fmaf(sk, fmaf(-v.x, tk, u.x), v.x);
+                    un.y = fmaf(-sk, fmaf(u.y, tk, v.y), u.y); vn.y = fmaf(sk, fmaf(-v.y, tk, u.y), v.y);
+                    *reinterpret_cast<float2 *>(&UT[pk][2 * lane]) = un;
+                    *reinterpret_cast<float2 *>(&UT[qk][2 * lane]) = vn;
+                }
             }
         }
         __syncthreads();
     }
-    if (mysig) atomicAdd(&nsig, mysig);
     float *ET = a.ET + (b * (a.nb / 2) + blockIdx.x) * (long long)(kBjW * kBjW);
     for (int e = tid; e < kBjW * kBjW; e += kLocalThreads) {
         const int n = e >> 6, k = e & 63;
         ET[e] = UT[n][k] - (n == k ? 1.f : 0.f);      // B operand of the update GEMMs: (n, k) = U[k][n] - delta
     }
-    __syncthreads();
-    if (tid == 0 && nsig) atomicAdd(&a.state[4 * b], nsig);
+    if (tid < kBjB) {
+        mysig = warp_sum(mysig);
+        if (tid == 0 && mysig) atomicAdd(&a.state[4 * b], mysig);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// rotation updates on tcgen05: one CTA = 128 columns (m) of the 64 rows IJ; out[IJ_n][m] = X(m, n) + sum_k X(m, k) E[k][n]
-//   PHASE 0: X(m, k) = S[IJ_k][m] -> W  (blockIdx.z even)   and   X(m, k) = VT[IJ_k][m] -> VT in place  (blockIdx.z odd)
-//   PHASE 1: X(m, k) = W[m][IJ_k] -> S
-constexpr int kUpdSbo = (kBjW / 4) * tc::kLbo;                       // 2304
-constexpr int kUpdABytes = (tc::kTileM / 8) * kUpdSbo;               // 36864 per hi / lo tile
-constexpr int kUpdBBytes = (kBjW / 8) * kUpdSbo;                     // 18432
-constexpr size_t kUpdSmem = 2 * kUpdABytes + 2 * kUpdBBytes + 1024;   // ~109 KB: two CTAs per SM
+// rotation updates on tcgen05: one CTA = 128 columns (m) of the 64 rows IJ:  Y(m, n) = X(m, n) + sum_k X(m, k) E[k][n],
+// X(m, k) = Xmat[IJ_k][m] (rows of a row-major matrix: lanes walk m, every load is coalesced).
+//   PHASE 0, blockIdx.z even: Xmat = S,  Y -> Z[m][IJ_n]   (Z = (U' S)' : the TRANSPOSE of the row-rotated matrix, 128-byte
+//                                                            row pieces per thread)
+//   PHASE 0, blockIdx.z odd : Xmat = VT, Y -> VT[IJ_n][m]  in place
+//   PHASE 1                 : Xmat = Z,  Y -> S[IJ_n][m]   (S_new = U' S U is symmetric: its rows IJ are U' times the rows IJ
+//                                                            of (S U)' ... = U' Z[IJ, :])
+// Storing Z transposed makes both phases the same rows-of-a-matrix GEMM.  The CTA is latency bound, so it is kept small
+// (55 KB of shared memory, 128 TMEM columns: four CTAs per SM): K = 64 is staged as two chunks of 32 through ONE buffer, the
+// loads of the second chunk are in flight while the tensor core works on the first, and the base term X(m, n) is re-read
+// (coalesced, from L2) in the epilogue instead of being kept on chip.  Two accumulators (hi*hi and the cross terms): in delta
+// form the truncating accumulation acts on the correction only (model: |V'V - I| 4.5e-6 against 3.7e-6 with four).
+constexpr int kUpdKC = 32;                                            // k values per staged chunk
+constexpr int kUpdSbo = (kUpdKC / 4) * tc::kLbo;                      // 1152
+constexpr int kUpdABytes = (tc::kTileM / 8) * kUpdSbo;                // 18432 per hi / lo tile
+constexpr int kUpdBBytes = (kBjW / 8) * kUpdSbo;                      // 9216
+constexpr size_t kUpdSmem = 2 * kUpdABytes + 2 * kUpdBBytes + 1024;    // 56320: four CTAs per SM
 
-struct LoadPairRows {        // element (m, k) = X[row(k)][m]; lanes walk m
-    static constexpr bool kRowsFast = true;
-    const float *X; int NP, I0, J0;
-    __device__ __forceinline__ void ld4(int m, int k, float (&v)[4]) const {
-        const int r0 = k < kBjB ? I0 + k : J0 + k - kBjB;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = X[(long long)(r0 + q) * NP + m];
-    }
-};
-struct LoadPairCols {        // element (m, k) = X[m][col(k)]; lanes walk k
-    static constexpr bool kRowsFast = false;
-    const float *X; int NP, I0, J0;
-    __device__ __forceinline__ void ld4(int m, int k, float (&v)[4]) const {
-        const int c0 = k < kBjB ? I0 + k : J0 + k - kBjB;
-        const float4 t = *reinterpret_cast<const float4 *>(X + (long long)m * NP + c0);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-};
-struct LoadE {               // element (n, k) = ET[n][k]
-    static constexpr bool kRowsFast = false;
-    const float *ET;
-    __device__ __forceinline__ void ld4(int n, int k, float (&v)[4]) const {
-        const float4 t = *reinterpret_cast<const float4 *>(ET + n * kBjW + k);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-};
+constexpr int kUpdThreads = 128;                                      // one warp per 32 TMEM lanes
 
 template <int PHASE>
-__global__ void __launch_bounds__(tc::kThreads) bj_update_kernel(BjArgs a, int round) {
+__global__ void __launch_bounds__(kUpdThreads, 4) bj_update_kernel(BjArgs a, int round) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ tc::TileShared sh;
     const int which = PHASE == 0 ? (blockIdx.z & 1) : 0;
@@ -311,42 +313,106 @@ __global__ void __launch_bounds__(tc::kThreads) bj_update_kernel(BjArgs a, int r
     const int I0 = bi * kBjB, J0 = bj * kBjB;
     if (I0 >= a.N) return;
     const int NP = a.NP, m0 = blockIdx.x * tc::kTileM;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const long long mat = (long long)NP * NP;
-    const float *X = PHASE == 0 ? (which ? a.VT : a.S) + b * mat : a.W + b * mat;
-    float *Y = PHASE == 0 ? (which ? a.VT : a.W) + b * mat : a.S + b * mat;
+    const float *X = (PHASE == 0 ? (which ? a.VT : a.S) : a.W) + b * mat;
+    float *Y = (PHASE == 0 ? (which ? a.VT : a.W) : a.S) + b * mat;
     const float *ET = a.ET + (b * (a.nb / 2) + blockIdx.y) * (long long)(kBjW * kBjW);
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char *a_hi = base, *a_lo = base + kUpdABytes, *b_hi = base + 2 * kUpdABytes, *b_lo = b_hi + kUpdBBytes;
-    constexpr uint32_t kCols = tc::kAccs * kBjW;      // 256
-    if (tid == 0) { mbar_init(&sh.fin, 1); fence_mbar_init(); }
+    constexpr uint32_t kCols = 2 * kBjW;      // 128: accumulator 0 = hi*hi, accumulator 1 = cross terms
+    constexpr uint32_t idesc = tc::idesc_tf32(tc::kTileM, kBjW);
+
+    // element (m, k): row IJ_k of X, column m0 + m.  Thread -> m = tid (its TMEM lane as well), all 8 groups of four k.
+    float va[8][4], vb[4][4];
+    auto load_chunk = [&](int c) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int k = c * kUpdKC + 4 * it;
+            const int r0 = k < kBjB ? I0 + k : J0 + k - kBjB;
+            const float *src = X + (long long)r0 * NP + m0 + tid;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) va[it][q] = __ldg(src + (long long)q * NP);
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {     // E^T: (n, k) = ET[n][k]; thread -> (k4 = id % 8, n = id / 8)
+            const int id = it * kUpdThreads + tid;
+            const float4 t4 = __ldg(reinterpret_cast<const float4 *>(ET + (id >> 3) * kBjW + c * kUpdKC + 4 * (id & 7)));
+            vb[it][0] = t4.x; vb[it][1] = t4.y; vb[it][2] = t4.z; vb[it][3] = t4.w;
+        }
+    };
+    auto store_chunk = [&]() {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            float4 h, l;
+            tc::split_tf32(va[it][0], h.x, l.x); tc::split_tf32(va[it][1], h.y, l.y);
+            tc::split_tf32(va[it][2], h.z, l.z); tc::split_tf32(va[it][3], h.w, l.w);
+            const int off = (tid >> 3) * kUpdSbo + it * tc::kLbo + (tid & 7) * 16;
+            *reinterpret_cast<float4 *>(a_hi + off) = h;
+            *reinterpret_cast<float4 *>(a_lo + off) = l;
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int id = it * kUpdThreads + tid, n = id >> 3, k4 = id & 7;
+            float4 h, l;
+            tc::split_tf32(vb[it][0], h.x, l.x); tc::split_tf32(vb[it][1], h.y, l.y);
+            tc::split_tf32(vb[it][2], h.z, l.z); tc::split_tf32(vb[it][3], h.w, l.w);
+            const int off = (n >> 3) * kUpdSbo + k4 * tc::kLbo + (n & 7) * 16;
+            *reinterpret_cast<float4 *>(b_hi + off) = h;
+            *reinterpret_cast<float4 *>(b_lo + off) = l;
+        }
+    };
+    auto issue_chunk = [&](int c, uint32_t tmem) {
+        const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+        for (int kk = 0; kk < kUpdKC / 8; ++kk) {
+            const uint32_t o = kk * 2 * tc::kLbo;
+            const uint64_t dah = tc::smem_desc(ah + o, tc::kLbo, kUpdSbo), dal = tc::smem_desc(al + o, tc::kLbo, kUpdSbo);
+            const uint64_t dbh = tc::smem_desc(bh + o, tc::kLbo, kUpdSbo), dbl = tc::smem_desc(bl + o, tc::kLbo, kUpdSbo);
+            tc::mma_tf32(tmem + kBjW, dal, dbh, idesc, (c | kk) != 0);
+            tc::mma_tf32(tmem + kBjW, dah, dbl, idesc, 1u);
+            tc::mma_tf32(tmem, dah, dbh, idesc, (c | kk) != 0);
+        }
+    };
+
+    load_chunk(0);
+    if (tid == 0) { mbar_init(&sh.done[0], 1); mbar_init(&sh.done[1], 1); fence_mbar_init(); }
     if (warp == 0) tc::tmem_alloc(&sh.tmem_base, kCols);
-    if (PHASE == 0) tc::stage_operand<tc::kTileM, kBjW>(LoadPairRows{X, NP, I0, J0}, m0, 0, a_hi, a_lo);
-    else tc::stage_operand<tc::kTileM, kBjW>(LoadPairCols{X, NP, I0, J0}, m0, 0, a_hi, a_lo);
-    tc::stage_operand<kBjW, kBjW>(LoadE{ET}, 0, 0, b_hi, b_lo);
+    store_chunk();
+    load_chunk(1);                            // in flight while the tensor core works on chunk 0
     fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = sh.tmem_base;
-    if (tid == 0) {
-        tc::issue_mma3<kBjW>(tmem, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_hi), smem_u32(b_lo), kBjW / 8, 0, tc::kLbo, kUpdSbo);
-        tc::mma_commit(&sh.fin);
-    }
-    mbar_wait(&sh.fin, 0);
-    tc::fence_after_sync();
-    {
-        const int ml = 32 * (warp & 3) + lane, c0 = 32 * (warp >> 2);
-        float v[32];
-        tc::load_acc32<kBjW>(tmem, warp, c0, v);
-        const int aoff = (ml >> 3) * kUpdSbo + (ml & 7) * 16;
+    if (tid == 0) { issue_chunk(0, tmem); tc::mma_commit(&sh.done[0]); }
+    mbar_wait(&sh.done[0], 0);                // chunk 0 consumed: the buffer is free again
+    store_chunk();
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) { tc::fence_after_sync(); issue_chunk(1, tmem); tc::mma_commit(&sh.done[1]); }
+    // epilogue: this thread owns row m = tid; the base term X(m, n) is re-read (coalesced over the warp, L2 hits)
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const int r0 = half ? J0 : I0;
+        float basev[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int n = c0 + j;
-            const int off = aoff + (n >> 2) * tc::kLbo + (n & 3) * 4;
-            const float basev = *reinterpret_cast<const float *>(a_hi + off) + *reinterpret_cast<const float *>(a_lo + off);
-            const int row = n < kBjB ? I0 + n : J0 + n - kBjB;
-            Y[(long long)row * NP + m0 + ml] = basev + v[j];
+        for (int j = 0; j < 32; ++j) basev[j] = __ldg(X + (long long)(r0 + j) * NP + m0 + tid);
+        if (half == 0) { mbar_wait(&sh.done[1], 0); tc::fence_after_sync(); }
+        const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * half);
+        float v[32], x[32];
+        tc::tmem_ld32(lane_addr, v);
+        tc::tmem_ld32(lane_addr + kBjW, x);
+        if (PHASE == 0 && which == 0) {
+            // Z[m][IJ_n]: 32 consecutive floats of row m
+            float4 *dst = reinterpret_cast<float4 *>(Y + (long long)(m0 + tid) * NP + r0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                dst[j] = make_float4(basev[4 * j] + (v[4 * j] + x[4 * j]), basev[4 * j + 1] + (v[4 * j + 1] + x[4 * j + 1]),
+                                     basev[4 * j + 2] + (v[4 * j + 2] + x[4 * j + 2]), basev[4 * j + 3] + (v[4 * j + 3] + x[4 * j + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) Y[(long long)(r0 + j) * NP + m0 + tid] = basev[j] + (v[j] + x[j]);
         }
     }
     tc::fence_before_sync();
@@ -464,8 +530,8 @@ static int covariance_fwd_large_slice(const float *x, const float *coef, int str
         bj_sweep_begin_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(a, sweep, 0);
         for (int round = -1; round < a.nb - 1; ++round) {
             bj_local_kernel<<<dim3(pairs, (unsigned)B), kLocalThreads, 0, st>>>(a, round);
-            bj_update_kernel<0><<<dim3(chunks, pairs, (unsigned)(2 * B)), tc::kThreads, kUpdSmem, st>>>(a, round);
-            bj_update_kernel<1><<<dim3(chunks, pairs, (unsigned)B), tc::kThreads, kUpdSmem, st>>>(a, round);
+            bj_update_kernel<0><<<dim3(chunks, pairs, (unsigned)(2 * B)), kUpdThreads, kUpdSmem, st>>>(a, round);
+            bj_update_kernel<1><<<dim3(chunks, pairs, (unsigned)B), kUpdThreads, kUpdSmem, st>>>(a, round);
         }
         if ((rc = check_launch("blocked Jacobi sweep"))) return rc;
     }

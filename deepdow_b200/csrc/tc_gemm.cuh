@@ -105,9 +105,9 @@ struct TileShared {            // static shared state of one tile GEMM
 // Loader: void ld4(int r, int k, float (&v)[4]) returns elements (r, k .. k+3), zero outside the operand, and
 // static constexpr bool kRowsFast: true when consecutive r are adjacent in memory (lanes then walk r), false when
 // consecutive k are (lanes walk k in groups of four).
-template <int ROWS, int KT, typename Loader>
+template <int ROWS, int KT, typename Loader, int kPer = 4>
 __device__ __forceinline__ void stage_operand(const Loader &ldr, int r0, int k0, unsigned char *hi, unsigned char *lo) {
-    constexpr int kItems = ROWS * (KT / 4), kPer = 4;     // items in flight per thread and pass
+    constexpr int kItems = ROWS * (KT / 4);               // kPer = items (4 elements each) in flight per thread and pass
     constexpr int kSboT = (KT / 4) * kLbo;
     static_assert(kItems % (kThreads * kPer) == 0 || kItems % kThreads == 0, "tile does not divide over the CTA");
     constexpr int kPasses = kItems / kThreads;

@@ -5,6 +5,8 @@ Argument meaning, error behaviour and output dtype/device follow the reference:
   SoftmaxAllocator     deepdow/layers/allocate.py:414-514
   SparsemaxAllocator   deepdow/layers/allocate.py:517-595
   CovarianceMatrix     deepdow/layers/misc.py:33-201
+  Resample             deepdow/layers/allocate.py:276-411 (the caller that chains CovarianceMatrix(sqrt=True) into
+                       NumericalMarkowitz; only its NumericalMarkowitz arm, the other allocators are out of scope)
 """
 import torch
 import torch.nn as nn
@@ -495,3 +497,50 @@ class CovarianceMatrix(nn.Module):
     def compute_sqrt(m):
         """Square root of a single positive semi-definite matrix (n_assets, n_assets), misc.py:168-201."""
         return _PsdSqrtFn.apply(m.unsqueeze(0))[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# Resample: the bootstrap meta-allocator on top of the two layers above
+# ------------------------------------------------------------------------------------------------
+class Resample(nn.Module):
+    """Meta allocator that bootstraps the input expected returns and covariance matrix.
+
+    The ``NumericalMarkowitz`` arm of ``deepdow.layers.Resample`` (allocate.py:276-411): view ``(rets, matrix)`` as the
+    parameters of a multivariate normal, then ``n_portfolios`` times draw ``n_draws`` samples (reparameterised, so gradients
+    reach ``rets`` and ``matrix``), re-estimate the expected returns (mean of the draws) and the square root of the covariance
+    (``CovarianceMatrix(sqrt=True)`` of the draws) and allocate; the portfolios are averaged.  Same constructor, same
+    keyword-only ``forward(matrix, rets, gamma=..., alpha=...)``, same seeding (``torch.manual_seed(random_state)``).
+    The reference's other arms (``AnalyticalMarkowitz``, ``NCO``) are not part of this package: they raise ``TypeError``
+    here exactly like any other unsupported allocator does there (allocate.py:323-328).
+    """
+
+    def __init__(self, allocator, n_draws=None, n_portfolios=5, sqrt=False, random_state=None):
+        super().__init__()
+        if not isinstance(allocator, NumericalMarkowitz):
+            raise TypeError("Unsupported type of allocator: {}".format(type(allocator)))
+        self.allocator = allocator
+        self.sqrt = sqrt
+        self.n_draws = n_draws
+        self.n_portfolios = n_portfolios
+        self.random_state = random_state
+        self.uses_sqrt = True          # NumericalMarkowitz consumes the square root (allocate.py:336-342)
+        self.covariance_layer = CovarianceMatrix(sqrt=self.uses_sqrt)
+
+    def forward(self, matrix, rets=None, **kwargs):
+        """matrix (n_samples, n_assets, n_assets): the covariance, or its square root when ``sqrt=True``; rets
+        (n_samples, n_assets); ``gamma`` and ``alpha`` (n_samples,) as keyword arguments.  Returns (n_samples, n_assets)."""
+        if rets is None:
+            raise ValueError("NumericalMarkowitz needs expected returns: pass rets")   # the reference fails inside cvxpylayers
+        if self.random_state is not None:
+            torch.manual_seed(self.random_state)
+        n_assets = matrix.shape[1]
+        n_draws = self.n_draws or n_assets
+        covmat = matrix @ matrix if self.sqrt else matrix
+        dist = torch.distributions.MultivariateNormal(loc=rets, covariance_matrix=covmat)
+        total = None
+        for _ in range(self.n_portfolios):
+            draws = dist.rsample((n_draws,))                                   # (n_draws, n_samples, n_assets)
+            covmat_ = self.covariance_layer(draws.permute(1, 0, 2))            # the layer takes (n_samples, n_draws, n_assets)
+            portfolio = self.allocator(draws.mean(dim=0), covmat_, kwargs["gamma"], kwargs["alpha"])
+            total = portfolio if total is None else total + portfolio
+        return total / self.n_portfolios

@@ -1,4 +1,5 @@
-"""Callers of the allocation hot path: BachelierNet and ThorpNet on the CUDA layers.
+"""Callers of the allocation hot path: BachelierNet, ThorpNet and KeynesNet on the
+CUDA layers.
 
 Only what sits between the data tensor and the allocator is here, and only because the reference's versions serialise the
 batch: ``RNN.forward`` (deepdow/layers/transform.py:151-159) and ``AttentionCollapse.forward`` (deepdow/layers/collapse.py:46-61)
@@ -11,7 +12,7 @@ moves between the two implementations unchanged (nn.py:129-150 for BachelierNet,
 import torch
 from torch import nn
 
-from .layers import CovarianceMatrix, NumericalMarkowitz
+from .layers import CovarianceMatrix, NumericalMarkowitz, SoftmaxAllocator
 
 
 class RNN(nn.Module):
@@ -115,6 +116,10 @@ class ThorpNet(nn.Module):
         super().__init__()
         self._hp = _hparams(dict(n_assets=n_assets, max_weight=max_weight, force_symmetric=force_symmetric))
         self.force_symmetric = force_symmetric
+        # Opt-in: every sample of a ThorpNet batch is the SAME problem (nn.py:563-575), so it can be
+        # solved once and broadcast; autograd of the broadcast sums the n identical upstream gradients, which is exactly what
+        # the reference's repeat_interleave backward does.  Off by default: the layer then sees the (n, N, N) copies, as there.
+        self.shared_problem = False
         self.matrix = nn.Parameter(torch.eye(n_assets), requires_grad=True)
         self.exp_returns = nn.Parameter(torch.zeros(n_assets), requires_grad=True)
         self.gamma_sqrt = nn.Parameter(torch.ones(1), requires_grad=True)
@@ -125,10 +130,57 @@ class ThorpNet(nn.Module):
         """x (n_samples, n_channels, lookback, n_assets) -> weights (n_samples, n_assets); only len(x) is used."""
         n = len(x)
         covariance = self.matrix @ self.matrix.t() if self.force_symmetric else self.matrix
+        if self.shared_problem:
+            one = torch.ones(1, device=x.device, dtype=x.dtype)
+            w = self.portfolio_opt_layer(self.exp_returns.unsqueeze(0), covariance.unsqueeze(0), one * self.gamma_sqrt,
+                                         one * self.alpha)
+            return w.expand(n, -1)
         rets_all = self.exp_returns.unsqueeze(0).expand(n, -1).contiguous()
         cov_all = covariance.unsqueeze(0).expand(n, -1, -1).contiguous()
         ones = torch.ones(n, device=x.device, dtype=x.dtype)
         return self.portfolio_opt_layer(rets_all, cov_all, ones * self.gamma_sqrt, ones * self.alpha)
+
+    @property
+    def hparams(self):
+        return dict(self._hp)
+
+
+class KeynesNet(nn.Module):
+    """``deepdow.nn.KeynesNet`` (nn.py:205-344): instance norm -> shared LSTM (or 1-D convolution) over time -> group norm ->
+    ReLU -> mean over time and channels -> allocator with one learnt temperature.  The reference hard-wires the analytical
+    ``SoftmaxAllocator(temperature=None)`` (nn.py:296) and a user swaps ``portfolio_opt_layer`` for the variational softmax or
+    the sparsemax (BASELINE config 3); here the layer can be passed to the constructor as well.  Any module with the
+    ``forward(x, temperature)`` signature works."""
+
+    def __init__(self, n_input_channels, hidden_size=32, transform_type="RNN", n_groups=4, portfolio_opt_layer=None):
+        super().__init__()
+        self._hp = _hparams(dict(n_input_channels=n_input_channels, hidden_size=hidden_size, transform_type=transform_type,
+                                 n_groups=n_groups))
+        self.transform_type = transform_type
+        if transform_type == "RNN":
+            self.transform_layer = RNN(n_input_channels, hidden_size=hidden_size, bidirectional=False, cell_type="LSTM")
+        elif transform_type == "Conv":
+            # the reference convolves every asset's (channels, lookback) series with the same 1-D kernel in a Python loop over
+            # the assets (nn.py:318-322); a (3, 1) 2-D kernel over (lookback, n_assets) is the same map in one call
+            self.transform_layer = nn.Conv2d(n_input_channels, hidden_size, kernel_size=(3, 1), padding=(1, 0))
+        else:
+            raise ValueError("Unsupported transform_type: {}".format(transform_type))
+        if hidden_size % n_groups != 0:
+            raise ValueError("The hidden_size needs to be divisible by the n_groups.")
+        self.norm_layer_1 = nn.InstanceNorm2d(n_input_channels, affine=True)
+        self.temperature = nn.Parameter(torch.ones(1), requires_grad=True)
+        self.norm_layer_2 = nn.GroupNorm(n_groups, hidden_size, affine=True)
+        self.time_collapse_layer = AverageCollapse(collapse_dim=2)
+        self.channel_collapse_layer = AverageCollapse(collapse_dim=1)
+        self.portfolio_opt_layer = SoftmaxAllocator(temperature=None) if portfolio_opt_layer is None else portfolio_opt_layer
+
+    def forward(self, x):
+        """x (n_samples, n_channels, lookback, n_assets) -> weights (n_samples, n_assets)."""
+        x = self.transform_layer(self.norm_layer_1(x))
+        x = torch.relu(self.norm_layer_2(x))
+        x = self.channel_collapse_layer(self.time_collapse_layer(x))
+        temperatures = torch.ones(len(x), device=x.device, dtype=x.dtype) * self.temperature
+        return self.portfolio_opt_layer(x, temperatures)
 
     @property
     def hparams(self):

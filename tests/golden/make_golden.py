@@ -117,7 +117,7 @@ def markowitz():
 
 
 def markowitz_large():
-    """Independent third-party fixtures at n_assets = 50 and 100 (SLSQP refined by trust-constr), including the diversified
+    """Independent third-party fixtures at n_assets = 50 and 100 (scipy SLSQP, restarted once), including the diversified
     ("dense": most assets free) and the cap-bound regimes of BASELINE configs 2 / 4.  Written to their own file so that
     markowitz_slsqp.npz keeps its bytes."""
     rng = np.random.default_rng(4048)
@@ -142,9 +142,10 @@ def markowitz_large():
             res = so.minimize(f, x0, jac=df, method="SLSQP", bounds=[(0, u)] * N,
                               constraints=[{"type": "eq", "fun": lambda w: w.sum() - 1, "jac": lambda w: np.ones(N)}],
                               options={"ftol": 1e-16, "maxiter": 2000})
-            res2 = so.minimize(f, res.x, jac=df, hess=lambda w: H, method="trust-constr", bounds=so.Bounds(0, u),
-                               constraints=[so.LinearConstraint(np.ones((1, N)), 1, 1)],
-                               options={"gtol": 1e-13, "xtol": 1e-15, "barrier_tol": 1e-14, "maxiter": 5000})
+            # restart from the first answer: SLSQP's active-set guess is then right and the final QP step is exact to rounding
+            res2 = so.minimize(f, res.x, jac=df, method="SLSQP", bounds=[(0, u)] * N,
+                               constraints=[{"type": "eq", "fun": lambda w: w.sum() - 1, "jac": lambda w: np.ones(N)}],
+                               options={"ftol": 1e-18, "maxiter": 2000})
             W[b] = res2.x if res2.fun <= res.fun else res.x
         k = f"m{case}"
         out[k + "_rets"] = rets; out[k + "_C"] = C; out[k + "_gamma"] = gamma; out[k + "_alpha"] = alpha

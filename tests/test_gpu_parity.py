@@ -46,6 +46,12 @@ def make_problems(rng, B, N, kind="sym", alpha=1.0, rscale=0.5, gamma="ones"):
         X = rng.standard_normal((B, 40, N)) * 0.01
         C = oracle.covariance_fwd(X, 0.5, "diagonal", True)
         rets = rng.standard_normal((B, N)) * 0.01
+    elif kind == "covsq":
+        # BachelierNet's quirk (nn.py:142-144,171): the covariance ITSELF (sqrt=False) sits in the covmat_sqrt slot, so the
+        # risk term is w' Sigma^2 w; with returns of the data's scale nearly every asset ends up free
+        X = rng.standard_normal((B, 40, N)) * 0.01
+        C = oracle.covariance_fwd(X, 0.5, "diagonal", False)
+        rets = rng.standard_normal((B, N)) * 0.01
     g = np.ones(B) if gamma == "ones" else rng.uniform(0.5, 2.0, B)
     a = np.full(B, float(alpha)) * (rng.choice([-1.0, 1.0], B) if gamma != "ones" else 1.0)
     return rets, C, g, a
@@ -64,6 +70,11 @@ def make_problems(rng, B, N, kind="sym", alpha=1.0, rscale=0.5, gamma="ones"):
     (4, 200, 0.1, "sym", "rand"),
     (4, 240, 1.0, "sqrtcov", "ones"),      # Q in global workspace, dense free set
     (3, 500, 0.01, "sym", "ones"),         # config 5 shape (reduced batch)
+    # the diversified ("dense") regime the networks train in: most assets free, handled by the dense kernels
+    (256, 100, 0.2, "dense", "ones"),      # config 4 shape, ~86 free (ThorpNet)
+    (256, 50, 1.0, "covsq", "ones"),       # config 2: BachelierNet's Sigma^2 quirk
+    (8, 129, 0.05, "dense", "ones"),       # 256-thread variant, dense free set
+    (64, 100, 0.2, "dense", "rand"),       # dense + gamma tiling + signed alpha
 ])
 def test_markowitz_forward_vs_oracle(dtype, B, N, u, kind, gamma):
     rng = np.random.default_rng(B * 1000 + N)
@@ -78,11 +89,24 @@ def test_markowitz_forward_vs_oracle(dtype, B, N, u, kind, gamma):
     assert torch.allclose(w.sum(1), torch.ones(B, dtype=dtype, device=DEV), atol=10 * W_ATOL[dtype])
     assert w.min() >= 0 and w.max() <= u + 1e-7
     assert int((layer.last_status & 12).ne(0).sum()) == 0
+    assert_state_matches(w, w_ref, st_ref, u)
+    if kind in ("dense", "covsq"):
+        assert (st_ref == 0).sum(1).mean() > 0.5 * N      # the case is what it claims to be: most assets free
+
+
+def assert_state_matches(w, w_ref, st_ref, u, tol=1e-6):
+    """The active set the kernel reports (a function of the returned weights: 0 -> lower, u -> upper) equals the oracle's,
+    except where the oracle's weight sits within `tol` of a bound (a degenerate asset)."""
+    wn = w.detach().double().cpu().numpy()
+    st = np.where(wn <= 0, -1, np.where(wn >= np.float64(w.new_tensor(u).item()), 1, 0))
+    near = (np.abs(w_ref) < tol) | (np.abs(w_ref - u) < tol)
+    assert ((st == st_ref) | near).all(), int(((st != st_ref) & ~near).sum())
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-def test_markowitz_golden_slsqp(dtype, golden_dir):
-    z = np.load(os.path.join(golden_dir, "markowitz_slsqp.npz"))
+@pytest.mark.parametrize("fixture", ["markowitz_slsqp.npz", "markowitz_scipy_large.npz"])
+def test_markowitz_golden_slsqp(dtype, fixture, golden_dir):
+    z = np.load(os.path.join(golden_dir, fixture))
     for c in range(int(z["n_cases"])):
         k = f"m{c}"
         N = z[k + "_rets"].shape[1]
@@ -183,6 +207,8 @@ def test_markowitz_hard_problems_use_fallback_and_stay_exact(dtype):
     (96, 100, 0.2, "sym", "ones"),
     (8, 150, 0.05, "sym", "ones"),
     (32, 100, 1.0, "dense", "ones"),       # nearly all assets free: generic factorisation + streaming path
+    (64, 100, 0.2, "dense", "rand"),       # config 4's regime with the gamma tiling
+    (64, 50, 1.0, "covsq", "ones"),        # config 2's regime (BachelierNet)
     (4, 240, 0.05, "dense", "ones"),       # factor in global workspace
     (3, 500, 0.01, "sym", "rand"),         # config 5 shape (reduced batch)
 ])
@@ -194,6 +220,8 @@ def test_markowitz_backward_vs_oracle(dtype, B, N, u, kind, gamma):
     ref = oracle.markowitz_bwd(G, w_ref, st_ref, C, g, a, u)
     tr, tC, tg, ta = t(rets, dtype, True), t(C, dtype, True), t(g, dtype, True), t(a, dtype, True)
     w = NumericalMarkowitz(N, u)(tr, tC, tg, ta)
+    assert np.abs(w.detach().double().cpu().numpy() - w_ref).max() < W_ATOL[dtype]
+    assert_state_matches(w, w_ref, st_ref, u)
     (w * t(G, dtype)).sum().backward()
     for name, got, want in zip(["rets", "covmat_sqrt", "gamma", "alpha"], [tr.grad, tC.grad, tg.grad, ta.grad], ref):
         assert got is not None and got.shape == want.shape, name
@@ -625,3 +653,49 @@ def test_kernels_are_bitwise_repeatable():
             outs = cur
         else:
             assert all(torch.equal(a, b) for a, b in zip(outs, cur))
+
+
+# ------------------------------------------------------------------ Resample over the CUDA layers (allocate.py:276-411)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("sqrt", [False, True])
+def test_resample_over_numerical_markowitz(dtype, sqrt):
+    """tests/test_layers.py:532-594 (NumericalMarkowitz arm): shape / dtype / device, the same seed gives the same weights,
+    gradients reach ``rets`` -- and here also: the weights and ``rets.grad`` equal the oracle's on the very draws the layer used
+    (the chain rsample -> CovarianceMatrix(sqrt=True) -> NumericalMarkowitz; the centred covariance does not depend on the
+    location, so d w / d rets goes through the mean of the draws only)."""
+    from deepdow_b200 import Resample
+    n_samples, n_assets, n_draws, n_portfolios, u, seed = 3, 6, 12, 4, 0.6, 7
+    rng = np.random.default_rng(31)
+    R = rng.standard_normal((n_samples, n_assets, n_assets)) * 0.05
+    cov = R @ R.transpose(0, 2, 1) + 0.01 * np.eye(n_assets)
+    matrix = oracle.psd_sqrt_fwd(cov) if sqrt else cov
+    rets = t(rng.standard_normal((n_samples, n_assets)) * 0.05, dtype, True)
+    mat = t(matrix, dtype, True)
+    gamma, alpha = t(np.ones(n_samples), dtype), t(np.ones(n_samples), dtype)
+    with pytest.raises(TypeError):
+        Resample(SparsemaxAllocator(n_assets))
+    layer = Resample(NumericalMarkowitz(n_assets, max_weight=u), n_draws=n_draws, n_portfolios=n_portfolios, sqrt=sqrt, random_state=seed)
+    w = layer(mat, rets, gamma=gamma, alpha=alpha)
+    assert w.shape == (n_samples, n_assets) and w.dtype == dtype and w.device == torch.device(DEV)
+    assert torch.allclose(w.sum(1), torch.ones(n_samples, dtype=dtype, device=DEV), atol=1e-5)
+    w2 = layer(mat, rets, gamma=gamma, alpha=alpha)
+    assert torch.equal(w, w2)                                  # random_state: same draws, same weights
+    G = rng.standard_normal((n_samples, n_assets))
+    (w * t(G, dtype)).sum().backward()
+    assert rets.grad is not None and torch.isfinite(rets.grad).all()
+    assert mat.grad is not None and torch.isfinite(mat.grad).all() and float(mat.grad.abs().max()) > 0
+    # replay the draws (same seed, same device, same call order) and push them through the oracle
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        covmat = mat @ mat if sqrt else mat
+        dist = torch.distributions.MultivariateNormal(loc=rets.detach(), covariance_matrix=covmat)
+        w_ref = np.zeros((n_samples, n_assets)); d_ref = np.zeros((n_samples, n_assets))
+        for _ in range(n_portfolios):
+            draws = dist.rsample((n_draws,)).permute(1, 0, 2).double().cpu().numpy()       # (n_samples, n_draws, n_assets)
+            C = oracle.covariance_fwd(draws, 0.5, "diagonal", True)
+            wp, stp, kkt, _ = oracle.markowitz_fwd(draws.mean(1), C, np.ones(n_samples), np.ones(n_samples), u)
+            w_ref += wp / n_portfolios
+            d_ref += oracle.markowitz_bwd(G / n_portfolios, wp, stp, C, np.ones(n_samples), np.ones(n_samples), u)[0]
+    tolw = 2e-5 if dtype == torch.float32 else 1e-9
+    assert np.abs(w.detach().double().cpu().numpy() - w_ref).max() < tolw
+    assert rel_err(rets.grad, d_ref) < (2e-3 if dtype == torch.float32 else 1e-7)

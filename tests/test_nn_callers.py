@@ -154,3 +154,97 @@ def test_thorpnet_training_steps(force_symmetric):
         loss.backward()
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
         opt.step()
+
+
+def test_keynesnet_constructor_follows_the_reference():
+    # nn.py:246-296: errors, parameter names, the analytical softmax as the default allocator
+    with pytest.raises(ValueError):
+        dnn.KeynesNet(2, transform_type="GRU")
+    with pytest.raises(ValueError):
+        dnn.KeynesNet(2, hidden_size=10, n_groups=4)
+    net = dnn.KeynesNet(2, hidden_size=8, n_groups=4)
+    assert {"temperature", "norm_layer_1.weight", "norm_layer_2.weight", "transform_layer.cell.weight_ih_l0"} <= set(net.state_dict())
+    assert net.portfolio_opt_layer.formulation == "analytical" and net.portfolio_opt_layer.temperature is None
+    w = net(torch.randn(3, 2, 7, 5))                         # the default allocator is plain torch: runs anywhere
+    assert w.shape == (3, 5) and torch.allclose(w.sum(1), torch.ones(3), atol=1e-6)
+    wc = dnn.KeynesNet(2, hidden_size=8, transform_type="Conv")(torch.randn(3, 2, 7, 5))
+    assert wc.shape == (3, 5)
+
+
+def test_keynesnet_conv_equals_the_per_asset_loop():
+    """nn.py:318-322 convolves every asset separately with one 1-D kernel; the (3, 1) 2-D kernel is the same map."""
+    torch.manual_seed(0)
+    net = dnn.KeynesNet(2, hidden_size=8, transform_type="Conv").double()
+    conv1d = torch.nn.Conv1d(2, 8, kernel_size=3, padding=1).double()
+    with torch.no_grad():
+        conv1d.weight.copy_(net.transform_layer.weight[..., 0])
+        conv1d.bias.copy_(net.transform_layer.bias)
+    x = torch.randn(3, 2, 7, 5, dtype=torch.float64)
+    loop = torch.stack([conv1d(x[..., i]) for i in range(5)], dim=-1)
+    assert torch.allclose(net.transform_layer(x), loop, atol=1e-12)
+
+
+def test_resample_rejects_other_allocators():
+    from deepdow_b200 import Resample
+    with pytest.raises(TypeError):                           # allocate.py:323-328
+        Resample(torch.nn.Identity())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,max_weight", [("sparsemax", 1.0), ("sparsemax", 0.05), ("softmax", 1.0), ("softmax", 0.05)])
+def test_keynesnet_with_cuda_allocators_config3(kind, max_weight):
+    """BASELINE.json config 3: KeynesNet with its allocator swapped for the sparsemax / variational softmax, n_assets=100,
+    batch=1024 (nn.py:296-298 is where a user swaps it).  The allocator's output inside the network equals the oracle's on
+    the logits and temperatures it was given, and a training step reaches every parameter."""
+    import oracle
+    from deepdow_b200 import SoftmaxAllocator, SparsemaxAllocator
+    dev = "cuda:0"
+    torch.manual_seed(3)
+    alloc = (SparsemaxAllocator(100, temperature=None, max_weight=max_weight) if kind == "sparsemax"
+             else SoftmaxAllocator(temperature=None, formulation="variational", n_assets=100, max_weight=max_weight))
+    net = dnn.KeynesNet(2, hidden_size=8, n_groups=4, portfolio_opt_layer=alloc).to(dev)
+    with torch.no_grad():
+        net.temperature.fill_(0.05)                           # sharp enough that the cap and the zero bound bind
+    X = torch.randn(1024, 2, 12, 100, device=dev)
+    y = torch.randn(1024, 2, 6, 100, device=dev) * 0.01
+    seen = {}
+    alloc.register_forward_hook(lambda m, inp, out: seen.update(x=inp[0].detach(), t=inp[1].detach(), w=out.detach()))
+    w = net(X)
+    assert w.shape == (1024, 100) and w.dtype == X.dtype and w.device == X.device
+    assert torch.allclose(w.sum(1), torch.ones(1024, device=dev), atol=1e-5)
+    assert (w >= -1e-6).all() and (w <= max_weight + 1e-6).all()
+    xin = (seen["x"].double() / seen["t"].double()[:, None]).cpu().numpy()
+    ref = oracle.capped_simplex_fwd(xin, max_weight) if kind == "sparsemax" else oracle.capped_softmax_fwd(xin, max_weight)
+    assert np.abs(seen["w"].double().cpu().numpy() - ref).max() < 1e-5
+    if kind == "sparsemax":
+        clear = np.abs(ref) > 1e-6                            # supports must match exactly away from ties
+        assert ((seen["w"].cpu().numpy() > 0) == (ref > 0))[clear | (ref == 0)].all()
+    loss = dnn.sharpe_ratio_loss(w, y).mean()
+    loss.backward()
+    for name, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    assert float(net.temperature.grad.abs()) > 0
+
+
+@pytest.mark.gpu
+def test_thorpnet_shared_problem_equals_the_per_sample_path():
+    """the n identical problems of a ThorpNet batch solved once (opt-in) give the weights and the
+    parameter gradients of the per-sample path (nn.py:563-579)."""
+    dev = "cuda:0"
+    torch.manual_seed(5)
+    net = dnn.ThorpNet(40, max_weight=0.1).to(dev)
+    with torch.no_grad():
+        net.exp_returns.normal_(0, 0.05)
+        net.matrix.add_(0.05 * torch.randn(40, 40, device=dev))
+    X = torch.randn(256, 1, 5, 40, device=dev)
+    y = torch.randn(256, 1, 6, 40, device=dev) * 0.01
+    grads = []
+    for shared in (False, True):
+        net.shared_problem = shared
+        net.zero_grad()
+        w = net(X)
+        dnn.sharpe_ratio_loss(w, y).mean().backward()
+        grads.append((w.detach().clone(), [p.grad.clone() for p in net.parameters()]))
+    assert torch.allclose(grads[0][0], grads[1][0], atol=1e-6)
+    for ga, gb in zip(grads[0][1], grads[1][1]):
+        assert torch.allclose(ga, gb, rtol=2e-4, atol=1e-6 * float(ga.abs().max()) + 1e-9)

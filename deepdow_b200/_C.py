@@ -37,6 +37,9 @@ SIGNATURES = {
     "ddw_markowitz_host_scratch_bytes": (_sz, [_i64, _i64, _i32, _i64]),
     "ddw_markowitz_host_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _sz, _vp]),
+    "ddw_risk_budgeting_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "ddw_risk_budgeting_fwd": (_i32, [_vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ddw_risk_budgeting_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ddw_capped_simplex_fwd": (_i32, [_vp, _vp, _dbl, _dbl, _i64, _i64, _i32, _vp, _vp]),
     "ddw_capped_simplex_bwd": (_i32, [_vp, _vp, _vp, _vp, _dbl, _dbl, _i64, _i64, _i32, _vp, _vp, _vp]),
     "ddw_capped_argmax_fwd": (_i32, [_vp, _dbl, _i64, _i64, _i32, _vp, _vp]),

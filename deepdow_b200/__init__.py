@@ -5,9 +5,9 @@ Same class names, constructor and ``forward`` signatures as ``deepdow.layers`` f
 (reference deepdow/layers/allocate.py:198-273, 414-595 and deepdow/layers/misc.py:33-201), backed by
 hand-written sm_100a CUDA kernels behind the C ABI of ``include/ddw.h``.
 """
-from .layers import (CovarianceMatrix, NumericalMarkowitz, Resample, SoftmaxAllocator, SolverError,
+from .layers import (CovarianceMatrix, NumericalMarkowitz, NumericalRiskBudgeting, Resample, SoftmaxAllocator, SolverError,
                      SparsemaxAllocator)
 
-__all__ = ["CovarianceMatrix", "NumericalMarkowitz", "Resample", "SoftmaxAllocator", "SparsemaxAllocator",
+__all__ = ["CovarianceMatrix", "NumericalMarkowitz", "NumericalRiskBudgeting", "Resample", "SoftmaxAllocator", "SparsemaxAllocator",
            "SolverError"]
 __version__ = "0.1.0"

@@ -62,7 +62,11 @@ class MinimumVariance(_Benchmark):
             covmat_sqrt = self._cov(x[:, self.returns_channel])
             zeros = torch.zeros(n_samples, n_assets, dtype=x.dtype, device=x.device)
             ones = torch.ones(n_samples, dtype=x.dtype, device=x.device)
-            return NumericalMarkowitz(n_assets, max_weight=self.max_weight)(zeros, covmat_sqrt, ones, zeros[:, 0])
+            layer = NumericalMarkowitz(n_assets, max_weight=self.max_weight)
+            # a benchmark is called once per evaluation and the layer is rebuilt per call: check the solver status inside the
+            # call (the reference raises SolverError from here too); the lazy mode would never get to report
+            layer.check_status = True
+            return layer(zeros, covmat_sqrt, ones, zeros[:, 0])
 
     @property
     def hparams(self):

@@ -36,6 +36,10 @@ int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, co
 template <typename T>
 int row_op_t(int, const void *, const void *, double, double, long long, int, const void *, const void *, void *,
              void *, void *, cudaStream_t);
+size_t risk_budgeting_workspace_bytes(long long B, int N, int tsize);      // risk_budgeting.cu
+template <typename T>
+int risk_budgeting_t(bool, const void *, const void *, const void *, const void *, const int8_t *, double, long long, int, void *,
+                     int8_t *, int32_t *, void *, void *, void *, size_t, cudaStream_t);
 size_t covariance_workspace_bytes(long long B, int L, int N, int tsize, int do_sqrt);
 template <typename T>
 int covariance_fwd_t(const void *, const void *, int, int, long long, int, int, void *, void *, void *, int32_t *,
@@ -136,6 +140,40 @@ static int row_call(const char *fn, int which, const void *x, const void *temper
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64 ? row_op_t<double>(which, x, temperature, tscalar, u, B, (int)N, grad_w, w, out, d_x, d_t, st)
                             : row_op_t<float>(which, x, temperature, tscalar, u, B, (int)N, grad_w, w, out, d_x, d_t, st);
+}
+
+size_t ddw_risk_budgeting_workspace_bytes(int64_t B, int64_t N, int dtype) {
+    if (B <= 0 || N <= 0 || N > 1024) return 0;
+    return risk_budgeting_workspace_bytes(B, (int)N, dtype == DDW_F64 ? 8 : 4);
+}
+
+int ddw_risk_budgeting_fwd(const void *covmat_sqrt, const void *b, double max_weight, int64_t B, int64_t N, int dtype,
+                           void *w, int8_t *state, int32_t *status, void *workspace, size_t workspace_bytes, void *stream) {
+    g_err[0] = 0;
+    int rc = check_dims("ddw_risk_budgeting_fwd", B, N, 1024, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!covmat_sqrt || !b || !w || !state || !status) { set_error("ddw_risk_budgeting_fwd: null pointer"); return DDW_ERR_ARG; }
+    DDW_CHECK_ALIGNED("ddw_risk_budgeting_fwd", covmat_sqrt, b, w, workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64
+               ? risk_budgeting_t<double>(false, covmat_sqrt, b, nullptr, nullptr, nullptr, max_weight, B, (int)N, w, state, status, nullptr, nullptr, workspace, workspace_bytes, st)
+               : risk_budgeting_t<float>(false, covmat_sqrt, b, nullptr, nullptr, nullptr, max_weight, B, (int)N, w, state, status, nullptr, nullptr, workspace, workspace_bytes, st);
+}
+
+int ddw_risk_budgeting_bwd(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt, const void *b,
+                           double max_weight, int64_t B, int64_t N, int dtype, void *d_covmat_sqrt, void *d_b,
+                           void *workspace, size_t workspace_bytes, void *stream) {
+    g_err[0] = 0;
+    int rc = check_dims("ddw_risk_budgeting_bwd", B, N, 1024, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!grad_w || !w || !state || !covmat_sqrt || !b || !d_covmat_sqrt || !d_b) { set_error("ddw_risk_budgeting_bwd: null pointer"); return DDW_ERR_ARG; }
+    DDW_CHECK_ALIGNED("ddw_risk_budgeting_bwd", grad_w, w, covmat_sqrt, b, d_covmat_sqrt, d_b, workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64
+               ? risk_budgeting_t<double>(true, covmat_sqrt, b, grad_w, w, state, max_weight, B, (int)N, nullptr, nullptr, nullptr, d_covmat_sqrt, d_b, workspace, workspace_bytes, st)
+               : risk_budgeting_t<float>(true, covmat_sqrt, b, grad_w, w, state, max_weight, B, (int)N, nullptr, nullptr, nullptr, d_covmat_sqrt, d_b, workspace, workspace_bytes, st);
 }
 
 int ddw_capped_simplex_fwd(const void *x, const void *temperature, double temperature_scalar, double max_weight,

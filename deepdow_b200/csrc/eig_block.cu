@@ -25,7 +25,7 @@ constexpr int kBjB = 32;              // block width
 constexpr int kBjW = 2 * kBjB;        // width of a block pair = K and N of the update GEMMs
 constexpr int kBjMaxSweeps = 20;
 constexpr float kBjSigRel = 1e-4f;    // a rotation is "significant" (another sweep is needed) above this relative size
-constexpr int kLocalThreads = 128;
+constexpr int kLocalThreads = 256;      // 8 warps: the per-step dependent chains (LDS -> 4 FMAs -> STS, two barriers) need the extra warps
 
 struct BjArgs {
     int N, NP, nb;                    // n_assets, padded size (multiple of 128), number of 32-wide blocks (NP / 32)
@@ -323,30 +323,31 @@ __global__ void __launch_bounds__(kUpdThreads, 4) bj_update_kernel(BjArgs a, int
     constexpr uint32_t kCols = 2 * kBjW;      // 128: accumulator 0 = hi*hi, accumulator 1 = cross terms
     constexpr uint32_t idesc = tc::idesc_tf32(tc::kTileM, kBjW);
 
-    // element (m, k): row IJ_k of X, column m0 + m.  Thread -> m = tid (its TMEM lane as well), all 8 groups of four k.
-    float va[8][4], vb[4][4];
-    auto load_chunk = [&](int c) {
+    // element (m, k): row IJ_k of X, column m0 + m.  Thread -> m = tid (its TMEM lane as well) and ALL 64 k: the values it
+    // stages are also the base term X(m, n) of its own epilogue row, so they stay in registers and nothing is re-read.
+    float va[16][4], vb[4][4];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int k = c * kUpdKC + 4 * it;
-            const int r0 = k < kBjB ? I0 + k : J0 + k - kBjB;
-            const float *src = X + (long long)r0 * NP + m0 + tid;
+    for (int it = 0; it < 16; ++it) {         // 64 independent 4-byte loads in flight per thread
+        const int k = 4 * it;
+        const int r0 = k < kBjB ? I0 + k : J0 + k - kBjB;
+        const float *src = X + (long long)r0 * NP + m0 + tid;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) va[it][q] = __ldg(src + (long long)q * NP);
-        }
+        for (int q = 0; q < 4; ++q) va[it][q] = __ldg(src + (long long)q * NP);
+    }
+    auto load_e = [&](int c) {               // E^T: (n, k) = ET[n][k]; thread -> (k4 = id % 8, n = id / 8)
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {     // E^T: (n, k) = ET[n][k]; thread -> (k4 = id % 8, n = id / 8)
+        for (int it = 0; it < 4; ++it) {
             const int id = it * kUpdThreads + tid;
             const float4 t4 = __ldg(reinterpret_cast<const float4 *>(ET + (id >> 3) * kBjW + c * kUpdKC + 4 * (id & 7)));
             vb[it][0] = t4.x; vb[it][1] = t4.y; vb[it][2] = t4.z; vb[it][3] = t4.w;
         }
     };
-    auto store_chunk = [&]() {
+    auto store_chunk = [&](int c) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             float4 h, l;
-            tc::split_tf32(va[it][0], h.x, l.x); tc::split_tf32(va[it][1], h.y, l.y);
-            tc::split_tf32(va[it][2], h.z, l.z); tc::split_tf32(va[it][3], h.w, l.w);
+            tc::split_tf32(va[8 * c + it][0], h.x, l.x); tc::split_tf32(va[8 * c + it][1], h.y, l.y);
+            tc::split_tf32(va[8 * c + it][2], h.z, l.z); tc::split_tf32(va[8 * c + it][3], h.w, l.w);
             const int off = (tid >> 3) * kUpdSbo + it * tc::kLbo + (tid & 7) * 16;
             *reinterpret_cast<float4 *>(a_hi + off) = h;
             *reinterpret_cast<float4 *>(a_lo + off) = l;
@@ -375,11 +376,11 @@ __global__ void __launch_bounds__(kUpdThreads, 4) bj_update_kernel(BjArgs a, int
         }
     };
 
-    load_chunk(0);
+    load_e(0);
     if (tid == 0) { mbar_init(&sh.done[0], 1); mbar_init(&sh.done[1], 1); fence_mbar_init(); }
     if (warp == 0) tc::tmem_alloc(&sh.tmem_base, kCols);
-    store_chunk();
-    load_chunk(1);                            // in flight while the tensor core works on chunk 0
+    store_chunk(0);
+    load_e(1);                                // in flight while the tensor core works on chunk 0
     fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
@@ -387,32 +388,30 @@ __global__ void __launch_bounds__(kUpdThreads, 4) bj_update_kernel(BjArgs a, int
     const uint32_t tmem = sh.tmem_base;
     if (tid == 0) { issue_chunk(0, tmem); tc::mma_commit(&sh.done[0]); }
     mbar_wait(&sh.done[0], 0);                // chunk 0 consumed: the buffer is free again
-    store_chunk();
+    store_chunk(1);
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) { tc::fence_after_sync(); issue_chunk(1, tmem); tc::mma_commit(&sh.done[1]); }
-    // epilogue: this thread owns row m = tid; the base term X(m, n) is re-read (coalesced over the warp, L2 hits)
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        const int r0 = half ? J0 : I0;
-        float basev[32];
+    mbar_wait(&sh.done[1], 0);
+    tc::fence_after_sync();
+    // epilogue: this thread owns row m = tid; four quarters of 16 columns keep the register count at 128
 #pragma unroll
-        for (int j = 0; j < 32; ++j) basev[j] = __ldg(X + (long long)(r0 + j) * NP + m0 + tid);
-        if (half == 0) { mbar_wait(&sh.done[1], 0); tc::fence_after_sync(); }
-        const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * half);
-        float v[32], x[32];
-        tc::tmem_ld32(lane_addr, v);
-        tc::tmem_ld32(lane_addr + kBjW, x);
+    for (int qt = 0; qt < 4; ++qt) {
+        const int r0 = (qt < 2 ? I0 : J0) + 16 * (qt & 1);
+        const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(16 * qt);
+        float v[16], x[16];
+        tc::tmem_ld16(lane_addr, v);
+        tc::tmem_ld16(lane_addr + kBjW, x);
         if (PHASE == 0 && which == 0) {
-            // Z[m][IJ_n]: 32 consecutive floats of row m
+            // Z[m][IJ_n]: 16 consecutive floats of row m
             float4 *dst = reinterpret_cast<float4 *>(Y + (long long)(m0 + tid) * NP + r0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                dst[j] = make_float4(basev[4 * j] + (v[4 * j] + x[4 * j]), basev[4 * j + 1] + (v[4 * j + 1] + x[4 * j + 1]),
-                                     basev[4 * j + 2] + (v[4 * j + 2] + x[4 * j + 2]), basev[4 * j + 3] + (v[4 * j + 3] + x[4 * j + 3]));
+            for (int j = 0; j < 4; ++j)
+                dst[j] = make_float4(va[4 * qt + j][0] + (v[4 * j] + x[4 * j]), va[4 * qt + j][1] + (v[4 * j + 1] + x[4 * j + 1]),
+                                     va[4 * qt + j][2] + (v[4 * j + 2] + x[4 * j + 2]), va[4 * qt + j][3] + (v[4 * j + 3] + x[4 * j + 3]));
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) Y[(long long)(r0 + j) * NP + m0 + tid] = basev[j] + (v[j] + x[j]);
+            for (int j = 0; j < 16; ++j) Y[(long long)(r0 + j) * NP + m0 + tid] = va[4 * qt + (j >> 2)][j & 3] + (v[j] + x[j]);
         }
     }
     tc::fence_before_sync();

@@ -369,18 +369,23 @@ __device__ __forceinline__ void diag_init_warp(const T *qdiag, int qstride, cons
     *dmax_out = dmax;
 }
 
-// write the result of a converged / abandoned active-set iteration
+// write the result of a converged / abandoned active-set iteration.  Returns (block-wide) whether a weight is not finite:
+// NaN / Inf inputs make every comparison of the active-set step false, which reads as "converged" -- the caller turns the
+// flag into DDW_STATUS_INEXACT so that the host layer raises SolverError instead of passing NaN weights on.
 template <typename T, int kThreads>
-__device__ __forceinline__ void write_result(const MkSmem<T> &s, int N, T u, T *w_out, int8_t *st_out) {
+__device__ __forceinline__ int write_result(const MkSmem<T> &s, int N, T u, T *w_out, int8_t *st_out) {
+    int bad = 0;
     for (int i = threadIdx.x; i < N; i += kThreads) {
         int8_t st = s.st[i];
         const T wi = st == 0 ? clampT(s.wv[i], T(0), u) : (st > 0 ? u : T(0));
         // tie rule: a free asset whose weight lands exactly on a bound (within rounding) is reported as
         // active, so the saved state is a function of the returned weights
         if (st == 0) st = wi <= T(0) ? -1 : (wi >= u ? 1 : 0);
+        bad |= !(absT(s.r[i]) < Num<T>::inf()) || (s.st[i] == 0 && !(absT(s.wv[i]) < Num<T>::inf()));   // NaN compares false
         w_out[i] = wi;
         st_out[i] = st;
     }
+    return __syncthreads_or(bad);
 }
 
 // returns 1 when the problem was decided by the box alone (infeasible or a single feasible point)

@@ -61,10 +61,11 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> 
         for (int it = 0; it < kMaxPdas; ++it) {
             if (!pdas_step<T, kThreads, NREG>(s, N, LD, p.u, dmin, tolw, lifted)) { converged = 1; break; }
         }
-        write_result<T, kThreads>(s, N, p.u, w_out, st_out);
+        const int nonfinite = write_result<T, kThreads>(s, N, p.u, w_out, st_out);
         if (tid == 0) {
             int st = lifted ? DDW_STATUS_REGULARIZED : 0;
-            if (!converged) {
+            if (nonfinite) { st |= DDW_STATUS_INEXACT; atomicAdd(p.bad_count, 1); }     // NaN / Inf in the inputs
+            else if (!converged) {
                 st |= DDW_STATUS_FALLBACK | DDW_STATUS_INEXACT;
                 const int slot = atomicAdd(p.fail_count, 1);
                 p.fail_list[slot] = (int)b;
@@ -272,8 +273,11 @@ __global__ void __launch_bounds__(kThreads) markowitz_ipm_kernel(MkFwdParams<T> 
             if (!pdas_step<T, kThreads, NREG>(s, N, LD, u, dmin, T(8) * Num<T>::eps(), lifted)) { converged = 1; break; }
         }
         if (converged) {
-            write_result<T, kThreads>(s, N, u, p.w + b * N, p.state + b * N);
-            if (tid == 0) p.status[b] = DDW_STATUS_FALLBACK | (lifted ? DDW_STATUS_REGULARIZED : 0);
+            const int nonfinite = write_result<T, kThreads>(s, N, u, p.w + b * N, p.state + b * N);
+            if (tid == 0) {
+                p.status[b] = DDW_STATUS_FALLBACK | (lifted ? DDW_STATUS_REGULARIZED : 0) | (nonfinite ? DDW_STATUS_INEXACT : 0);
+                if (nonfinite) atomicAdd(p.bad_count, 1);
+            }
         } else {
             const T thr = T(1e3) * Num<T>::eps();
             for (int i = tid; i < N; i += kThreads) {

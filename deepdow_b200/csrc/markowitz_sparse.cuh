@@ -308,16 +308,19 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fw
         if (tid == 0) { const int sl = atomicAdd(p.work_count, 1); p.work_list[sl] = (int)b; }
         return;
     }
+    int bad = 0;
     for (int i = tid; i < N; i += kThreads) {
         int8_t st = s.st[i];
         const T wi = st == 0 ? clampT(s.wv[i], T(0), u) : (st > 0 ? u : T(0));
-        if (st == 0) st = wi <= T(0) ? -1 : (wi >= u ? 1 : 0);   // tie rule, see write_result
+        if (st == 0) { bad |= !(absT(s.wv[i]) < Num<T>::inf()); st = wi <= T(0) ? -1 : (wi >= u ? 1 : 0); }   // tie rule, see write_result
         w_out[i] = wi;
         st_out[i] = st;
     }
+    const int nonfinite = __syncthreads_or(bad);      // NaN / Inf inputs read as "converged": report them (see write_result)
     if (tid == 0) {
         int st = lifted ? DDW_STATUS_REGULARIZED : 0;
-        if (!converged) {
+        if (nonfinite) { st |= DDW_STATUS_INEXACT; atomicAdd(p.bad_count, 1); }
+        else if (!converged) {
             st |= DDW_STATUS_FALLBACK | DDW_STATUS_INEXACT;
             const int sl = atomicAdd(p.fail_count, 1);
             p.fail_list[sl] = (int)b;

@@ -5,6 +5,7 @@ Argument meaning, error behaviour and output dtype/device follow the reference:
   SoftmaxAllocator     deepdow/layers/allocate.py:414-514
   SparsemaxAllocator   deepdow/layers/allocate.py:517-595
   CovarianceMatrix     deepdow/layers/misc.py:33-201
+  NumericalRiskBudgeting  deepdow/layers/allocate.py:631-691
   Resample             deepdow/layers/allocate.py:276-411 (the caller that chains CovarianceMatrix(sqrt=True) into
                        NumericalMarkowitz; only its NumericalMarkowitz arm, the other allocators are out of scope)
 """
@@ -244,6 +245,99 @@ class NumericalMarkowitz(nn.Module):
     def __setstate__(self, state):
         self.__dict__.update(state)
         self._watch = _StatusWatch()
+
+
+# ------------------------------------------------------------------------------------------------
+# NumericalRiskBudgeting
+# ------------------------------------------------------------------------------------------------
+class _RiskBudgetingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, covmat_sqrt, b, max_weight):
+        _C.require_cuda(covmat_sqrt, b)
+        lib = _C.lib()
+        B, N = b.shape
+        dt = _C.dtype_code(b)
+        cov_c, b_c = _C.aligned(covmat_sqrt), _C.aligned(b)
+        w = torch.empty_like(b_c)
+        state = torch.empty((B, N), dtype=torch.int8, device=b.device)
+        status = torch.empty((B,), dtype=torch.int32, device=b.device)
+        ws = _workspace(lib.ddw_risk_budgeting_workspace_bytes(B, N, dt), b.device)
+        with _C.device_guard(b):
+            rc = lib.ddw_risk_budgeting_fwd(_C.ptr(cov_c), _C.ptr(b_c), float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state),
+                                            _C.ptr(status), _C.ptr(ws), ws.numel(), _C.stream(b.device))
+        _C.check(rc, "ddw_risk_budgeting_fwd")
+        bad = int(ws[:4].view(torch.int32))          # the reference raises from inside the call; so do we (one sync)
+        if bad:
+            raise SolverError(f"{bad} risk budgeting problems could not be solved (batch of {B}, n_assets={N}, "
+                              f"max_weight={max_weight})")
+        ctx.save_for_backward(w, state, cov_c, b_c)
+        ctx.max_weight = float(max_weight)
+        ctx.mark_non_differentiable(status)
+        return w, status
+
+    @staticmethod
+    def backward(ctx, grad_w, _grad_status):
+        w, state, cov_c, b_c = ctx.saved_tensors
+        lib = _C.lib()
+        B, N = w.shape
+        dt = _C.dtype_code(w)
+        g = _C.aligned(grad_w)
+        d_cov = torch.empty_like(cov_c)
+        d_b = torch.empty_like(b_c)
+        ws = _workspace(lib.ddw_risk_budgeting_workspace_bytes(B, N, dt), w.device)
+        with _C.device_guard(w):
+            rc = lib.ddw_risk_budgeting_bwd(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov_c), _C.ptr(b_c), ctx.max_weight, B, N,
+                                            dt, _C.ptr(d_cov), _C.ptr(d_b), _C.ptr(ws), ws.numel(), _C.stream(w.device))
+        _C.check(rc, "ddw_risk_budgeting_bwd")
+        return d_cov, d_b, None
+
+
+class NumericalRiskBudgeting(nn.Module):
+    """Convex optimization layer stylized into portfolio optimization problem.
+
+    Drop-in for ``deepdow.layers.NumericalRiskBudgeting`` (allocate.py:631-691).  Solves, per sample,
+
+        minimize  0.5 * ||covmat_sqrt @ w||^2 - b @ log(w)
+        s.t.      sum(w) == 1, 0 <= w <= max_weight
+
+    (at the optimum with a loose cap the risk contribution of every asset is proportional to its budget ``b``) by a
+    feasible-point Newton method on the GPU instead of through cvxpylayers.
+
+    Parameters
+    ----------
+    n_assets : int
+        Number of assets.
+    max_weight : float
+        Upper bound of every weight.
+    """
+
+    def __init__(self, n_assets, max_weight=1):
+        super().__init__()
+        self.n_assets = n_assets
+        self.max_weight = max_weight
+        self.last_status = None
+
+    def forward(self, covmat_sqrt, b):
+        """covmat_sqrt (n_samples, n_assets, n_assets); b (n_samples, n_assets) risk budgets.  Returns weights
+        (n_samples, n_assets), same dtype and device."""
+        n_samples, n_assets = b.shape
+        if n_assets != self.n_assets:
+            raise ValueError(f"expected n_assets={self.n_assets}, got {n_assets}")
+        if covmat_sqrt.shape != (n_samples, n_assets, n_assets):
+            raise ValueError("covmat_sqrt needs shape (n_samples, n_assets, n_assets)")
+        if n_assets * float(self.max_weight) < 1.0 - 1e-6:
+            raise SolverError(f"infeasible: n_assets * max_weight = {n_assets * float(self.max_weight):g} < 1")
+        w, status = _RiskBudgetingFn.apply(covmat_sqrt.to(b.dtype), b, self.max_weight)
+        self.last_status = status
+        return w
+
+    def extra_repr(self):
+        return f"n_assets={self.n_assets}, max_weight={self.max_weight}"
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["last_status"] = None
+        return state
 
 
 # ------------------------------------------------------------------------------------------------

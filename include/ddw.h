@@ -7,6 +7,7 @@
  *     deepdow/layers/allocate.py:273   NumericalMarkowitz   (CvxpyLayer built at :236-238)
  *     deepdow/layers/allocate.py:595   SparsemaxAllocator   (CvxpyLayer built at :560)
  *     deepdow/layers/allocate.py:513   SoftmaxAllocator, formulation="variational" (:475)
+ *     deepdow/layers/allocate.py:691   NumericalRiskBudgeting (CvxpyLayer built at :669-671)
  * and the per-sample torch loop of
  *     deepdow/layers/misc.py:107-119   CovarianceMatrix.forward
  *                        :121-166      compute_covariance, :168-201 compute_sqrt.
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DDW_VERSION 101
+#define DDW_VERSION 102
 
 enum ddw_dtype { DDW_F32 = 0, DDW_F64 = 1 };
 
@@ -131,6 +132,24 @@ int ddw_markowitz_host_step(ddw_host_pipeline *pipe,
                             void *h_w, int32_t *h_status,
                             void *h_d_rets, void *h_d_covmat_sqrt, void *h_d_gamma_sqrt, void *h_d_alpha,
                             void *dev_scratch, size_t dev_scratch_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NumericalRiskBudgeting -- replaces self.cvxpylayer(covmat_sqrt, b)[0] (deepdow/layers/allocate.py:673-691; the
+ * program is stated at :651-671):
+ *   minimise  1/2 ||covmat_sqrt w||^2 - b' log(w)   s.t.  sum(w) = 1, 0 <= w <= max_weight
+ * covmat_sqrt (B,N,N)  b (B,N) risk budgets (nonnegative; zeros are floored at the smallest normal number)
+ * w (B,N) out; state (B,N) int8 out: +1 at max_weight, 0 free (saved for backward); status (B) int32 out: the
+ * ddw_status bits in the low 16 bits, the number of Newton / active-set iterations used above them.
+ * After the forward the first int32 of the workspace holds the number of portfolios left DDW_STATUS_INFEASIBLE or
+ * DDW_STATUS_INEXACT.  The backward is the implicit differentiation of the KKT system on the free set:
+ * grad_w (B,N) -> d_covmat_sqrt (B,N,N), d_b (B,N).
+ * ------------------------------------------------------------------------------------------- */
+size_t ddw_risk_budgeting_workspace_bytes(int64_t B, int64_t N, int dtype);
+int ddw_risk_budgeting_fwd(const void *covmat_sqrt, const void *b, double max_weight, int64_t B, int64_t N, int dtype,
+                           void *w, int8_t *state, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+int ddw_risk_budgeting_bwd(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt, const void *b,
+                           double max_weight, int64_t B, int64_t N, int dtype, void *d_covmat_sqrt, void *d_b,
+                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SparsemaxAllocator -- replaces self.layer(x / temperature[:, None])[0] (allocate.py:586-595):

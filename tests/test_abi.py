@@ -37,7 +37,7 @@ def test_ctypes_table_matches_header():
 
 
 def test_version_and_error_channel(lib):
-    assert lib.ddw_version() == 101
+    assert lib.ddw_version() == 102
     assert isinstance(lib.ddw_last_error(), bytes)
 
 

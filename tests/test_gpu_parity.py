@@ -699,3 +699,66 @@ def test_resample_over_numerical_markowitz(dtype, sqrt):
     tolw = 2e-5 if dtype == torch.float32 else 1e-9
     assert np.abs(w.detach().double().cpu().numpy() - w_ref).max() < tolw
     assert rel_err(rets.grad, d_ref) < (2e-3 if dtype == torch.float32 else 1e-7)
+
+
+# ------------------------------------------------------------------ NumericalRiskBudgeting (allocate.py:631-691)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B,N,u,kind", [(16, 6, 1.0, "ref"), (64, 20, 1.0, "ref"), (32, 50, 0.05, "ref"), (64, 100, 1.0, "sqrtcov"),
+                                        (32, 100, 0.02, "sqrtcov"), (4, 150, 0.02, "ref"), (3, 300, 1.0, "sqrtcov")])
+def test_risk_budgeting_vs_oracle(dtype, B, N, u, kind):
+    from deepdow_b200 import NumericalRiskBudgeting
+    rng = np.random.default_rng(B * 13 + N)
+    if kind == "ref":                        # the matrices of tests/test_layers.py:1011-1015
+        R = rng.random((B, N, N))
+        A = R @ R / N + np.eye(N)
+    else:
+        A = oracle.covariance_fwd(rng.standard_normal((B, max(40, N // 2), N)), 0.5, "diagonal", True)
+    b = rng.random((B, N)); b /= b.sum(1, keepdims=True)
+    G = rng.standard_normal((B, N))
+    tA, tb = t(A, dtype, True), t(b, dtype, True)
+    w_ref, st_ref, kkt, status = oracle.risk_budgeting_fwd(tA.detach().double().cpu().numpy(), tb.detach().double().cpu().numpy(), u)
+    assert kkt.max() < 1e-8 and (status == 0).all()
+    layer = NumericalRiskBudgeting(N, max_weight=u)
+    w = layer(tA, tb)
+    assert w.shape == (B, N) and w.dtype == dtype and w.device == torch.device(DEV)
+    assert np.abs(w.detach().double().cpu().numpy() - w_ref).max() < W_ATOL[dtype]
+    assert torch.allclose(w.sum(1), torch.ones(B, dtype=dtype, device=DEV), atol=10 * W_ATOL[dtype])
+    assert w.min() > 0 and w.max() <= u + 1e-7
+    assert int((layer.last_status & 0xFFFF).ne(0).sum()) == 0
+    if u < 1:
+        assert (st_ref == 1).sum() > 0          # the cap binds somewhere: the case is what it claims to be
+    (w * t(G, dtype)).sum().backward()
+    dA_ref, db_ref = oracle.risk_budgeting_bwd(G, w_ref, st_ref, tA.detach().double().cpu().numpy(), tb.detach().double().cpu().numpy(), u)
+    assert rel_err(tb.grad, db_ref) < 2 * G_RTOL[dtype], rel_err(tb.grad, db_ref)
+    assert rel_err(tA.grad, dA_ref) < 2 * G_RTOL[dtype], rel_err(tA.grad, dA_ref)
+
+
+def test_risk_budgeting_reference_behaviour():
+    """tests/test_layers.py:1003-1030 restated: shape, budget, dtype, device, identical problems give identical weights; plus
+    the SolverError conventions of the other allocators, zero parameters and pickling."""
+    import pickle
+    from deepdow_b200 import NumericalRiskBudgeting
+    n_samples, n_assets = 5, 6
+    for dtype in (torch.float32, torch.float64):
+        popt = NumericalRiskBudgeting(n_assets)
+        c = torch.rand(n_assets, n_assets, device=DEV, dtype=dtype)
+        c = c @ c + torch.eye(n_assets, device=DEV, dtype=dtype)
+        covmat_sqrt = torch.stack(n_samples * [c])
+        budgets = torch.rand(n_samples, n_assets, device=DEV, dtype=dtype)
+        budgets /= budgets.sum(-1, keepdim=True)
+        weights = popt(covmat_sqrt, budgets)
+        assert weights.shape == (n_samples, n_assets)
+        assert torch.allclose(weights.sum(-1), torch.ones(n_samples, device=DEV, dtype=dtype))
+        assert weights.dtype == dtype and weights.device == torch.device(DEV)
+    assert sum(p.numel() for p in popt.parameters()) == 0
+    assert isinstance(pickle.loads(pickle.dumps(popt)), NumericalRiskBudgeting)
+    with pytest.raises(SolverError):
+        NumericalRiskBudgeting(4, 0.2)(covmat_sqrt[:, :4, :4], budgets[:, :4])
+    w = NumericalRiskBudgeting(5, 0.2)(covmat_sqrt[:, :5, :5], budgets[:, :5])
+    assert torch.allclose(w, torch.full_like(w, 0.2))
+    # equal budgets and a diagonal risk matrix: the closed form w_i ~ 1 / sigma_i (risk parity)
+    sig = torch.tensor([1.0, 2.0, 4.0, 8.0], device=DEV, dtype=torch.float64)
+    w = NumericalRiskBudgeting(4)(torch.diag(sig)[None], torch.full((1, 4), 0.25, device=DEV, dtype=torch.float64))
+    # stationarity: sigma_i^2 w_i - b / w_i + nu = 0 with sum w = 1; compare against the oracle and the identity
+    w_ref = oracle.risk_budgeting_fwd(torch.diag(sig)[None].cpu().numpy(), np.full((1, 4), 0.25), 1.0)[0]
+    assert np.abs(w.cpu().numpy() - w_ref).max() < 1e-9

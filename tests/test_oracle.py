@@ -244,3 +244,47 @@ def test_markowitz_bwd_fd():
     assert np.allclose(d_C, _fd(lambda v: L(rets, v, gamma, alpha), C), atol=2e-6)
     assert np.allclose(d_g, _fd(lambda v: L(rets, C, v, alpha), gamma), atol=2e-6)
     assert np.allclose(d_a, _fd(lambda v: L(rets, C, gamma, v), alpha), atol=2e-6)
+
+
+# ------------------------------------------------------------------ NumericalRiskBudgeting oracle (allocate.py:651-691)
+def test_risk_budgeting_oracle_kkt_scipy_and_finite_differences():
+    """The reference holds no numeric golden for NumericalRiskBudgeting (tests/test_layers.py:1003-1030 checks shape, budget
+    and dtype only): the oracle is anchored by its KKT certificate, by scipy SLSQP on the same program and by central finite
+    differences of both gradients; with a loose cap the risk contributions w_i (Q w)_i equal the budgets up to the multiplier."""
+    import scipy.optimize as so
+    rng = np.random.default_rng(0)
+    for (B, N, u) in [(3, 6, 1.0), (2, 10, 0.2), (2, 30, 0.05)]:
+        R = rng.random((B, N, N))
+        A = R @ R + np.eye(N)                                   # as tests/test_layers.py:1011-1015
+        b = rng.random((B, N)); b /= b.sum(1, keepdims=True)
+        w, st, kkt, status = oracle.risk_budgeting_fwd(A, b, u)
+        assert kkt.max() < 1e-9 and (status == 0).all()
+        assert np.allclose(w.sum(1), 1.0, atol=1e-12) and w.min() > 0 and w.max() <= u + 1e-15
+        for i in range(B):
+            Q = A[i].T @ A[i]
+            res = so.minimize(lambda x: 0.5 * x @ Q @ x - b[i] @ np.log(x), np.full(N, 1.0 / N), jac=lambda x: Q @ x - b[i] / x,
+                              method="SLSQP", bounds=[(1e-9, u)] * N,
+                              constraints=[{"type": "eq", "fun": lambda x: x.sum() - 1, "jac": lambda x: np.ones(N)}],
+                              options={"ftol": 1e-16, "maxiter": 2000})
+            assert np.abs(res.x - w[i]).max() < 1e-6
+        if u == 1.0:                                            # risk budgeting identity: w_i (Q w)_i - b_i = -nu w_i
+            Qw = np.einsum("bji,bjk,bk->bi", A, A, w)
+            nu = (b - w * Qw) / w
+            assert np.abs(nu - nu[:, :1]).max() < 1e-8
+        G = rng.standard_normal((B, N))
+        dA, db = oracle.risk_budgeting_bwd(G, w, st, A, b, u)
+        eps = 1e-6
+        for j in range(N):
+            bp, bm = b[:1].copy(), b[:1].copy()
+            bp[0, j] += eps; bm[0, j] -= eps
+            fd = G[0] @ (oracle.risk_budgeting_fwd(A[:1], bp, u)[0][0] - oracle.risk_budgeting_fwd(A[:1], bm, u)[0][0]) / (2 * eps)
+            assert abs(fd - db[0, j]) < 1e-5 * max(1.0, np.abs(db[0]).max())
+        for (j, k) in [(0, 0), (1, 2), (N - 1, 0)]:
+            Ap, Am = A[:1].copy(), A[:1].copy()
+            Ap[0, j, k] += eps; Am[0, j, k] -= eps
+            fd = G[0] @ (oracle.risk_budgeting_fwd(Ap, b[:1], u)[0][0] - oracle.risk_budgeting_fwd(Am, b[:1], u)[0][0]) / (2 * eps)
+            assert abs(fd - dA[0, j, k]) < 1e-4 * max(1e-3, np.abs(dA[0]).max())
+    # box-only cases
+    w, st, kkt, status = oracle.risk_budgeting_fwd(np.eye(4)[None], np.full((1, 4), 0.25), 0.25)
+    assert np.allclose(w, 0.25) and (st == 1).all()
+    assert oracle.risk_budgeting_fwd(np.eye(4)[None], np.full((1, 4), 0.25), 0.2)[3][0] == 8

@@ -26,8 +26,13 @@ template <typename T> int launch_fwd_sparse(const MkFwdParams<T> &p, cudaStream_
 bool bwd_sparse_eligible(int N, int tsize, int smem_limit);
 template <typename T> int launch_bwd_sparse(const MkBwdParams<T> &p, cudaStream_t st);
 
+// markowitz_gram_tc.cu: Q = A'A + |alpha| I on tensor cores into the global workspace (float32, Q beyond shared memory)
+int markowitz_gram_tc(const float *C, const float *gamma, const float *alpha, long long B, long long Bmod, long long b0, int N,
+                      int LD, float *Q, cudaStream_t st);
+
 // Dense forward kernel.  Direct mode (work_list == nullptr): one CTA per portfolio, grid = B.
 // List mode: a fixed grid walks the portfolios that the sparse kernel handed over.
+// MAXT > 0: Gram tiles in registers; 0: Gram through the shared staging area; < 0: Q was formed by markowitz_gram_tc.
 template <typename T, int kThreads, int NREG, bool kGlobal, int MAXT>
 __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -46,9 +51,11 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> 
             gram_lower_reg<T, kThreads, (MAXT > 0 ? MAXT : 1), false>(p.C + b * (long long)N * N, p.gamma,
                                                                        (p.b0 + b) * (long long)N * N, p.Bmod, N, N, nullptr, nullptr,
                                                                        N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
-        else
+        else if (MAXT == 0)
             gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, (p.b0 + b) * (long long)N * N, p.Bmod, N, N,
                                            nullptr, nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
+        else
+            __syncthreads();          // rets staged; Q already sits in the global workspace
         if (tid < 32) {
             T dmax;
             diag_init_warp<T, NREG>(s.Qs, LD + 1, s.r, s.st, N, p.u, &dmax);
@@ -80,7 +87,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> 
 // Launched with a fixed small grid; CTAs walk the list of failed problems.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int kThreads, int NREG, bool kGlobal>
-__global__ void __launch_bounds__(kThreads) markowitz_ipm_kernel(MkFwdParams<T> p, T *ipm_ws) {
+__global__ void __launch_bounds__(kThreads) markowitz_ipm_kernel(MkFwdParams<T> p, T *ipm_ws, int have_q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.N, LD = p.LD, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NP = round_up(N + 2, 32);
@@ -96,8 +103,13 @@ __global__ void __launch_bounds__(kThreads) markowitz_ipm_kernel(MkFwdParams<T> 
         __syncthreads();
         for (int i = tid; i < N; i += kThreads) s.r[i] = p.rets[b * N + i];
         const T aabs = absT(p.alpha[b]);
-        gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, (p.b0 + b) * (long long)N * N, p.Bmod, N, N, nullptr,
-                                       nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
+        // have_q: the lower triangle of Q in the global workspace is still intact (the active-set kernel only wrote the factor
+        // into the strictly upper part)
+        if (!(kGlobal && have_q))
+            gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, (p.b0 + b) * (long long)N * N, p.Bmod, N, N, nullptr,
+                                           nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
+        else
+            __syncthreads();
         // objective scale so that gradients are O(1)
         T sc = T(0);
         for (int i = tid; i < N; i += kThreads) {
@@ -762,7 +774,7 @@ static int launch_fwd_variant(MkFwdParams<T> p, const MkPlan &pl, T *ipm_ws, boo
     }
     if ((rc = check_launch("markowitz_fwd_kernel"))) return rc;
     const unsigned grid = (unsigned)min((long long)kIpmGrid, p.B);
-    ki<<<grid, kThreads, pl.smem, st>>>(p, ipm_ws);
+    ki<<<grid, kThreads, pl.smem, st>>>(p, ipm_ws, MAXT < 0 ? 1 : 0);
     return check_launch("markowitz_ipm_kernel");
 }
 
@@ -795,6 +807,14 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
             return launch_fwd_variant<T, 128, 4, false, 5>(p, pl, l.ipm, sparse_first, st);
         }
         if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, false, 0>(p, pl, l.ipm, false, st);
+    }
+    if (sizeof(T) == 4 && pl.threads >= 256) {
+        // Q in the global workspace (n_assets beyond shared memory), float32: the Gram runs on tensor cores as a pre-pass
+        int rc = markowitz_gram_tc((const float *)C, (const float *)gamma, (const float *)alpha, B, Bmod, b0, N, pl.LD, (float *)l.q, st);
+        if (rc) return rc;
+        if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, true, -1>(p, pl, l.ipm, false, st);
+        if (pl.nreg == 16) return launch_fwd_variant<T, 512, 16, true, -1>(p, pl, l.ipm, false, st);
+        return launch_fwd_variant<T, 512, 32, true, -1>(p, pl, l.ipm, false, st);
     }
     if (pl.threads == 128) return launch_fwd_variant<T, 128, 4, true, 0>(p, pl, l.ipm, false, st);
     if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, true, 0>(p, pl, l.ipm, false, st);

@@ -28,6 +28,10 @@ SIGNATURES = {
     "ddw_markowitz_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "ddw_markowitz_fwd": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddw_markowitz_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ddw_markowitz_saved_bytes": (_sz, [_i64, _i64, _i32]),
+    "ddw_markowitz_fwd_saved": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "ddw_markowitz_bwd_saved": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
+                                       _vp]),
     "ddw_markowitz_fwd_chunk": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddw_markowitz_bwd_chunk": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _i32,
                                        _vp, _vp, _sz, _vp]),

@@ -27,12 +27,13 @@ int check_launch(const char *what) {
 
 // implemented in markowitz_impl.cuh (instantiated in markowitz_{fwd,bwd}_{f32,f64}.cu) / rowproj.cu / covariance.cu
 size_t markowitz_workspace_bytes(long long B, int N, int tsize);
+size_t markowitz_saved_bytes(long long B, int N, int tsize);
 template <typename T>
 int markowitz_fwd_t(const void *, const void *, const void *, const void *, double, long long, int, void *, int8_t *,
-                    int32_t *, void *, size_t, cudaStream_t, long long, long long);
+                    int32_t *, void *, size_t, cudaStream_t, long long, long long, void *);
 template <typename T>
 int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, const void *, const void *, long long,
-                    int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int);
+                    int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int, const void *);
 template <typename T>
 int row_op_t(int, const void *, const void *, double, double, long long, int, const void *, const void *, void *,
              void *, void *, cudaStream_t);
@@ -78,21 +79,43 @@ size_t ddw_markowitz_workspace_bytes(int64_t B, int64_t N, int dtype) {
     return markowitz_workspace_bytes(B, (int)N, dtype == DDW_F64 ? 8 : 4);
 }
 
-int ddw_markowitz_fwd_chunk(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
-                            double max_weight, int64_t B, int64_t N, int dtype, int64_t batch_total, int64_t batch_offset,
-                            void *w, int8_t *state, int32_t *status, void *workspace, size_t workspace_bytes,
-                            void *stream) {
+size_t ddw_markowitz_saved_bytes(int64_t B, int64_t N, int dtype) {
+    if (B <= 0 || N <= 0 || N > 1024) return 0;
+    return markowitz_saved_bytes(B, (int)N, dtype == DDW_F64 ? 8 : 4);
+}
+
+static int markowitz_fwd_impl(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                              double max_weight, int64_t B, int64_t N, int dtype, int64_t batch_total, int64_t batch_offset,
+                              void *w, int8_t *state, int32_t *status, void *workspace, size_t workspace_bytes,
+                              void *saved, size_t saved_bytes, void *stream) {
     g_err[0] = 0;
     int rc = check_dims("ddw_markowitz_fwd", B, N, 1024, dtype);
     if (rc) return rc;
     if (B == 0) return 0;
     if (batch_offset < 0 || batch_offset + B > batch_total || batch_total >= (1LL << 31)) { set_error("ddw_markowitz_fwd: chunk [%lld, %lld) outside the batch of %lld", (long long)batch_offset, (long long)(batch_offset + B), (long long)batch_total); return DDW_ERR_ARG; }
     if (!rets || !covmat_sqrt || !gamma_sqrt || !alpha || !w || !state || !status) { set_error("ddw_markowitz_fwd: null pointer"); return DDW_ERR_ARG; }
-    DDW_CHECK_ALIGNED("ddw_markowitz_fwd", rets, covmat_sqrt, gamma_sqrt, alpha, w, workspace);
+    DDW_CHECK_ALIGNED("ddw_markowitz_fwd", rets, covmat_sqrt, gamma_sqrt, alpha, w, workspace, saved);
+    if (saved && saved_bytes < ddw_markowitz_saved_bytes(B, N, dtype)) { set_error("ddw_markowitz_fwd_saved: saved buffer too small (%zu < %zu)", saved_bytes, ddw_markowitz_saved_bytes(B, N, dtype)); return DDW_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64
-               ? markowitz_fwd_t<double>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, batch_total, batch_offset)
-               : markowitz_fwd_t<float>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, batch_total, batch_offset);
+               ? markowitz_fwd_t<double>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, batch_total, batch_offset, saved)
+               : markowitz_fwd_t<float>(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, batch_total, batch_offset, saved);
+}
+
+int ddw_markowitz_fwd_chunk(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                            double max_weight, int64_t B, int64_t N, int dtype, int64_t batch_total, int64_t batch_offset,
+                            void *w, int8_t *state, int32_t *status, void *workspace, size_t workspace_bytes,
+                            void *stream) {
+    return markowitz_fwd_impl(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, N, dtype, batch_total, batch_offset, w, state,
+                              status, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+int ddw_markowitz_fwd_saved(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                            double max_weight, int64_t B, int64_t N, int dtype, void *w, int8_t *state, int32_t *status,
+                            void *workspace, size_t workspace_bytes, void *saved, size_t saved_bytes, void *stream) {
+    if (!saved) { g_err[0] = 0; set_error("ddw_markowitz_fwd_saved: null saved buffer"); return DDW_ERR_ARG; }
+    return markowitz_fwd_impl(rets, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, N, dtype, B, 0, w, state, status, workspace,
+                              workspace_bytes, saved, saved_bytes, stream);
 }
 
 int ddw_markowitz_fwd(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
@@ -102,11 +125,11 @@ int ddw_markowitz_fwd(const void *rets, const void *covmat_sqrt, const void *gam
                                    workspace, workspace_bytes, stream);
 }
 
-int ddw_markowitz_bwd_chunk(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt,
-                            const void *gamma_sqrt, const void *alpha, double max_weight, int64_t B, int64_t N, int dtype,
-                            int64_t batch_total, int64_t batch_offset, void *d_rets, void *d_covmat_sqrt,
-                            void *d_gamma_sqrt, int accumulate_gamma, void *d_alpha, void *workspace,
-                            size_t workspace_bytes, void *stream) {
+static int markowitz_bwd_impl(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt,
+                              const void *gamma_sqrt, const void *alpha, double max_weight, int64_t B, int64_t N, int dtype,
+                              int64_t batch_total, int64_t batch_offset, void *d_rets, void *d_covmat_sqrt,
+                              void *d_gamma_sqrt, int accumulate_gamma, void *d_alpha, void *workspace,
+                              size_t workspace_bytes, const void *saved, size_t saved_bytes, void *stream) {
     (void)max_weight;
     g_err[0] = 0;
     int rc = check_dims("ddw_markowitz_bwd", B, N, 1024, dtype);
@@ -114,11 +137,31 @@ int ddw_markowitz_bwd_chunk(const void *grad_w, const void *w, const int8_t *sta
     if (B == 0) return 0;
     if (batch_offset < 0 || batch_offset + B > batch_total || batch_total >= (1LL << 31)) { set_error("ddw_markowitz_bwd: chunk [%lld, %lld) outside the batch of %lld", (long long)batch_offset, (long long)(batch_offset + B), (long long)batch_total); return DDW_ERR_ARG; }
     if (!grad_w || !w || !state || !covmat_sqrt || !gamma_sqrt || !alpha || !d_rets || !d_covmat_sqrt || !d_alpha) { set_error("ddw_markowitz_bwd: null pointer"); return DDW_ERR_ARG; }
-    DDW_CHECK_ALIGNED("ddw_markowitz_bwd", grad_w, w, covmat_sqrt, gamma_sqrt, alpha, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace);
+    DDW_CHECK_ALIGNED("ddw_markowitz_bwd", grad_w, w, covmat_sqrt, gamma_sqrt, alpha, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, saved);
+    if (saved && saved_bytes < ddw_markowitz_saved_bytes(B, N, dtype)) { set_error("ddw_markowitz_bwd_saved: saved buffer too small"); return DDW_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64
-               ? markowitz_bwd_t<double>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st, batch_total, batch_offset, accumulate_gamma)
-               : markowitz_bwd_t<float>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st, batch_total, batch_offset, accumulate_gamma);
+               ? markowitz_bwd_t<double>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st, batch_total, batch_offset, accumulate_gamma, saved)
+               : markowitz_bwd_t<float>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st, batch_total, batch_offset, accumulate_gamma, saved);
+}
+
+int ddw_markowitz_bwd_chunk(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt,
+                            const void *gamma_sqrt, const void *alpha, double max_weight, int64_t B, int64_t N, int dtype,
+                            int64_t batch_total, int64_t batch_offset, void *d_rets, void *d_covmat_sqrt,
+                            void *d_gamma_sqrt, int accumulate_gamma, void *d_alpha, void *workspace,
+                            size_t workspace_bytes, void *stream) {
+    return markowitz_bwd_impl(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, N, dtype, batch_total, batch_offset,
+                              d_rets, d_covmat_sqrt, d_gamma_sqrt, accumulate_gamma, d_alpha, workspace, workspace_bytes, nullptr, 0,
+                              stream);
+}
+
+int ddw_markowitz_bwd_saved(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt,
+                            const void *gamma_sqrt, const void *alpha, double max_weight, int64_t B, int64_t N, int dtype,
+                            void *d_rets, void *d_covmat_sqrt, void *d_gamma_sqrt, void *d_alpha, void *workspace,
+                            size_t workspace_bytes, const void *saved, size_t saved_bytes, void *stream) {
+    if (!saved) { g_err[0] = 0; set_error("ddw_markowitz_bwd_saved: null saved buffer"); return DDW_ERR_ARG; }
+    return markowitz_bwd_impl(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, max_weight, B, N, dtype, B, 0, d_rets, d_covmat_sqrt,
+                              d_gamma_sqrt, 0, d_alpha, workspace, workspace_bytes, saved, saved_bytes, stream);
 }
 
 int ddw_markowitz_bwd(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt,

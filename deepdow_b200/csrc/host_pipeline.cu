@@ -23,10 +23,11 @@ namespace ddw {
 size_t markowitz_workspace_bytes(long long B, int N, int tsize);
 template <typename T>
 int markowitz_fwd_t(const void *, const void *, const void *, const void *, double, long long, int, void *, int8_t *,
-                    int32_t *, void *, size_t, cudaStream_t, long long, long long);
+                    int32_t *, void *, size_t, cudaStream_t, long long, long long, void * = nullptr);
 template <typename T>
 int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, const void *, const void *, long long,
-                    int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int);
+                    int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int,
+                    const void * = nullptr);
 
 constexpr int kMaxSlots = 8, kMaxRun = 4;
 // chunk slots in the device scratch / solver streams (consecutive chunks are solved concurrently: a chunk alone cannot

@@ -46,6 +46,10 @@ template <typename T> struct MkFwdParams {
     int *work_count;  // dense kernel in list mode: number of entries of work_list (nullptr: one CTA per problem)
     int *work_list;
     int *bad_count;   // number of portfolios left INFEASIBLE or INEXACT (what the host layer raises on)
+    // optional: the factor of the converged reduced KKT system, kept for the backward (ddw_markowitz_fwd_saved)
+    int *saved_n;            // per problem: number of free assets whose factor was saved, -1 = none
+    T *saved;                // Q in shared memory: packed columns + 1 / pivots, `saved_stride` elements per problem;
+    long long saved_stride;  // Q in the global workspace: the workspace itself (the kernel works in place in it)
 };
 
 template <typename T> struct MkBwdParams {
@@ -56,6 +60,12 @@ template <typename T> struct MkBwdParams {
     T *d_rets, *d_C, *d_alpha, *vecs;
     T *ws;  // global factor storage when it does not fit shared memory
     int *work_count, *work_list;   // sparse-support backward -> dense backward hand-over (nullptr: one CTA per problem)
+    // optional: factors saved by the forward (ddw_markowitz_bwd_saved); problems without one go to work_list2
+    const int *saved_n;
+    const T *saved;
+    long long saved_stride;
+    int LDF;                       // row stride of the forward's Q / factor array (global variant of `saved`)
+    int *work_count2, *work_list2;
 };
 
 template <typename T> __device__ __forceinline__ T sym_at(const T *Qs, int LD, int i, int j) {

@@ -4,5 +4,5 @@
 
 namespace ddw {
 template int markowitz_fwd_t<double>(const void *, const void *, const void *, const void *, double, long long, int,
-                                    void *, int8_t *, int32_t *, void *, size_t, cudaStream_t, long long, long long);
+                                    void *, int8_t *, int32_t *, void *, size_t, cudaStream_t, long long, long long, void *);
 }  // namespace ddw

@@ -69,6 +69,30 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> 
             if (!pdas_step<T, kThreads, NREG>(s, N, LD, p.u, dmin, tolw, lifted)) { converged = 1; break; }
         }
         const int nonfinite = write_result<T, kThreads>(s, N, p.u, w_out, st_out);
+        if (p.saved_n) {
+            // keep the factor of the converged reduced KKT system for the backward: the last active-set step factored exactly
+            // the final free set.  Not when a free weight landed on a bound (the reported state then differs from that set).
+            const int nF = s.misc[0];
+            int tie = 0;
+            for (int i = tid; i < N; i += kThreads)
+                if (s.st[i] == 0) { const T wi = s.wv[i]; tie |= (wi <= T(0)) || (wi >= p.u); }
+            tie = __syncthreads_or(tie);
+            const bool keep = converged && !nonfinite && !tie;
+            if (keep && nF > 0) {
+                const T *Lb = s.Qs + 1;
+                if (kGlobal) {
+                    for (int k = tid; k < nF; k += kThreads) s.Qs[(long long)k * LD + k] = s.dinv[k];   // Q is dead after convergence
+                } else {
+                    T *dst = p.saved + b * p.saved_stride;
+                    for (int cc = tid >> 5; cc < nF; cc += kThreads / 32) {
+                        const int off = cc * nF - cc * (cc - 1) / 2 - cc;        // column cc holds rows cc .. nF-1
+                        for (int a = cc + (tid & 31); a < nF; a += 32) dst[off + a] = Lb[cc * LD + a];
+                    }
+                    for (int k = tid; k < nF; k += kThreads) dst[nF * (nF + 1) / 2 + k] = s.dinv[k];
+                }
+            }
+            if (tid == 0) p.saved_n[b] = keep ? nF : -1;
+        }
         if (tid == 0) {
             int st = lifted ? DDW_STATUS_REGULARIZED : 0;
             if (nonfinite) { st |= DDW_STATUS_INEXACT; atomicAdd(p.bad_count, 1); }     // NaN / Inf in the inputs
@@ -618,6 +642,168 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_kernel(MkBwdParams<T> 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward from the factor the forward kept (ddw_markowitz_fwd_saved): no Gram, no factorisation -- two forward
+// substitutions (g_F and 1), the budget multiplier, one back substitution, then the same streaming tail as above
+// (A d, A w from covmat_sqrt, the rank-2 gradient).  kGlobal == false: the packed factor is unpacked into shared memory;
+// true: the factor is read in place from the forward's global Q / L array (row stride LDF, 1 / pivot on Q's diagonal).
+// Problems without a saved factor are appended to work_list2 for markowitz_bwd_kernel.
+// ------------------------------------------------------------------------------------------------
+static size_t mk_bwd_saved_smem_bytes(int N, int tsize, bool global_l) {
+    const int NP = round_up(N + 2, 32);
+    size_t elems = (global_l ? 0 : (size_t)round_up(N * (N | 1), 4)) + (size_t)6 * NP + 64;
+    return elems * tsize + ((size_t)NP + 8) * sizeof(int);
+}
+
+template <typename T, int kThreads, int NREG, bool kGlobal>
+__global__ void __launch_bounds__(kThreads) markowitz_bwd_saved_kernel(MkBwdParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (p.work_list && (long long)blockIdx.x >= (long long)*p.work_count) return;
+    const long long b = p.work_list ? (long long)p.work_list[blockIdx.x] : (long long)blockIdx.x;
+    const int N = p.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kThreads / 32;
+    const int nF = p.saved_n[b];
+    if (nF < 0) {
+        if (tid == 0) { const int sl = atomicAdd(p.work_count2, 1); p.work_list2[sl] = (int)b; }
+        return;
+    }
+    const int NP = round_up(N + 2, 32);
+    T *ptr = reinterpret_cast<T *>(smem_raw);
+    T *Lsm = ptr; ptr += kGlobal ? 0 : round_up(N * (N | 1), 4);
+    T *wv = ptr; ptr += NP;
+    T *dv = ptr; ptr += NP;
+    T *gv = ptr; ptr += NP;
+    T *qv = ptr; ptr += NP;
+    T *dinv = ptr; ptr += NP;
+    T *spare = ptr; ptr += NP;
+    T *red = ptr; ptr += 64;
+    int *idx = reinterpret_cast<int *>(ptr);
+    (void)spare;
+    if (warp == 0) {
+        int nf = 0;
+        for (int base = 0; base < N; base += 32) {
+            const int i = base + lane;
+            const int v = i < N ? (int)p.state[b * N + i] : 2;
+            const unsigned mf = __ballot_sync(kFullMask, v == 0);
+            if (v == 0) idx[nf + __popc(mf & ((1u << lane) - 1u))] = i;
+            nf += __popc(mf);
+        }
+    }
+    for (int i = tid; i < N; i += kThreads) { wv[i] = p.w[b * N + i]; gv[i] = p.grad_w[b * N + i]; dv[i] = T(0); }
+    const T *Lb;
+    int ldl;
+    if (kGlobal) {
+        const T *Qg = p.saved + b * p.saved_stride;
+        Lb = Qg + 1; ldl = p.LDF;
+        for (int k = tid; k < nF; k += kThreads) dinv[k] = Qg[(long long)k * p.LDF + k];
+    } else {
+        const T *src = p.saved + b * p.saved_stride;
+        ldl = nF | 1;
+        for (int cc = warp; cc < nF; cc += kWarps) {
+            const int off = cc * nF - cc * (cc - 1) / 2 - cc;
+            for (int a = cc + lane; a < nF; a += 32) Lsm[cc * ldl + a] = src[off + a];
+        }
+        for (int k = tid; k < nF; k += kThreads) dinv[k] = src[nF * (nF + 1) / 2 + k];
+        Lb = Lsm;
+    }
+    __syncthreads();
+    if (warp == 0 && nF > 0) {
+        T z1[NREG], z2[NREG];
+#pragma unroll
+        for (int m = 0; m < NREG; ++m) {
+            const int k = lane + 32 * m;
+            z1[m] = k < nF ? gv[idx[k]] : T(0);
+            z2[m] = k < nF ? T(1) : T(0);
+        }
+        fwdsub_warp<T, NREG>(Lb, ldl, nF, dinv, z1);
+        fwdsub_warp<T, NREG>(Lb, ldl, nF, dinv, z2);
+        T s12 = T(0), s22 = T(0);
+#pragma unroll
+        for (int m = 0; m < NREG; ++m) {
+            const int k = lane + 32 * m;
+            if (k < nF) { s12 = fma(z1[m] * z2[m], dinv[k], s12); s22 = fma(z2[m] * z2[m], dinv[k], s22); }
+        }
+        s12 = warp_sum(s12); s22 = warp_sum(s22);
+        const T eta = s12 / s22;
+#pragma unroll
+        for (int m = 0; m < NREG; ++m) z1[m] = T(0.5) * (z1[m] - eta * z2[m]);
+        backsub_warp<T, NREG>(Lb, ldl, nF, dinv, z1);
+#pragma unroll
+        for (int m = 0; m < NREG; ++m) {
+            const int k = lane + 32 * m;
+            if (k < nF) dv[idx[k]] = z1[m];
+        }
+    }
+    __syncthreads();
+    const T *Cb = p.C + b * (long long)N * N;
+    const long long gflat0 = (p.b0 + b) * (long long)N * N;
+    const T alpha = p.alpha[b];
+    const unsigned uB = (unsigned)p.Bmod;
+    T *pv = gv;   // p = A d overwrites grad_w now that d is known
+    T ldot = T(0);
+    for (int i = tid; i < N; i += kThreads) { p.d_rets[b * N + i] = dv[i]; ldot = fma(dv[i], wv[i], ldot); }
+    const T dot = block_sum<T, kThreads>(ldot, red);
+    if (tid == 0) p.d_alpha[b] = (alpha > T(0) ? T(1) : (alpha < T(0) ? T(-1) : T(0))) * (T(-2) * dot);
+    if (nF > 0) {
+        // p = A d, q = A w: one warp per row, coalesced reads of covmat_sqrt
+        unsigned grow = (unsigned)((gflat0 + (long long)warp * N + lane) % p.Bmod);
+        const unsigned growstep = (unsigned)(((long long)kWarps * N) % p.Bmod);
+        const unsigned gstep = (unsigned)(32 % p.Bmod);
+        for (int j = warp; j < N; j += kWarps) {
+            T sp = T(0), sq = T(0);
+            unsigned gi = grow;
+            grow += growstep; if (grow >= uB) grow -= uB;
+            for (int k = lane; k < N; k += 32) {
+                const T a = Cb[(long long)j * N + k] * p.gamma[gi];
+                sp = fma(a, dv[k], sp); sq = fma(a, wv[k], sq);
+                gi += gstep; if (gi >= uB) gi -= uB;
+            }
+            sp = warp_sum(sp); sq = warp_sum(sq);
+            if (lane == 0) { pv[j] = sp; qv[j] = sq; }
+        }
+    } else {
+        for (int j = tid; j < N; j += kThreads) { pv[j] = T(0); qv[j] = T(0); }
+    }
+    __syncthreads();
+    if (p.vecs) for (int i = tid; i < N; i += kThreads) { p.vecs[(b * 2) * N + i] = pv[i]; p.vecs[(b * 2 + 1) * N + i] = qv[i]; }
+    T *dC = p.d_C + b * (long long)N * N;
+    if ((N & 3) == 0) {
+        unsigned grow = (unsigned)((gflat0 + (long long)warp * N + 4 * lane) % p.Bmod);
+        const unsigned growstep = (unsigned)(((long long)kWarps * N) % p.Bmod);
+        const unsigned gstep = (unsigned)(128 % p.Bmod);
+        const bool gvec = (uB & 3u) == 0u;
+        for (int j = warp; j < N; j += kWarps) {
+            const T pj = T(-2) * pv[j], qj = T(-2) * qv[j];
+            unsigned gi = grow;
+            for (int k = 4 * lane; k < N; k += 128) {
+                const Vec4<T> w4 = ld4(wv + k), d4 = ld4(dv + k);
+                Vec4<T> o, g4;
+                if (gvec) g4 = ld4(p.gamma + gi);
+                else { unsigned g = gi;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { g4.v[q] = p.gamma[g]; if (++g >= uB) g = 0; } }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) o.v[q] = g4.v[q] * fma(pj, w4.v[q], qj * d4.v[q]);
+                st4(dC + (long long)j * N + k, o);
+                gi += gstep; if (gi >= uB) gi -= uB;
+            }
+            grow += growstep; if (grow >= uB) grow -= uB;
+        }
+    } else {
+        const int total = N * N;
+        int j = tid / N, k = tid - j * N;
+        const int dj = kThreads / N, dkk = kThreads % N;
+        unsigned gi = (unsigned)((gflat0 + tid) % p.Bmod);
+        const unsigned gstep = (unsigned)(kThreads % p.Bmod);
+        for (int e = tid; e < total; e += kThreads) {
+            dC[e] = p.gamma[gi] * T(-2) * fma(pv[j], wv[k], qv[j] * dv[k]);
+            k += dkk; j += dj;
+            if (k >= N) { k -= N; ++j; }
+            gi += gstep; if (gi >= uB) gi -= uB;
+        }
+    }
+}
+
 // d_gamma[m] += sum over the launch's elements with (flat % Bmod) == m of covmat_sqrt[flat] * dA[flat]
 // (backward of the tiling).  `flat` counts from the first problem of the whole batch; this launch holds the
 // `total` = B N^2 elements that start at flat = b0 N^2, so its local element f sits in bin (f + off) % Bmod with
@@ -709,7 +895,15 @@ constexpr int kIpmGrid = 296;
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 size_t markowitz_workspace_bytes(long long B, int N, int tsize);
+size_t markowitz_saved_bytes(long long B, int N, int tsize);
+static long long saved_stride_elems(int N, int tsize) {
+    const MkPlan pf = plan_fwd(N, tsize);
+    return pf.global_q ? (long long)N * pf.LD : (long long)round_up(N * (N + 1) / 2 + N, 4);
+}
 #ifdef DDW_MK_DEFINE_WORKSPACE
+size_t markowitz_saved_bytes(long long B, int N, int tsize) {
+    return align256(sizeof(int) * (size_t)B) + (size_t)B * (size_t)saved_stride_elems(N, tsize) * tsize;
+}
 size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
     const MkPlan pf = plan_fwd(N, tsize), pb = plan_bwd(N, tsize);
     const int NP = round_up(N + 2, 32);
@@ -781,7 +975,7 @@ static int launch_fwd_variant(MkFwdParams<T> p, const MkPlan &pl, T *ipm_ws, boo
 template <typename T>
 int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const void *alpha, double u, long long B,
                     int N, void *w, int8_t *state, int32_t *status, void *ws, size_t ws_bytes, cudaStream_t st,
-                    long long Bmod, long long b0) {
+                    long long Bmod, long long b0, void *saved) {
     if (ws_bytes < markowitz_workspace_bytes(B, N, sizeof(T)) || !ws) {
         set_error("ddw_markowitz_fwd: workspace too small (%zu < %zu)", ws_bytes, markowitz_workspace_bytes(B, N, sizeof(T)));
         return DDW_ERR_WORKSPACE;
@@ -795,6 +989,16 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
     p.w = (T *)w; p.state = state; p.status = status; p.ws = l.q;
     p.fail_count = l.fail_count; p.fail_list = l.fail_list;
     p.work_count = l.work_count; p.work_list = l.work_list; p.bad_count = l.bad_count;
+    p.saved_n = nullptr; p.saved = nullptr; p.saved_stride = 0;
+    if (saved) {
+        // keep the converged factors for ddw_markowitz_bwd_saved; with Q in the global workspace the solver works in place in
+        // the caller's `saved` buffer instead of the workspace
+        p.saved_n = reinterpret_cast<int *>(saved);
+        p.saved = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(saved) + align256(sizeof(int) * (size_t)B));
+        p.saved_stride = saved_stride_elems(N, sizeof(T));
+        cudaMemsetAsync(saved, 0xFF, sizeof(int) * (size_t)B, st);      // -1: no factor (sparse-support kernel, fallback)
+        if (pl.global_q) { p.ws = p.saved; l.q = p.saved; }
+    }
     // sparse-support kernel first whenever A (4 N^2 bytes) fits shared memory with room for >= 2 CTAs per SM
     const bool sparse_first = fwd_sparse_eligible(N, sizeof(T), smem_limit());
     if (!pl.global_q) {
@@ -836,10 +1040,26 @@ static int launch_bwd_variant(const MkBwdParams<T> &p, const MkPlan &pl, cudaStr
     return check_launch("markowitz_bwd_kernel");
 }
 
+template <typename T, int kThreads, int NREG, bool kGlobal>
+static int launch_bwd_saved_variant(const MkBwdParams<T> &p, cudaStream_t st) {
+    auto kb = markowitz_bwd_saved_kernel<T, kThreads, NREG, kGlobal>;
+    static DeviceOnce configured;
+    const int dev = current_device();
+    if (configured.needs(dev)) {
+        if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(markowitz_bwd_saved)");
+        configured.mark(dev);
+    }
+    const size_t smem = mk_bwd_saved_smem_bytes(p.N, sizeof(T), kGlobal);
+    if (smem > (size_t)smem_limit()) { set_error("ddw_markowitz_bwd_saved: n_assets=%d needs %zu B of shared memory", p.N, smem); return DDW_ERR_UNSUPPORTED; }
+    kb<<<(unsigned)p.B, kThreads, smem, st>>>(p);
+    return check_launch("markowitz_bwd_saved_kernel");
+}
+
 template <typename T>
 int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, const void *C, const void *gamma,
                     const void *alpha, long long B, int N, void *d_rets, void *d_C, void *d_gamma, void *d_alpha,
-                    void *ws, size_t ws_bytes, cudaStream_t st, long long Bmod, long long b0, int accumulate_gamma) {
+                    void *ws, size_t ws_bytes, cudaStream_t st, long long Bmod, long long b0, int accumulate_gamma, const void *saved) {
     if (ws_bytes < markowitz_workspace_bytes(B, N, sizeof(T)) || !ws) {
         set_error("ddw_markowitz_bwd: workspace too small (%zu < %zu)", ws_bytes, markowitz_workspace_bytes(B, N, sizeof(T)));
         return DDW_ERR_WORKSPACE;
@@ -854,10 +1074,29 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
     int rc;
     // sparse-support kernel first (A staged by TMA, free set <= kCandMax); it lists the portfolios it cannot take
     p.work_count = nullptr; p.work_list = nullptr;
+    p.saved_n = nullptr; p.saved = nullptr; p.saved_stride = 0; p.LDF = 0; p.work_count2 = nullptr; p.work_list2 = nullptr;
     if (!pl.global_q && pl.threads == 128 && bwd_sparse_eligible(N, sizeof(T), smem_limit())) {
         p.work_count = l.fail_count + 3; p.work_list = l.work_list;
         cudaMemsetAsync(p.work_count, 0, sizeof(int), st);
         if ((rc = launch_bwd_sparse<T>(p, st))) return rc;
+    }
+    const MkPlan pf = plan_fwd(N, sizeof(T));
+    if (saved && mk_bwd_saved_smem_bytes(N, sizeof(T), pf.global_q) <= (size_t)smem_limit()) {
+        // factors kept by the forward: substitutions only; what it cannot take (no factor saved) lands on the second list
+        p.saved_n = reinterpret_cast<const int *>(saved);
+        p.saved = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(saved) + align256(sizeof(int) * (size_t)B));
+        p.saved_stride = saved_stride_elems(N, sizeof(T));
+        p.LDF = pf.LD;
+        p.work_count2 = l.fail_count; p.work_list2 = l.fail_list;
+        cudaMemsetAsync(p.work_count2, 0, sizeof(int), st);
+        if (!pf.global_q && pl.threads == 128) rc = launch_bwd_saved_variant<T, 128, 4, false>(p, st);
+        else if (!pf.global_q) rc = launch_bwd_saved_variant<T, 256, 8, false>(p, st);
+        else if (pl.threads == 256) rc = launch_bwd_saved_variant<T, 256, 8, true>(p, st);
+        else if (pl.nreg == 16) rc = launch_bwd_saved_variant<T, 512, 16, true>(p, st);
+        else rc = launch_bwd_saved_variant<T, 512, 32, true>(p, st);
+        if (rc) return rc;
+        p.work_count = p.work_count2; p.work_list = p.work_list2;      // the generic kernel walks what is left
+        p.saved_n = nullptr;
     }
     if (!pl.global_q && pl.threads == 128) rc = launch_bwd_variant<T, 128, 4, false>(p, pl, st);
     else if (!pl.global_q && pl.threads == 256) rc = launch_bwd_variant<T, 256, 8, false>(p, pl, st);

@@ -90,10 +90,20 @@ class _MarkowitzFn(torch.autograd.Function):
         state = torch.empty((B, N), dtype=torch.int8, device=rets.device)
         status = torch.empty((B,), dtype=torch.int32, device=rets.device)
         ws = _workspace(_C.markowitz_workspace_bytes(B, N, dt), rets.device)
+        # when a backward will follow, the forward keeps the factor of every converged reduced KKT system (dense kernels) in
+        # `saved`, and the backward runs substitutions only (include/ddw.h: ddw_markowitz_fwd_saved / _bwd_saved)
+        saved = None
+        if any(ctx.needs_input_grad[:4]):
+            saved = _workspace(lib.ddw_markowitz_saved_bytes(B, N, dt), rets.device)
         with _C.device_guard(rets):
-            rc = lib.ddw_markowitz_fwd(_C.ptr(rets_c), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
-                                       float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status),
-                                       _C.ptr(ws), ws.numel(), _C.stream(rets.device))
+            if saved is None:
+                rc = lib.ddw_markowitz_fwd(_C.ptr(rets_c), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
+                                           float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status),
+                                           _C.ptr(ws), ws.numel(), _C.stream(rets.device))
+            else:
+                rc = lib.ddw_markowitz_fwd_saved(_C.ptr(rets_c), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
+                                                 float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status),
+                                                 _C.ptr(ws), ws.numel(), _C.ptr(saved), saved.numel(), _C.stream(rets.device))
         _C.check(rc, "ddw_markowitz_fwd")
         what = f"batch of {B}, n_assets={N}, max_weight={max_weight}"
         counter = ws[8:12].view(torch.int32)          # counter [2] of the workspace header (include/ddw.h)
@@ -105,14 +115,14 @@ class _MarkowitzFn(torch.autograd.Function):
         elif check_status == "lazy":
             with _C.device_guard(rets):              # the event is recorded on this tensor's device
                 watch.push(counter, what)
-        ctx.save_for_backward(w, state, cov_c, gam_c, alp_c)
+        ctx.save_for_backward(w, state, cov_c, gam_c, alp_c, saved)
         ctx.max_weight = float(max_weight)
         ctx.mark_non_differentiable(status)
         return w, status
 
     @staticmethod
     def backward(ctx, grad_w, _grad_status):
-        w, state, cov_c, gam_c, alp_c = ctx.saved_tensors
+        w, state, cov_c, gam_c, alp_c, saved = ctx.saved_tensors
         lib = _C.lib()
         B, N = w.shape
         dt = _C.dtype_code(w)
@@ -124,9 +134,15 @@ class _MarkowitzFn(torch.autograd.Function):
         d_gamma = torch.empty_like(gam_c) if need_gamma else None
         ws = _workspace(_C.markowitz_workspace_bytes(B, N, dt), w.device)
         with _C.device_guard(w):
-            rc = lib.ddw_markowitz_bwd(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
-                                       ctx.max_weight, B, N, dt, _C.ptr(d_rets), _C.ptr(d_cov), _C.ptr(d_gamma),
-                                       _C.ptr(d_alpha), _C.ptr(ws), ws.numel(), _C.stream(w.device))
+            if saved is None:
+                rc = lib.ddw_markowitz_bwd(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov_c), _C.ptr(gam_c), _C.ptr(alp_c),
+                                           ctx.max_weight, B, N, dt, _C.ptr(d_rets), _C.ptr(d_cov), _C.ptr(d_gamma),
+                                           _C.ptr(d_alpha), _C.ptr(ws), ws.numel(), _C.stream(w.device))
+            else:
+                rc = lib.ddw_markowitz_bwd_saved(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov_c), _C.ptr(gam_c),
+                                                 _C.ptr(alp_c), ctx.max_weight, B, N, dt, _C.ptr(d_rets), _C.ptr(d_cov),
+                                                 _C.ptr(d_gamma), _C.ptr(d_alpha), _C.ptr(ws), ws.numel(), _C.ptr(saved),
+                                                 saved.numel(), _C.stream(w.device))
         _C.check(rc, "ddw_markowitz_bwd")
         return d_rets, d_cov, d_gamma, d_alpha, None, None, None
 

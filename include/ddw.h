@@ -87,6 +87,22 @@ int ddw_markowitz_bwd(const void *grad_w, const void *w, const int8_t *state,
                       void *d_rets, void *d_covmat_sqrt, void *d_gamma_sqrt, void *d_alpha,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* Forward / backward pair that keeps the factor of each converged reduced KKT system between the two calls (what autograd
+ * does with saved tensors): the backward then runs substitutions only instead of forming Q_FF and factoring it again.
+ * `saved` is an opaque DEVICE buffer of ddw_markowitz_saved_bytes() bytes, written by the forward and read by the backward
+ * of the SAME batch; portfolios for which no factor was kept (small supports solved by the sparse-support kernel, interior
+ * point fallbacks) take the regular backward path.  Results are those of ddw_markowitz_fwd / ddw_markowitz_bwd. */
+size_t ddw_markowitz_saved_bytes(int64_t B, int64_t N, int dtype);
+int ddw_markowitz_fwd_saved(const void *rets, const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                            double max_weight, int64_t B, int64_t N, int dtype,
+                            void *w, int8_t *state, int32_t *status,
+                            void *workspace, size_t workspace_bytes, void *saved, size_t saved_bytes, void *stream);
+int ddw_markowitz_bwd_saved(const void *grad_w, const void *w, const int8_t *state,
+                            const void *covmat_sqrt, const void *gamma_sqrt, const void *alpha,
+                            double max_weight, int64_t B, int64_t N, int dtype,
+                            void *d_rets, void *d_covmat_sqrt, void *d_gamma_sqrt, void *d_alpha,
+                            void *workspace, size_t workspace_bytes, const void *saved, size_t saved_bytes, void *stream);
+
 /* Chunked launches of the two calls above: the same kernels on the `B` consecutive problems that start at
  * index `batch_offset` of a batch of `batch_total` problems.  Every pointer addresses the chunk's first
  * problem EXCEPT gamma_sqrt / d_gamma_sqrt, which address the whole batch's (batch_total) arrays: the

@@ -762,3 +762,48 @@ def test_risk_budgeting_reference_behaviour():
     # stationarity: sigma_i^2 w_i - b / w_i + nu = 0 with sum w = 1; compare against the oracle and the identity
     w_ref = oracle.risk_budgeting_fwd(torch.diag(sig)[None].cpu().numpy(), np.full((1, 4), 0.25), 1.0)[0]
     assert np.abs(w.cpu().numpy() - w_ref).max() < 1e-9
+
+
+# ------------------------------------------------------------------ backward from the factors the forward kept
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B,N,u,kind", [(64, 100, 0.2, "dense"), (64, 50, 1.0, "covsq"), (96, 100, 0.2, "sym"), (8, 150, 0.05, "dense"),
+                                        (4, 240, 0.05, "dense"), (3, 500, 0.01, "sym")])
+def test_markowitz_saved_factor_backward_equals_the_regular_one(dtype, B, N, u, kind):
+    """ddw_markowitz_fwd_saved / _bwd_saved (what the layer uses when a backward follows) against ddw_markowitz_fwd / _bwd
+    called directly through the C ABI: same weights bit for bit, gradients equal to rounding of a different elimination order."""
+    from deepdow_b200 import _C
+    lib = _C.lib()
+    rng = np.random.default_rng(B + N)
+    rets, C, g, a = make_problems(rng, B, N, kind, 1.0, 0.5, "rand")
+    G = rng.standard_normal((B, N))
+    tr, tC, tg, ta, tG = (t(x, dtype) for x in (rets, C, g, a, G))
+    dt = _C.dtype_code(tr)
+    outs = []
+    for use_saved in (False, True):
+        w = torch.empty_like(tr); st = torch.empty(B, N, dtype=torch.int8, device=DEV); status = torch.empty(B, dtype=torch.int32, device=DEV)
+        ws = torch.empty(lib.ddw_markowitz_workspace_bytes(B, N, dt), dtype=torch.uint8, device=DEV)
+        d_r, d_C, d_g, d_a = torch.empty_like(tr), torch.empty_like(tC), torch.empty_like(tg), torch.empty_like(ta)
+        if use_saved:
+            sv = torch.empty(lib.ddw_markowitz_saved_bytes(B, N, dt), dtype=torch.uint8, device=DEV)
+            rc = lib.ddw_markowitz_fwd_saved(_C.ptr(tr), _C.ptr(tC), _C.ptr(tg), _C.ptr(ta), u, B, N, dt, _C.ptr(w), _C.ptr(st), _C.ptr(status),
+                                             _C.ptr(ws), ws.numel(), _C.ptr(sv), sv.numel(), _C.stream())
+            assert rc == 0, lib.ddw_last_error()
+            kept = sv[:4 * B].view(torch.int32)
+            rc = lib.ddw_markowitz_bwd_saved(_C.ptr(tG), _C.ptr(w), _C.ptr(st), _C.ptr(tC), _C.ptr(tg), _C.ptr(ta), u, B, N, dt, _C.ptr(d_r),
+                                             _C.ptr(d_C), _C.ptr(d_g), _C.ptr(d_a), _C.ptr(ws), ws.numel(), _C.ptr(sv), sv.numel(), _C.stream())
+            assert rc == 0, lib.ddw_last_error()
+            if kind in ("dense", "covsq") or N > 128:
+                assert int((kept >= 0).sum()) > 0          # the dense kernels did keep factors
+        else:
+            rc = lib.ddw_markowitz_fwd(_C.ptr(tr), _C.ptr(tC), _C.ptr(tg), _C.ptr(ta), u, B, N, dt, _C.ptr(w), _C.ptr(st), _C.ptr(status),
+                                       _C.ptr(ws), ws.numel(), _C.stream())
+            assert rc == 0, lib.ddw_last_error()
+            rc = lib.ddw_markowitz_bwd(_C.ptr(tG), _C.ptr(w), _C.ptr(st), _C.ptr(tC), _C.ptr(tg), _C.ptr(ta), u, B, N, dt, _C.ptr(d_r),
+                                       _C.ptr(d_C), _C.ptr(d_g), _C.ptr(d_a), _C.ptr(ws), ws.numel(), _C.stream())
+            assert rc == 0, lib.ddw_last_error()
+        torch.cuda.synchronize()
+        outs.append((w, st, d_r, d_C, d_g, d_a))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    tol = 2e-4 if dtype == torch.float32 else 1e-9
+    for name, x, y in zip(["rets", "covmat_sqrt", "gamma", "alpha"], outs[0][2:], outs[1][2:]):
+        assert rel_err(y, x.double().cpu().numpy()) < tol, (name, rel_err(y, x.double().cpu().numpy()))

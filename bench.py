@@ -13,6 +13,15 @@ same through the layer API from pinned host buffers (H2D of every input and D2H 
 inside the timed region).  `roofline` is for the dominant kernel (the forward solver) against the
 measured HBM peak; `cpu_baseline` is the float64 oracle port on the host cores.
 
+Extra keys of the line (all measured in the same run, on the same GPUs):
+  f64            the same step in float64 (the reference solves in float64 internally)
+  dense_regime   the same matrices with expected returns scaled down 25x (~86 of 100 assets free: the regime the networks
+                 train in), CUDA-graph replays, with its own roofline fraction
+  strong_scaling the SAME global batch of 4096 problems split over the N ranks (value = 4096 K / max-over-ranks time)
+  bachelier_train  BASELINE config 2: BachelierNet training steps (256 samples per GPU, n_assets=50, lookback=40,
+                 horizon=10, SharpeRatio loss, Adam) with the NCCL all-reduce of the parameter gradients INSIDE the
+                 timed region (north_star: "near-linear 1->8 GPU scaling of BachelierNet training throughput")
+
 `--impl reference` times the reference arm: the reference's cvxpylayers/SCS path is not installable
 here, so it is the CPU oracle port (oracle/ddw_oracle.c, OpenMP, all host
 threads) on a bounded sample of the same workload.
@@ -258,6 +267,7 @@ def main():
     # kernels + 3 memsets, and at ~0.6 ms per step the Python side (autograd engine, ctypes, allocator: ~0.3 ms)
     # is of the same order as the kernels.  `value` is the replayed step; the eager loop is reported beside it.
     graph_ms, fwd_graph_ms, graph_note = None, None, "eager launches (graph capture unavailable)"
+    rounds, timed_region_s = 1, None
     try:
         layer.check_status = False              # the status copy to pinned memory + event is not capturable
         side = torch.cuda.Stream()
@@ -278,7 +288,26 @@ def main():
             graph.replay()
         g1.record()
         barrier()
-        graph_ms = g0.elapsed_time(g1)
+        pilot_ms = g0.elapsed_time(g1)
+        # `value` = median over ROUNDS of exactly `steps` replays each; enough rounds that the timed region lasts >= 1 s, so
+        # that the 200 ms clock sampler sees it (every rank runs the same number of rounds)
+        pil = torch.tensor([pilot_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(pil, op=dist.ReduceOp.MAX)
+        rounds = int(min(400, max(3, -(-1000.0 // max(float(pil), 1e-3)))))
+        rev = [torch.cuda.Event(enable_timing=True) for _ in range(rounds + 1)]
+        barrier()
+        rev[0].record()
+        for r in range(rounds):
+            for _ in range(args.steps):
+                graph.replay()
+            rev[r + 1].record()
+        barrier()
+        round_ms = torch.tensor([rev[r].elapsed_time(rev[r + 1]) for r in range(rounds)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(round_ms, op=dist.ReduceOp.MAX)      # every round: the slowest rank
+        graph_ms = float(round_ms.median())
+        timed_region_s = float(round_ms.sum()) * 1e-3
         # forward alone, replayed the same way: the per-kernel times behind `roofline` must not contain host gaps
         detached_g = [t.detach() for t in inputs]
         with torch.cuda.stream(side), torch.no_grad():
@@ -321,32 +350,133 @@ def main():
     barrier()
     fwd_only_ms = f0.elapsed_time(f1)
 
-    # side measurement (rank-local, not part of `value`): the same matrices with expected returns scaled down 25x, so that
-    # ~86 of the 100 assets end up free -- the diversified regime BachelierNet / ThorpNet train in, which runs through the
-    # dense kernels (profiles/r01_final/dense_regime.txt)
+    # ---- side measurements (not part of `value`): CUDA-graph replays of the layer's fwd+bwd step on other inputs ---------
+    def graph_step_ms(ins, upstream, fwd_only=False, steps=None):
+        """ms per step (max over ranks) of `steps` replays of one captured fwd (+ bwd) step of a fresh layer on `ins`."""
+        steps = steps or args.steps
+        lay = NumericalMarkowitz(ins[0].shape[1], max_weight=u)
+        lay.check_status = False
+
+        def one():
+            if fwd_only:
+                with torch.no_grad():
+                    return lay(*[t.detach() for t in ins]), None
+            wq = lay(*ins)
+            return wq, torch.autograd.grad(wq, ins, upstream)
+
+        sd = torch.cuda.Stream()
+        sd.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(sd):
+            for _ in range(3):
+                one()
+        torch.cuda.current_stream().wait_stream(sd)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            wq, _ = one()
+        for _ in range(3):
+            gr.replay()
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(steps):
+            gr.replay()
+        q1.record()
+        barrier()
+        ms = torch.tensor([q0.elapsed_time(q1) / steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        assert int((lay.last_status & 12).ne(0).sum()) == 0
+        return float(ms), wq
+
+    # (1) the diversified regime: the same matrices with expected returns scaled down 25x, so that ~86 of the 100 assets end
+    #     up free -- what BachelierNet / ThorpNet train in; it runs through the dense kernels
     dense_info = None
     try:
         d_in = [(rets.detach() * 0.04).requires_grad_()] + [t.detach().clone().requires_grad_() for t in (C, gam, alp)]
-        d0, d1, d2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        n_dense = 5
-        for _ in range(2):
-            torch.autograd.grad(layer(*d_in), d_in, G)
-        with torch.no_grad():
-            d0.record()
-            for _ in range(n_dense):
-                wd = layer(*d_in)
-            d1.record()
-        for _ in range(n_dense):
-            torch.autograd.grad(layer(*d_in), d_in, G)
-        d2.record()
-        torch.cuda.synchronize()
-        dense_info = {"workload": "same covmat_sqrt, rets~N(0,0.02^2): diversified optimum",
+        d_fb, wd = graph_step_ms(d_in, G)
+        d_f, _ = graph_step_ms(d_in, G, fwd_only=True)
+        dense_info = {"workload": "same covmat_sqrt, rets~N(0,0.02^2): diversified optimum, CUDA-graph replays",
                       "mean_free": float(((wd > 0) & (wd < u)).sum(1).float().mean()),
-                      "fwd_only": {"value": B * n_dense / (d0.elapsed_time(d1) * 1e-3), "unit": UNIT + " per GPU"},
-                      "fwd_bwd": {"value": B * n_dense / (d1.elapsed_time(d2) * 1e-3), "unit": UNIT + " per GPU"}}
+                      "fwd_only": {"value": world * B / (d_f * 1e-3), "unit": UNIT, "ms_per_step": d_f},
+                      "fwd_bwd": {"value": world * B / (d_fb * 1e-3), "unit": UNIT, "ms_per_step": d_fb}}
         del d_in, wd
-    except Exception as exc:                      # never let the side measurement take the bench line down
+    except Exception as exc:                      # never let a side measurement take the bench line down
         dense_info = {"error": f"{type(exc).__name__}: {exc}"}
+    barrier()
+    # (2) float64: the reference solves in float64 internally; the same kernels instantiated for double
+    f64_info = None
+    try:
+        i64 = [t.detach().double().requires_grad_() for t in (rets, C, gam, alp)]
+        ms64, w64 = graph_step_ms(i64, G.double(), steps=max(3, args.steps // 4))
+        f64_info = {"value": world * B / (ms64 * 1e-3), "unit": UNIT, "ms_per_step": ms64,
+                    "max_abs_diff_vs_f32": float((w64.float() - w_g).abs().max()) if graph_ms is not None else None}
+        del i64, w64
+    except Exception as exc:
+        f64_info = {"error": f"{type(exc).__name__}: {exc}"}
+    barrier()
+    # (3) strong scaling: ONE global batch of 4096 problems (rank 0's) split over the ranks
+    strong_info = None
+    try:
+        if world > 1:
+            gl = [t.detach().clone() for t in (rets, C, gam, alp, G)]
+            for t in gl:
+                dist.broadcast(t, src=0)
+            from deepdow_b200.distributed import shard_bounds
+            lo, hi = shard_bounds(B, rank, world)
+            # the gamma tiling indexes the whole batch: constant gamma here, so the shard is self-contained
+            si = [t[lo:hi].contiguous().requires_grad_() for t in gl[:4]]
+            sms, _ = graph_step_ms(si, gl[4][lo:hi].contiguous())
+            del gl, si
+        else:
+            sms = graph_ms / args.steps if graph_ms is not None else None
+        strong_info = {"value": B / (sms * 1e-3) if sms else None, "unit": UNIT, "ms_per_step": sms, "global_batch": B,
+                       "per_rank": (B + world - 1) // world, "scaling": "strong"}
+    except Exception as exc:
+        strong_info = {"error": f"{type(exc).__name__}: {exc}"}
+    barrier()
+    # (4) BachelierNet training (BASELINE config 2), NCCL all-reduce of the parameter gradients inside the timed region
+    bach_info = None
+    try:
+        from deepdow_b200 import nn as dnn
+        from deepdow_b200.distributed import GradAllReducer
+        torch.manual_seed(0)                                      # identical initial parameters on every rank
+        net = dnn.BachelierNet(1, 50, hidden_size=32, max_weight=1, shrinkage_strategy="diagonal", p=0.5).to(dev)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+        reduce_grads = GradAllReducer(net.parameters())
+        bgen = torch.Generator(device=dev).manual_seed(2000 + rank)
+        Xb = torch.randn(256, 1, 40, 50, generator=bgen, device=dev) * 0.01
+        yb = torch.randn(256, 1, 10, 50, generator=bgen, device=dev) * 0.01
+
+        def train_step():
+            loss = dnn.sharpe_ratio_loss(net(Xb), yb).mean()
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            reduce_grads()
+            opt.step()
+            return loss
+
+        for _ in range(5):
+            train_step()
+        barrier()
+        n_train = max(10, min(50, args.steps))
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(n_train):
+            loss_b = train_step()
+        b1.record()
+        barrier()
+        bms = torch.tensor([b0.elapsed_time(b1) / n_train], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(bms, op=dist.ReduceOp.MAX)
+        net.portfolio_opt_layer.synchronize_status()
+        bach_info = {"value": world * 256 / (float(bms) * 1e-3), "unit": "samples/s", "ms_per_step": float(bms), "steps": n_train,
+                     "scaling": "weak", "collective": "NCCL all-reduce of 3524 parameter gradients (one flat bucket) per step, inside "
+                                                      "the timed region" if world > 1 else "none (1 GPU)",
+                     "config": "BachelierNet(1, 50, hidden 32), batch 256 per GPU, lookback 40, horizon 10, SharpeRatio, Adam lr 1e-2",
+                     "final_loss": float(loss_b.detach())}
+        del net, opt, Xb, yb
+    except Exception as exc:
+        bach_info = {"error": f"{type(exc).__name__}: {exc}"}
     barrier()
 
     # ---- timed region 2: end to end from pinned host buffers -----------------------------------
@@ -425,7 +555,14 @@ def main():
             fwd_ms, bwd_ms = fwd_graph_ms, graph_max / args.steps - fwd_graph_ms
         dom_fwd = fwd_ms >= bwd_ms
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_final", "ncu_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02", "ncu_traffic.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r01_final", "ncu_traffic.json")
+        if isinstance(dense_info, dict) and "fwd_bwd" in dense_info:
+            # roofline of the diversified regime: algorithmic bytes of fwd + bwd over the step time (122 016 B / solve)
+            for key, nbytes in (("fwd_only", fwd_bytes), ("fwd_bwd", fwd_bytes + bwd_bytes)):
+                gbs = nbytes / (dense_info[key]["ms_per_step"] * 1e-3) / 1e9
+                dense_info[key]["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak}
         if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
             tj = json.load(open(tpath))
             tk = tj["markowitz_fwd_sparse_kernel" if dom_fwd else "markowitz_bwd_sparse_kernel"]
@@ -439,7 +576,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world} (independent problems, no collective)",
                        "l2": "inputs (164 MB covmat_sqrt) + gradients (164 MB) per step exceed the 126 MB L2",
-                       "status_check": args.status_mode, "launch": graph_note,
+                       "status_check": ("off inside the timed graph replays (the status copy to pinned memory is not capturable); "
+                                        f"'{args.status_mode}' in the eager and end-to-end measurements") if graph_ms is not None
+                       else args.status_mode,
+                       "launch": graph_note, "rounds": rounds, "timed_region_s": timed_region_s,
                        "active_set": {"mean_free": nfree, "mean_at_cap": ncap, "fallback_problems": nfallback,
                                       "dense_kernel_problems": ndense}},
             "e2e": {"value": world * B * steps_total / (e2e_ms * 1e-3), "unit": UNIT,
@@ -451,12 +591,16 @@ def main():
                                               "ms_per_step": e2e_layer_ms / steps_total}},
             "eager": {"value": world * B * steps_total / (eager_ms * 1e-3), "unit": UNIT, "ms_per_step": eager_ms / steps_total,
                       "note": "same step launched from Python every time (autograd Function + ctypes)"},
-            "gpu_launches": 6 * steps_total,
+            "gpu_launches": 7 * steps_total * rounds,
             "kernels_per_step": ["markowitz_fwd_sparse_kernel", "markowitz_fwd_kernel (dense work list)",
                                  "markowitz_ipm_kernel (fallback list, empty here)", "markowitz_bwd_sparse_kernel",
-                                 "markowitz_bwd_kernel (dense work list)", "markowitz_gamma_kernel"],
+                                 "markowitz_bwd_saved_kernel (factors kept by the dense forward)",
+                                 "markowitz_bwd_kernel (what is left)", "markowitz_gamma_kernel"],
             "fwd_only": {"value": world * B * steps_total / (fwd_only_ms * 1e-3), "unit": UNIT},
             "dense_regime": dense_info,
+            "f64": f64_info,
+            "strong_scaling": strong_info,
+            "bachelier_train": bach_info,
             "phase_ms": {"fwd": fwd_ms, "bwd": bwd_ms, "host_enqueue": cpu_enqueue_ms,
                          "source": "CUDA-graph replays (forward alone; step minus forward)" if graph_ms is not None
                          else "CUDA events around the eager layer calls"},

@@ -248,6 +248,26 @@ class NumericalMarkowitz(nn.Module):
         """Block until every outstanding solve has reported; raise SolverError if any failed."""
         self._watch.poll(block=True)
 
+    def train(self, mode=True):
+        """``model.train()`` / ``model.eval()`` are the natural synchronisation points of a training loop (deepdow's
+        ``Run.launch`` validates after every epoch, callbacks.py:807-836): in the lazy mode the outstanding status reads are
+        flushed here, so a solve that failed in the LAST batch of an epoch raises ``SolverError`` at the switch instead of
+        going unreported."""
+        if self.check_status == "lazy" and self._watch is not None and self._watch.pending:
+            self._watch.poll(block=True)
+        return super().train(mode)
+
+    def __del__(self):
+        watch = self.__dict__.get("_watch")
+        if watch is not None and watch.pending:
+            try:
+                watch.poll(block=True)
+            except SolverError as exc:      # cannot raise from a finaliser: make the loss of the report visible at least
+                import warnings
+                warnings.warn(f"NumericalMarkowitz discarded with an unreported solver failure: {exc}")
+            except Exception:               # interpreter shutdown: CUDA may already be gone
+                pass
+
     def extra_repr(self):
         return f"n_assets={self.n_assets}, max_weight={self.max_weight}"
 

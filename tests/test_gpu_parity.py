@@ -807,3 +807,55 @@ def test_markowitz_saved_factor_backward_equals_the_regular_one(dtype, B, N, u, 
     tol = 2e-4 if dtype == torch.float32 else 1e-9
     for name, x, y in zip(["rets", "covmat_sqrt", "gamma", "alpha"], outs[0][2:], outs[1][2:]):
         assert rel_err(y, x.double().cpu().numpy()) < tol, (name, rel_err(y, x.double().cpu().numpy()))
+
+
+# ------------------------------------------------------------------ robustness
+def test_markowitz_failure_in_the_last_batch_is_reported():
+    """Lazy status + a Run.launch-style loop (experiments.py:322-390): the batch with a non-finite input is the LAST one of
+    the epoch, nothing calls the layer again -- the switch to eval() (validation, callbacks.py:814) must raise SolverError.
+    With check_status=True the failing call itself raises."""
+    rng = np.random.default_rng(8)
+    rets, C, g, a = make_problems(rng, 16, 12)
+    good = [t(x, torch.float32) for x in (rets, C, g, a)]
+    bad_rets = rets.copy(); bad_rets[3, 5] = np.nan
+    layer = NumericalMarkowitz(12, 0.5)
+    assert layer.check_status == "lazy"
+    for _ in range(3):
+        layer(*good)
+    w = layer(t(bad_rets, torch.float32), *good[1:])             # last batch of the "epoch"
+    with pytest.raises(SolverError):
+        layer.eval()
+    layer.train()                                                # the report was consumed: the next epoch starts clean
+    layer(*good); layer.synchronize_status()
+    strict = NumericalMarkowitz(12, 0.5); strict.check_status = True
+    with pytest.raises(SolverError):
+        strict(t(bad_rets, torch.float32), *good[1:])
+    bad_C = C.copy(); bad_C[2, 1, 1] = np.inf
+    with pytest.raises(SolverError):
+        strict(good[0], t(bad_C, torch.float32), *good[2:])
+    assert int((strict.last_status & 4).ne(0).sum()) >= 1
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_layers_on_a_second_gpu_in_the_same_process():
+    """The > 48 KB shared-memory opt-in belongs to a device: every layer must work on cuda:1 after cuda:0 in one process."""
+    from deepdow_b200 import NumericalRiskBudgeting
+    rng = np.random.default_rng(9)
+    rets, C, g, a = make_problems(rng, 8, 100)
+    x = rng.standard_normal((4, 40, 50)) * 0.01
+    xl = rng.standard_normal((2, 40, 200)) * 0.01
+    outs = []
+    for d in ("cuda:0", "cuda:1"):
+        ins = [torch.tensor(v, dtype=torch.float32, device=d, requires_grad=True) for v in (rets, C, g, a)]
+        w = NumericalMarkowitz(100, 0.2)(*ins)
+        grads = torch.autograd.grad(w, ins, torch.ones_like(w))
+        dense = NumericalMarkowitz(100, 0.2)(ins[0].detach() * 0.04, *[v.detach() for v in ins[1:]])
+        cov = CovarianceMatrix(sqrt=True)(torch.tensor(x, dtype=torch.float32, device=d))
+        covp = CovarianceMatrix(sqrt=False)(torch.tensor(x, dtype=torch.float32, device=d))
+        covl = CovarianceMatrix(sqrt=True)(torch.tensor(xl, dtype=torch.float32, device=d))
+        sm = SparsemaxAllocator(100, 1.0, 0.05)(ins[0].detach())
+        b = torch.full((8, 100), 0.01, device=d)
+        rb = NumericalRiskBudgeting(100)(ins[1].detach(), b)
+        outs.append([v.cpu() for v in (w.detach(), grads[1], dense, cov, covp, covl, sm, rb)])
+    for x0, x1 in zip(*outs):
+        assert torch.equal(x0, x1)

@@ -32,6 +32,8 @@ SIGNATURES = {
     "ddw_markowitz_fwd_saved": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "ddw_markowitz_bwd_saved": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
                                        _vp]),
+    "ddw_covariance_markowitz_fwd": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
+                                            _vp]),
     "ddw_markowitz_fwd_chunk": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddw_markowitz_bwd_chunk": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _i32,
                                        _vp, _vp, _sz, _vp]),

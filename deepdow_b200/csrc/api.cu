@@ -37,6 +37,9 @@ int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, co
 template <typename T>
 int row_op_t(int, const void *, const void *, double, double, long long, int, const void *, const void *, void *,
              void *, void *, cudaStream_t);
+template <typename T>
+int markowitz_fused_fwd_t(const void *, const void *, int, int, const void *, const void *, const void *, double, long long, int,
+                          void *, int8_t *, int32_t *, void *, size_t, cudaStream_t, void *);
 size_t risk_budgeting_workspace_bytes(long long B, int N, int tsize);      // risk_budgeting.cu
 template <typename T>
 int risk_budgeting_t(bool, const void *, const void *, const void *, const void *, const int8_t *, double, long long, int, void *,
@@ -183,6 +186,25 @@ static int row_call(const char *fn, int which, const void *x, const void *temper
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64 ? row_op_t<double>(which, x, temperature, tscalar, u, B, (int)N, grad_w, w, out, d_x, d_t, st)
                             : row_op_t<float>(which, x, temperature, tscalar, u, B, (int)N, grad_w, w, out, d_x, d_t, st);
+}
+
+int ddw_covariance_markowitz_fwd(const void *x, const void *coef, int strategy, int64_t L, const void *rets,
+                                 const void *gamma_sqrt, const void *alpha, double max_weight, int64_t B, int64_t N, int dtype,
+                                 void *w, int8_t *state, int32_t *status, void *workspace, size_t workspace_bytes,
+                                 void *saved, size_t saved_bytes, void *stream) {
+    g_err[0] = 0;
+    int rc = check_dims("ddw_covariance_markowitz_fwd", B, N, 1024, dtype);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (L < 2 || L >= (1LL << 24)) { set_error("ddw_covariance_markowitz_fwd: need 2 <= dim < 2^24 observations, got %lld", (long long)L); return DDW_ERR_ARG; }
+    if (strategy < DDW_SHRINK_NONE || strategy > DDW_SHRINK_SCALED_IDENTITY) { set_error("ddw_covariance_markowitz_fwd: bad strategy %d", strategy); return DDW_ERR_ARG; }
+    if (!x || !rets || !gamma_sqrt || !alpha || !w || !state || !status || (strategy != DDW_SHRINK_NONE && !coef)) { set_error("ddw_covariance_markowitz_fwd: null pointer"); return DDW_ERR_ARG; }
+    DDW_CHECK_ALIGNED("ddw_covariance_markowitz_fwd", x, rets, gamma_sqrt, alpha, w, workspace, saved);
+    if (saved && saved_bytes < ddw_markowitz_saved_bytes(B, N, dtype)) { set_error("ddw_covariance_markowitz_fwd: saved buffer too small"); return DDW_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DDW_F64
+               ? markowitz_fused_fwd_t<double>(x, coef, strategy, (int)L, rets, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, saved)
+               : markowitz_fused_fwd_t<float>(x, coef, strategy, (int)L, rets, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, saved);
 }
 
 size_t ddw_risk_budgeting_workspace_bytes(int64_t B, int64_t N, int dtype) {

@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "linalg.cuh"
+#include "cov_tile.cuh"
 
 namespace ddw {
 
@@ -50,6 +51,10 @@ template <typename T> struct MkFwdParams {
     int *saved_n;            // per problem: number of free assets whose factor was saved, -1 = none
     T *saved;                // Q in shared memory: packed columns + 1 / pivots, `saved_stride` elements per problem;
     long long saved_stride;  // Q in the global workspace: the workspace itself (the kernel works in place in it)
+    // fused covariance -> solver (ddw_covariance_markowitz_fwd): covmat_sqrt is not read from HBM but formed in shared memory
+    // from the (L, N) lookback tile as CovarianceMatrix(sqrt=False) would (BachelierNet, nn.py:170-171,189-191)
+    const T *X, *coef;
+    int L, strategy;
 };
 
 template <typename T> struct MkBwdParams {
@@ -100,7 +105,7 @@ __device__ __forceinline__ MkSmem<T> carve(unsigned char *raw, int N, int LD, in
     return s;
 }
 
-static size_t mk_smem_bytes(int N, int LD, int AS, int CH, int tsize, bool global_q) {
+__host__ __device__ static inline size_t mk_smem_bytes(int N, int LD, int AS, int CH, int tsize, bool global_q) {
     const int NP = round_up(N + 2, 32);
     size_t elems = (global_q ? 0 : (size_t)round_up(N * LD, 4)) + (size_t)2 * CH * AS + (size_t)4 * NP + 64;
     return elems * tsize + ((size_t)2 * NP + 8) * sizeof(int) + (size_t)NP;

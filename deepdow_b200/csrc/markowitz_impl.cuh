@@ -33,7 +33,9 @@ int markowitz_gram_tc(const float *C, const float *gamma, const float *alpha, lo
 // Dense forward kernel.  Direct mode (work_list == nullptr): one CTA per portfolio, grid = B.
 // List mode: a fixed grid walks the portfolios that the sparse kernel handed over.
 // MAXT > 0: Gram tiles in registers; 0: Gram through the shared staging area; < 0: Q was formed by markowitz_gram_tc.
-template <typename T, int kThreads, int NREG, bool kGlobal, int MAXT>
+// kFused: covmat_sqrt = CovarianceMatrix(sqrt=False)(X) is formed in shared memory from the (L, N) lookback tile (cov_tile.cuh,
+// the code of covariance_plain_kernel: same bits) instead of being read from HBM; direct mode only, 128 threads.
+template <typename T, int kThreads, int NREG, bool kGlobal, int MAXT, bool kFused = false>
 __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.N, LD = p.LD, tid = threadIdx.x;
@@ -47,12 +49,27 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> 
         __syncthreads();   // list mode: the previous portfolio's shared state is dead from here on
         for (int i = tid; i < N; i += kThreads) s.r[i] = p.rets[b * N + i];
         const T aabs = absT(p.alpha[b]);
+        const T *Cb = p.C + b * (long long)N * N;
+        if (kFused) {
+            // the covariance tile lives behind the solver's own shared memory
+            const int XS = round_up(N, 4), L = p.L;
+            T *X = reinterpret_cast<T *>(smem_raw + round_up((int)mk_smem_bytes(N, LD, p.AS, p.CH, sizeof(T), false), 16));
+            T *Xc = X + round_up(L * N, 4);
+            T *S = Xc + L * XS;
+            T *part = S + round_up(N * N, 4);
+            T *red2 = part + kPlainParts * XS;
+            const T *xb = p.X + b * (long long)L * N;
+            for (int e = tid; e < L * N; e += kThreads) X[e] = xb[e];
+            __syncthreads();
+            cov_plain_tile<T>(X, Xc, S, part, red2, L, N, XS, p.strategy, p.strategy == DDW_SHRINK_NONE ? T(1) : p.coef[b]);
+            Cb = S;
+        }
         if (MAXT > 0)
-            gram_lower_reg<T, kThreads, (MAXT > 0 ? MAXT : 1), false>(p.C + b * (long long)N * N, p.gamma,
+            gram_lower_reg<T, kThreads, (MAXT > 0 ? MAXT : 1), false>(Cb, p.gamma,
                                                                        (p.b0 + b) * (long long)N * N, p.Bmod, N, N, nullptr, nullptr,
                                                                        N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
         else if (MAXT == 0)
-            gram_lower<T, kThreads, false>(p.C + b * (long long)N * N, p.gamma, (p.b0 + b) * (long long)N * N, p.Bmod, N, N,
+            gram_lower<T, kThreads, false>(Cb, p.gamma, (p.b0 + b) * (long long)N * N, p.Bmod, N, N,
                                            nullptr, nullptr, N, s.As, p.AS, p.CH, s.Qs, LD, aabs);
         else
             __syncthreads();          // rets staged; Q already sits in the global workspace
@@ -98,8 +115,11 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> 
             if (nonfinite) { st |= DDW_STATUS_INEXACT; atomicAdd(p.bad_count, 1); }     // NaN / Inf in the inputs
             else if (!converged) {
                 st |= DDW_STATUS_FALLBACK | DDW_STATUS_INEXACT;
-                const int slot = atomicAdd(p.fail_count, 1);
-                p.fail_list[slot] = (int)b;
+                if (kFused) atomicAdd(p.bad_count, 1);      // no covmat_sqrt in HBM for the fallback kernel: the host layer re-runs unfused
+                else {
+                    const int slot = atomicAdd(p.fail_count, 1);
+                    p.fail_list[slot] = (int)b;
+                }
             }
             p.status[b] = st;
         }
@@ -1024,6 +1044,64 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
     if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, true, 0>(p, pl, l.ipm, false, st);
     if (pl.nreg == 16) return launch_fwd_variant<T, 512, 16, true, 0>(p, pl, l.ipm, false, st);
     return launch_fwd_variant<T, 512, 32, true, 0>(p, pl, l.ipm, false, st);
+}
+
+// ---- fused covariance -> NumericalMarkowitz forward ----------------------------------------
+size_t markowitz_fused_smem_bytes(int N, int L, int tsize);
+#ifdef DDW_MK_DEFINE_WORKSPACE
+size_t markowitz_fused_smem_bytes(int N, int L, int tsize) {
+    const MkPlan pl = plan_fwd(N, tsize);
+    return (size_t)round_up((int)pl.smem, 16) + cov_tile_elems(L, N) * tsize;
+}
+#endif
+
+template <typename T, int MAXT>
+static int launch_fwd_fused(const MkFwdParams<T> &p, size_t smem, cudaStream_t st) {
+    auto kf = markowitz_fwd_kernel<T, 128, 4, false, MAXT, true>;
+    static DeviceOnce configured;
+    const int dev = current_device();
+    if (configured.needs(dev)) {
+        if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(markowitz_fwd fused)");
+        configured.mark(dev);
+    }
+    cudaMemsetAsync(p.fail_count, 0, 4 * sizeof(int), st);
+    kf<<<(unsigned)p.B, 128, smem, st>>>(p);
+    return check_launch("markowitz_fwd_kernel (fused covariance)");
+}
+
+// x (B, L, N) observations -> covariance (sqrt = False, `strategy`, coef) -> NumericalMarkowitz.  DDW_ERR_UNSUPPORTED when the
+// tile does not fit next to the solver (n_assets > 128, long lookbacks): the caller composes the two layers instead.
+template <typename T>
+int markowitz_fused_fwd_t(const void *x, const void *coef, int strategy, int L, const void *rets, const void *gamma,
+                          const void *alpha, double u, long long B, int N, void *w, int8_t *state, int32_t *status, void *ws,
+                          size_t ws_bytes, cudaStream_t st, void *saved) {
+    const MkPlan pl = plan_fwd(N, sizeof(T));
+    const size_t smem = markowitz_fused_smem_bytes(N, L, sizeof(T));
+    if (pl.global_q || pl.threads != 128 || smem > (size_t)smem_limit() || L < 2) {
+        set_error("ddw_covariance_markowitz_fwd: n_assets=%d, lookback=%d does not fit the fused kernel (%zu B of shared memory)", N, L, smem);
+        return DDW_ERR_UNSUPPORTED;
+    }
+    if (ws_bytes < markowitz_workspace_bytes(B, N, sizeof(T)) || !ws) { set_error("ddw_covariance_markowitz_fwd: workspace too small"); return DDW_ERR_WORKSPACE; }
+    WsLayout<T> l = ws_layout<T>(ws, B, N);
+    MkFwdParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.rets = (const T *)rets; p.C = nullptr; p.gamma = (const T *)gamma; p.alpha = (const T *)alpha;
+    p.u = (T)u; p.B = B; p.Bmod = B; p.b0 = 0; p.N = N; p.LD = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
+    p.w = (T *)w; p.state = state; p.status = status; p.ws = l.q;
+    p.fail_count = l.fail_count; p.fail_list = l.fail_list; p.bad_count = l.bad_count;
+    p.X = (const T *)x; p.coef = (const T *)coef; p.L = L; p.strategy = strategy;
+    if (saved) {
+        p.saved_n = reinterpret_cast<int *>(saved);
+        p.saved = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(saved) + align256(sizeof(int) * (size_t)B));
+        p.saved_stride = saved_stride_elems(N, sizeof(T));
+        cudaMemsetAsync(saved, 0xFF, sizeof(int) * (size_t)B, st);
+    }
+    const int mt = gram_tiles_per_thread(N, 128);
+    if (mt <= 1) return launch_fwd_fused<T, 1>(p, smem, st);
+    if (mt <= 2) return launch_fwd_fused<T, 2>(p, smem, st);
+    if (mt <= 3) return launch_fwd_fused<T, 3>(p, smem, st);
+    return launch_fwd_fused<T, 5>(p, smem, st);
 }
 
 template <typename T, int kThreads, int NREG, bool kGlobal>

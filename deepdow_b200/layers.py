@@ -630,6 +630,107 @@ class CovarianceMatrix(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
+# Fused CovarianceMatrix(sqrt=False) -> NumericalMarkowitz (BachelierNet's chain)
+# ------------------------------------------------------------------------------------------------
+class _CovMarkowitzFn(torch.autograd.Function):
+    """x (B, L, N) -> covariance in shared memory -> solver: the (B, N, N) matrix never exists in HBM in the forward.  The
+    backward recomputes it (one covariance launch) and chains the two ordinary backward kernels."""
+
+    @staticmethod
+    def forward(ctx, x, coef, rets, gamma_sqrt, alpha, strategy, max_weight):
+        _C.require_cuda(x, coef, rets, gamma_sqrt, alpha)
+        lib = _C.lib()
+        B, L, N = x.shape
+        dt = _C.dtype_code(x)
+        x_c, rets_c = _C.aligned(x), _C.aligned(rets)
+        coef_c = None if coef is None else _C.aligned(coef.to(x.dtype))
+        gam_c, alp_c = _C.aligned(gamma_sqrt), _C.aligned(alpha)
+        w = torch.empty_like(rets_c)
+        state = torch.empty((B, N), dtype=torch.int8, device=x.device)
+        status = torch.empty((B,), dtype=torch.int32, device=x.device)
+        ws = _workspace(_C.markowitz_workspace_bytes(B, N, dt), x.device)
+        saved = _workspace(lib.ddw_markowitz_saved_bytes(B, N, dt), x.device) if any(ctx.needs_input_grad[:5]) else None
+        with _C.device_guard(x):
+            rc = lib.ddw_covariance_markowitz_fwd(_C.ptr(x_c), _C.ptr(coef_c), strategy, L, _C.ptr(rets_c), _C.ptr(gam_c), _C.ptr(alp_c),
+                                                  float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status), _C.ptr(ws),
+                                                  ws.numel(), _C.ptr(saved), 0 if saved is None else saved.numel(),
+                                                  _C.stream(x.device))
+        if rc == -2:
+            raise _FusedUnsupported()
+        _C.check(rc, "ddw_covariance_markowitz_fwd")
+        if int(ws[8:12].view(torch.int32)):          # a portfolio needs the fallback solver, which wants covmat_sqrt in HBM
+            raise _FusedUnsupported()
+        ctx.save_for_backward(x_c, coef_c, rets_c, gam_c, alp_c, w, state, saved)
+        ctx.args = (strategy, float(max_weight))
+        ctx.mark_non_differentiable(status)
+        return w, status
+
+    @staticmethod
+    def backward(ctx, grad_w, _grad_status):
+        x_c, coef_c, rets_c, gam_c, alp_c, w, state, saved = ctx.saved_tensors
+        strategy, max_weight = ctx.args
+        lib = _C.lib()
+        B, L, N = x_c.shape
+        dt = _C.dtype_code(x_c)
+        dev = x_c.device
+        cov = torch.empty((B, N, N), dtype=x_c.dtype, device=dev)
+        cws = _workspace(lib.ddw_covariance_workspace_bytes(B, L, N, dt, 0), dev)
+        ws = _workspace(_C.markowitz_workspace_bytes(B, N, dt), dev)
+        g = _C.aligned(grad_w)
+        d_rets, d_cov, d_alpha, d_gamma = torch.empty_like(w), torch.empty_like(cov), torch.empty_like(alp_c), torch.empty_like(gam_c)
+        d_x = torch.empty_like(x_c)
+        d_coef = torch.empty_like(coef_c) if (coef_c is not None and ctx.needs_input_grad[1]) else None
+        with _C.device_guard(x_c):
+            st = _C.stream(dev)
+            rc = lib.ddw_covariance_fwd(_C.ptr(x_c), _C.ptr(coef_c), strategy, 0, B, L, N, dt, _C.ptr(cov), None, None, None,
+                                        _C.ptr(cws), cws.numel(), st)
+            _C.check(rc, "ddw_covariance_fwd")
+            if saved is None:
+                rc = lib.ddw_markowitz_bwd(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov), _C.ptr(gam_c), _C.ptr(alp_c), max_weight, B, N,
+                                           dt, _C.ptr(d_rets), _C.ptr(d_cov), _C.ptr(d_gamma), _C.ptr(d_alpha), _C.ptr(ws), ws.numel(), st)
+            else:
+                rc = lib.ddw_markowitz_bwd_saved(_C.ptr(g), _C.ptr(w), _C.ptr(state), _C.ptr(cov), _C.ptr(gam_c), _C.ptr(alp_c), max_weight,
+                                                 B, N, dt, _C.ptr(d_rets), _C.ptr(d_cov), _C.ptr(d_gamma), _C.ptr(d_alpha), _C.ptr(ws),
+                                                 ws.numel(), _C.ptr(saved), saved.numel(), st)
+            _C.check(rc, "ddw_markowitz_bwd")
+            rc = lib.ddw_covariance_bwd(_C.ptr(d_cov), _C.ptr(x_c), _C.ptr(coef_c), strategy, 0, None, None, B, L, N, dt, _C.ptr(d_x),
+                                        _C.ptr(d_coef), _C.ptr(cws), cws.numel(), st)
+            _C.check(rc, "ddw_covariance_bwd")
+        return d_x, d_coef, d_rets, d_gamma, d_alpha, None, None
+
+
+class _FusedUnsupported(Exception):
+    """The fused kernel cannot take this shape / batch: compose the two layers."""
+
+
+def covariance_markowitz(x, rets, gamma_sqrt, alpha, covariance_layer, allocator, shrinkage_coef=None):
+    """``allocator(rets, covariance_layer(x), gamma_sqrt, alpha)`` for a ``CovarianceMatrix(sqrt=False)`` and a
+    ``NumericalMarkowitz`` -- BachelierNet's chain (deepdow/nn.py:170-171,189-191) -- through the fused kernel
+    ``ddw_covariance_markowitz_fwd``: the (n_samples, n_assets, n_assets) matrix is formed in shared memory and never written
+    to HBM in the forward.  Same results as the composition (the covariance tile is the same code); shapes the fused kernel
+    cannot take (n_assets > 128, long lookbacks) and batches that need the fallback solver run the composition."""
+    if covariance_layer.sqrt or x.shape[1] == 1 or not x.is_cuda:
+        return allocator(rets, covariance_layer(x, shrinkage_coef), gamma_sqrt, alpha)
+    n_samples = x.shape[0]
+    if not ((shrinkage_coef is None) ^ (covariance_layer.shrinkage_coef is None)):
+        raise ValueError("Not clear which shrinkage coefficient to use")
+    coef = None
+    if covariance_layer.shrinkage_strategy is not None:
+        coef = (shrinkage_coef if shrinkage_coef is not None
+                else covariance_layer.shrinkage_coef * torch.ones(n_samples, dtype=x.dtype, device=x.device)).reshape(-1)
+    dtype = rets.dtype
+    if allocator.check_status:
+        allocator._watch.poll()
+    try:
+        w, status = _CovMarkowitzFn.apply(x.to(dtype), coef, rets, gamma_sqrt.reshape(-1).to(dtype), alpha.reshape(-1).to(dtype),
+                                          _C.SHRINKAGE[covariance_layer.shrinkage_strategy], allocator.max_weight)
+    except _FusedUnsupported:
+        return allocator(rets, covariance_layer(x, shrinkage_coef), gamma_sqrt, alpha)
+    allocator.last_status = status
+    return w
+
+
+# ------------------------------------------------------------------------------------------------
 # Resample: the bootstrap meta-allocator on top of the two layers above
 # ------------------------------------------------------------------------------------------------
 class Resample(nn.Module):

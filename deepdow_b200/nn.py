@@ -12,7 +12,7 @@ moves between the two implementations unchanged (nn.py:129-150 for BachelierNet,
 import torch
 from torch import nn
 
-from .layers import CovarianceMatrix, NumericalMarkowitz, SoftmaxAllocator
+from .layers import CovarianceMatrix, NumericalMarkowitz, SoftmaxAllocator, covariance_markowitz
 
 
 class RNN(nn.Module):
@@ -91,14 +91,20 @@ class BachelierNet(nn.Module):
         self.portfolio_opt_layer = NumericalMarkowitz(n_assets, max_weight=max_weight)
         self.gamma_sqrt = nn.Parameter(torch.ones(1), requires_grad=True)
         self.alpha = nn.Parameter(torch.ones(1), requires_grad=True)
+        # Opt-in: form the covariance inside the solver kernel (ddw_covariance_markowitz_fwd) instead of
+        # writing (n_samples, n_assets, n_assets) to HBM and reading it back.  Same weights, bit for bit.
+        self.fused_covariance = False
 
     def forward(self, x):
         """x (n_samples, n_channels, lookback, n_assets) -> weights (n_samples, n_assets)."""
         x = self.norm_layer(x)
-        covmat = self.covariance_layer(x[:, 0])
         h = self.time_collapse_layer(self.dropout_layer(self.transform_layer(x)))
         exp_rets = self.channel_collapse_layer(h)
         ones = torch.ones(len(x), device=x.device, dtype=x.dtype)
+        if self.fused_covariance:
+            return covariance_markowitz(x[:, 0], exp_rets, ones * self.gamma_sqrt, ones * self.alpha, self.covariance_layer,
+                                        self.portfolio_opt_layer)
+        covmat = self.covariance_layer(x[:, 0])
         return self.portfolio_opt_layer(exp_rets, covmat, ones * self.gamma_sqrt, ones * self.alpha)
 
     @property

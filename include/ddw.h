@@ -103,6 +103,21 @@ int ddw_markowitz_bwd_saved(const void *grad_w, const void *w, const int8_t *sta
                             void *d_rets, void *d_covmat_sqrt, void *d_gamma_sqrt, void *d_alpha,
                             void *workspace, size_t workspace_bytes, const void *saved, size_t saved_bytes, void *stream);
 
+/* Fused CovarianceMatrix(sqrt=False) -> NumericalMarkowitz forward (BachelierNet's chain, deepdow/nn.py:170-171,189-191):
+ * covmat_sqrt is never written to HBM -- each portfolio's (L, N) lookback tile x[b] is turned into its shrunk sample covariance
+ * in shared memory (the code of ddw_covariance_fwd with do_sqrt = 0: same bits) and handed to the solver there, so the forward
+ * reads L N + 2 N + 2 elements per portfolio instead of N^2 + 2 N + 2.  gamma_sqrt is applied with the reference's tiling as
+ * in ddw_markowitz_fwd.  Returns DDW_ERR_UNSUPPORTED when the tile does not fit next to the solver (n_assets > 128 or a long
+ * lookback): compose ddw_covariance_fwd and ddw_markowitz_fwd then.  A portfolio whose active set does not converge is left
+ * DDW_STATUS_INEXACT (counter [2] of the workspace header) -- there is no covmat_sqrt in HBM for the interior-point fallback;
+ * the host layer re-runs such a batch through the composed path.  `saved` (may be NULL) as in ddw_markowitz_fwd_saved; the
+ * backward is ddw_covariance_fwd (recompute) + ddw_markowitz_bwd[_saved] + ddw_covariance_bwd. */
+int ddw_covariance_markowitz_fwd(const void *x, const void *coef, int strategy, int64_t L,
+                                 const void *rets, const void *gamma_sqrt, const void *alpha,
+                                 double max_weight, int64_t B, int64_t N, int dtype,
+                                 void *w, int8_t *state, int32_t *status,
+                                 void *workspace, size_t workspace_bytes, void *saved, size_t saved_bytes, void *stream);
+
 /* Chunked launches of the two calls above: the same kernels on the `B` consecutive problems that start at
  * index `batch_offset` of a batch of `batch_total` problems.  Every pointer addresses the chunk's first
  * problem EXCEPT gamma_sqrt / d_gamma_sqrt, which address the whole batch's (batch_total) arrays: the

@@ -248,3 +248,23 @@ def test_thorpnet_shared_problem_equals_the_per_sample_path():
     assert torch.allclose(grads[0][0], grads[1][0], atol=1e-6)
     for ga, gb in zip(grads[0][1], grads[1][1]):
         assert torch.allclose(ga, gb, rtol=2e-4, atol=1e-6 * float(ga.abs().max()) + 1e-9)
+
+
+@pytest.mark.gpu
+def test_bacheliernet_fused_covariance_equals_the_default_path():
+    """BachelierNet.fused_covariance (opt-in): same weights bit for bit, same parameter gradients."""
+    dev = "cuda:0"
+    torch.manual_seed(4)
+    net = dnn.BachelierNet(1, 50, hidden_size=16, max_weight=1, p=0.0).to(dev)
+    X = torch.randn(64, 1, 40, 50, device=dev) * 0.01
+    y = torch.randn(64, 1, 10, 50, device=dev) * 0.01
+    out = []
+    for fused in (False, True):
+        net.fused_covariance = fused
+        net.zero_grad()
+        w = net(X)
+        dnn.sharpe_ratio_loss(w, y).mean().backward()
+        out.append((w.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()}))
+    assert torch.equal(out[0][0], out[1][0])
+    for k in out[0][1]:
+        assert torch.allclose(out[0][1][k], out[1][1][k], rtol=1e-4, atol=1e-7), k

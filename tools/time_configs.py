@@ -52,11 +52,27 @@ X4 = torch.randn(4096, 1, 5, 100, device=dev); y4 = torch.randn(4096, 1, 10, 100
 def thorp_step():
     loss = dnn.sharpe_ratio_loss(net(X4), y4).mean()
     opt.zero_grad(set_to_none=True); loss.backward(); opt.step()
-print(f"C4  ThorpNet N=100 B=4096 max_weight=0.2: training step {timeit(thorp_step, 10):.3f} ms")
+t_thorp = timeit(thorp_step, 10)
+net.shared_problem = True            # opt-in: the 4096 identical problems solved once
+t_thorp_shared = timeit(thorp_step, 10)
+net.shared_problem = False
+print(f"C4  ThorpNet N=100 B=4096 max_weight=0.2: training step {t_thorp:.3f} ms; shared_problem=True {t_thorp_shared:.3f} ms")
 # C2 as BASELINE.json states it: BachelierNet training (tools/train_bachelier.py has the multi-GPU form)
 bn = dnn.BachelierNet(1, 50, hidden_size=32).to(dev); ob = torch.optim.Adam(bn.parameters(), lr=1e-2)
 X2 = torch.randn(256, 1, 40, 50, device=dev) * 0.01; y2 = torch.randn(256, 1, 10, 50, device=dev) * 0.01
 def bach_step():
     loss = dnn.sharpe_ratio_loss(bn(X2), y2).mean()
     ob.zero_grad(set_to_none=True); loss.backward(); ob.step()
-print(f"C2  BachelierNet N=50 L=40 H=10 B=256: training step {timeit(bach_step, 10):.3f} ms")
+t_b = timeit(bach_step, 10)
+bn.fused_covariance = True           # opt-in: covariance formed inside the solver kernel
+t_bf = timeit(bach_step, 10)
+bn.fused_covariance = False
+# the allocation part alone (covariance -> markowitz, fwd + bwd) on the network's shapes, composed vs fused
+from deepdow_b200.layers import covariance_markowitz
+xs = (torch.randn(256, 40, 50, generator=gen, device=dev) * 0.01).requires_grad_(); rs = (torch.randn(256, 50, generator=gen, device=dev) * 0.01).requires_grad_()
+o2 = torch.ones(256, device=dev); G2 = torch.randn(256, 50, device=dev)
+cl, al = CovarianceMatrix(sqrt=False), NumericalMarkowitz(50, 1.0)
+t_comp = timeit(lambda: torch.autograd.grad(al(rs, cl(xs), o2, o2), (xs, rs), G2), 20)
+t_fus = timeit(lambda: torch.autograd.grad(covariance_markowitz(xs, rs, o2, o2, cl, al), (xs, rs), G2), 20)
+print(f"C2  BachelierNet N=50 L=40 H=10 B=256: training step {t_b:.3f} ms; fused_covariance=True {t_bf:.3f} ms; "
+      f"covariance->markowitz fwd+bwd alone: composed {t_comp:.3f} ms, fused {t_fus:.3f} ms")

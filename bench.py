@@ -122,6 +122,29 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank to the CPUs of its GPU's NUMA node before any pinned buffer is allocated, so that the staging buffers of
+    the end-to-end path are first-touched (hence placed) next to the GPU's PCIe root instead of wherever the launcher ran.
+    Eight ranks pushing 2 x 167 MB per step through one host are bound by the host memory system, not by PCIe."""
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(index)
+        bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return f"GPU {index}: local cpulist {spec} not in this process's affinity mask; default placement"
+        os.sched_setaffinity(0, allowed)
+        return f"rank bound to the {len(allowed)} CPUs local to GPU {index} ({spec}) before allocating pinned memory"
+    except Exception as exc:  # noqa: BLE001 - topology files missing in a container: keep the default placement
+        return f"default placement ({type(exc).__name__}: {exc})"
+
+
 class ClockSampler:
     """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -194,6 +217,7 @@ def main():
     _C.lib()  # fail loudly if the extension is not built
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_note = bind_to_gpu_numa(local_rank) if world > 1 else "single process: default placement"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner to stdout at the first collective; the contract is ONE JSON line there
@@ -499,8 +523,23 @@ def main():
     e1.record()
     barrier()
     pipe.check()
-    clocks = sampler.stop()          # sampled over both timed regions (device-resident and end-to-end)
     e2e_ms = e0.elapsed_time(e1)
+    # the same with the gradient of covmat_sqrt returned in factored form (ddw_markowitz_host_step_factored: two N-vectors
+    # per portfolio instead of the N x N outer products; 6.6 MB come back instead of 167 MB)
+    outf = pipe.step(*host_in, factored=True)
+    d2h_bytes_f = sum(t.numel() * t.element_size() for t in outf)
+    for _ in range(2):
+        outf = pipe.step(*host_in, out=outf, sync=False, factored=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        outf = pipe.step(*host_in, out=outf, sync=False, factored=True)
+    e1.record()
+    barrier()
+    pipe.check()
+    e2e_fact_ms = e0.elapsed_time(e1)
+    assert torch.equal(outf.w, out.w) and torch.equal(outf.d_rets, out.d_rets)
+    clocks = sampler.stop()          # sampled over the timed regions (device-resident and end-to-end)
     n_chunks = (B + args.chunk - 1) // args.chunk
     # the pipelined host path must reproduce the device path bit for bit (same kernels, chunked)
     with torch.no_grad():
@@ -528,7 +567,7 @@ def main():
     barrier()
     e2e_layer_ms = l0.elapsed_time(l1)
 
-    times = torch.tensor([elapsed_ms, e2e_ms, fwd_only_ms, e2e_layer_ms, graph_ms if graph_ms is not None else -1.0],
+    times = torch.tensor([elapsed_ms, e2e_ms, fwd_only_ms, e2e_layer_ms, graph_ms if graph_ms is not None else -1.0, e2e_fact_ms],
                          device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -536,7 +575,7 @@ def main():
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if float(ok) == 0.0:
             graph_ms = None
-    elapsed_ms, e2e_ms, fwd_only_ms, e2e_layer_ms, graph_max = [float(x) for x in times.tolist()]
+    elapsed_ms, e2e_ms, fwd_only_ms, e2e_layer_ms, graph_max, e2e_fact_ms = [float(x) for x in times.tolist()]
     eager_ms = elapsed_ms
     if graph_ms is not None:
         elapsed_ms = graph_max
@@ -588,7 +627,13 @@ def main():
                     "api": f"ddw_markowitz_host_step via MarkowitzHostPipeline.step (pinned host buffers, {n_chunks} chunks of "
                            f"{args.chunk} problems on H2D / kernel / D2H streams)",
                     "layer_api_unpipelined": {"value": world * B * steps_total / (e2e_layer_ms * 1e-3),
-                                              "ms_per_step": e2e_layer_ms / steps_total}},
+                                              "ms_per_step": e2e_layer_ms / steps_total},
+                    "factored_gradient": {"value": world * B * steps_total / (e2e_fact_ms * 1e-3), "unit": UNIT,
+                                          "ms_per_step": e2e_fact_ms / steps_total, "h2d_bytes_per_step": h2d_bytes,
+                                          "d2h_bytes_per_step": d2h_bytes_f,
+                                          "api": "ddw_markowitz_host_step_factored: d_covmat_sqrt returned as its two factor "
+                                                 "vectors per portfolio (rank 2), everything else identical"},
+                    "pinned_buffers": numa_note},
             "eager": {"value": world * B * steps_total / (eager_ms * 1e-3), "unit": UNIT, "ms_per_step": eager_ms / steps_total,
                       "note": "same step launched from Python every time (autograd Function + ctypes)"},
             "gpu_launches": 7 * steps_total * rounds,

@@ -33,7 +33,7 @@ SIGNATURES = {
     "ddw_markowitz_bwd_saved": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
                                        _vp]),
     "ddw_covariance_markowitz_fwd": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
-                                            _vp]),
+                                            _vp, _vp]),
     "ddw_markowitz_fwd_chunk": (_i32, [_vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddw_markowitz_bwd_chunk": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _i32,
                                        _vp, _vp, _sz, _vp]),
@@ -43,6 +43,8 @@ SIGNATURES = {
     "ddw_markowitz_host_scratch_bytes": (_sz, [_i64, _i64, _i32, _i64]),
     "ddw_markowitz_host_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _sz, _vp]),
+    "ddw_markowitz_host_step_factored": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                _vp, _sz, _vp]),
     "ddw_risk_budgeting_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "ddw_risk_budgeting_fwd": (_i32, [_vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddw_risk_budgeting_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),

@@ -33,13 +33,14 @@ int markowitz_fwd_t(const void *, const void *, const void *, const void *, doub
                     int32_t *, void *, size_t, cudaStream_t, long long, long long, void *);
 template <typename T>
 int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, const void *, const void *, long long,
-                    int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int, const void *);
+                    int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int, const void *,
+                    void *);
 template <typename T>
 int row_op_t(int, const void *, const void *, double, double, long long, int, const void *, const void *, void *,
              void *, void *, cudaStream_t);
 template <typename T>
 int markowitz_fused_fwd_t(const void *, const void *, int, int, const void *, const void *, const void *, double, long long, int,
-                          void *, int8_t *, int32_t *, void *, size_t, cudaStream_t, void *);
+                          void *, int8_t *, int32_t *, void *, size_t, cudaStream_t, void *, void *);
 size_t risk_budgeting_workspace_bytes(long long B, int N, int tsize);      // risk_budgeting.cu
 template <typename T>
 int risk_budgeting_t(bool, const void *, const void *, const void *, const void *, const int8_t *, double, long long, int, void *,
@@ -144,8 +145,8 @@ static int markowitz_bwd_impl(const void *grad_w, const void *w, const int8_t *s
     if (saved && saved_bytes < ddw_markowitz_saved_bytes(B, N, dtype)) { set_error("ddw_markowitz_bwd_saved: saved buffer too small"); return DDW_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64
-               ? markowitz_bwd_t<double>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st, batch_total, batch_offset, accumulate_gamma, saved)
-               : markowitz_bwd_t<float>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st, batch_total, batch_offset, accumulate_gamma, saved);
+               ? markowitz_bwd_t<double>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st, batch_total, batch_offset, accumulate_gamma, saved, nullptr)
+               : markowitz_bwd_t<float>(grad_w, w, state, covmat_sqrt, gamma_sqrt, alpha, B, (int)N, d_rets, d_covmat_sqrt, d_gamma_sqrt, d_alpha, workspace, workspace_bytes, st, batch_total, batch_offset, accumulate_gamma, saved, nullptr);
 }
 
 int ddw_markowitz_bwd_chunk(const void *grad_w, const void *w, const int8_t *state, const void *covmat_sqrt,
@@ -191,7 +192,7 @@ static int row_call(const char *fn, int which, const void *x, const void *temper
 int ddw_covariance_markowitz_fwd(const void *x, const void *coef, int strategy, int64_t L, const void *rets,
                                  const void *gamma_sqrt, const void *alpha, double max_weight, int64_t B, int64_t N, int dtype,
                                  void *w, int8_t *state, int32_t *status, void *workspace, size_t workspace_bytes,
-                                 void *saved, size_t saved_bytes, void *stream) {
+                                 void *saved, size_t saved_bytes, void *covmat_scratch, void *stream) {
     g_err[0] = 0;
     int rc = check_dims("ddw_covariance_markowitz_fwd", B, N, 1024, dtype);
     if (rc) return rc;
@@ -199,12 +200,12 @@ int ddw_covariance_markowitz_fwd(const void *x, const void *coef, int strategy, 
     if (L < 2 || L >= (1LL << 24)) { set_error("ddw_covariance_markowitz_fwd: need 2 <= dim < 2^24 observations, got %lld", (long long)L); return DDW_ERR_ARG; }
     if (strategy < DDW_SHRINK_NONE || strategy > DDW_SHRINK_SCALED_IDENTITY) { set_error("ddw_covariance_markowitz_fwd: bad strategy %d", strategy); return DDW_ERR_ARG; }
     if (!x || !rets || !gamma_sqrt || !alpha || !w || !state || !status || (strategy != DDW_SHRINK_NONE && !coef)) { set_error("ddw_covariance_markowitz_fwd: null pointer"); return DDW_ERR_ARG; }
-    DDW_CHECK_ALIGNED("ddw_covariance_markowitz_fwd", x, rets, gamma_sqrt, alpha, w, workspace, saved);
+    DDW_CHECK_ALIGNED("ddw_covariance_markowitz_fwd", x, rets, gamma_sqrt, alpha, w, workspace, saved, covmat_scratch);
     if (saved && saved_bytes < ddw_markowitz_saved_bytes(B, N, dtype)) { set_error("ddw_covariance_markowitz_fwd: saved buffer too small"); return DDW_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DDW_F64
-               ? markowitz_fused_fwd_t<double>(x, coef, strategy, (int)L, rets, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, saved)
-               : markowitz_fused_fwd_t<float>(x, coef, strategy, (int)L, rets, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, saved);
+               ? markowitz_fused_fwd_t<double>(x, coef, strategy, (int)L, rets, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, saved, covmat_scratch)
+               : markowitz_fused_fwd_t<float>(x, coef, strategy, (int)L, rets, gamma_sqrt, alpha, max_weight, B, (int)N, w, state, status, workspace, workspace_bytes, st, saved, covmat_scratch);
 }
 
 size_t ddw_risk_budgeting_workspace_bytes(int64_t B, int64_t N, int dtype) {

@@ -27,7 +27,7 @@ int markowitz_fwd_t(const void *, const void *, const void *, const void *, doub
 template <typename T>
 int markowitz_bwd_t(const void *, const void *, const int8_t *, const void *, const void *, const void *, long long,
                     int, void *, void *, void *, void *, void *, size_t, cudaStream_t, long long, long long, int,
-                    const void * = nullptr);
+                    const void * = nullptr, void * = nullptr);
 
 constexpr int kMaxSlots = 8, kMaxRun = 4;
 // chunk slots in the device scratch / solver streams (consecutive chunks are solved concurrently: a chunk alone cannot
@@ -45,7 +45,7 @@ static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
 // device scratch: whole-batch vectors, then kSlots chunk slots of (covmat_sqrt, d_covmat_sqrt, workspace)
 struct ScratchLayout {
-    size_t gamma, d_gamma, rets, alpha, grad_w, w, state, status, d_rets, d_alpha;   // whole batch
+    size_t gamma, d_gamma, rets, alpha, grad_w, w, state, status, d_rets, d_alpha, vecs;   // whole batch
     size_t slots, slot_bytes, C, d_C, ws, ws_bytes;                                  // per slot
     size_t total;
 };
@@ -65,6 +65,7 @@ static ScratchLayout scratch_layout(long long B, long long chunk, int N, int tsi
     l.status = take(b * sizeof(int32_t));
     l.d_rets = take(b * n * tsize);
     l.d_alpha = take(b * tsize);
+    l.vecs = take(b * 2 * n * tsize);      // (A d, A w): the factored form of d_covmat_sqrt
     l.slots = o;
     o = 0;
     l.C = take(c * n * n * tsize);
@@ -85,12 +86,13 @@ struct StepArgs {
     int32_t *h_status;
     void *h_d_rets, *h_d_covmat_sqrt, *h_d_gamma_sqrt, *h_d_alpha, *dev_scratch;
     size_t dev_scratch_bytes;
+    void *h_factors;     // non-null: return (A d, A w) per problem instead of d_covmat_sqrt (ddw_markowitz_host_step_factored)
     bool operator==(const StepArgs &o) const {
         return h_rets == o.h_rets && h_covmat_sqrt == o.h_covmat_sqrt && h_gamma_sqrt == o.h_gamma_sqrt &&
                h_alpha == o.h_alpha && h_grad_w == o.h_grad_w && max_weight == o.max_weight && B == o.B && N == o.N &&
                chunk == o.chunk && dtype == o.dtype && h_w == o.h_w && h_status == o.h_status && h_d_rets == o.h_d_rets &&
                h_d_covmat_sqrt == o.h_d_covmat_sqrt && h_d_gamma_sqrt == o.h_d_gamma_sqrt && h_d_alpha == o.h_d_alpha &&
-               dev_scratch == o.dev_scratch && dev_scratch_bytes == o.dev_scratch_bytes;
+               dev_scratch == o.dev_scratch && dev_scratch_bytes == o.dev_scratch_bytes && h_factors == o.h_factors;
     }
 };
 
@@ -182,16 +184,17 @@ static int enqueue_step(ddw_host_pipeline *pipe, const StepArgs &a, cudaStream_t
             rc = markowitz_fwd_t<float>(rets, S + L.C, base + L.gamma, alpha, a.max_weight, c, n, w, state, status, S + L.ws, L.ws_bytes, run, B, b0);
         if (!rc && bwd) {
             void *dg = want_dgamma ? base + L.d_gamma : nullptr;
+            void *vo = a.h_factors ? base + L.vecs + b0 * 2 * row : nullptr;
             if (a.dtype == DDW_F64)
-                rc = markowitz_bwd_t<double>(grad_w, w, state, S + L.C, base + L.gamma, alpha, c, n, d_rets, S + L.d_C, dg, d_alpha, S + L.ws, L.ws_bytes, run, B, b0, 1);
+                rc = markowitz_bwd_t<double>(grad_w, w, state, S + L.C, base + L.gamma, alpha, c, n, d_rets, S + L.d_C, dg, d_alpha, S + L.ws, L.ws_bytes, run, B, b0, 1, nullptr, vo);
             else
-                rc = markowitz_bwd_t<float>(grad_w, w, state, S + L.C, base + L.gamma, alpha, c, n, d_rets, S + L.d_C, dg, d_alpha, S + L.ws, L.ws_bytes, run, B, b0, 1);
+                rc = markowitz_bwd_t<float>(grad_w, w, state, S + L.C, base + L.gamma, alpha, c, n, d_rets, S + L.d_C, dg, d_alpha, S + L.ws, L.ws_bytes, run, B, b0, 1, nullptr, vo);
         }
         cudaEventRecord(pipe->run_done[sl], run);
         if (rc) break;
 
         cudaStreamWaitEvent(pipe->s_out, pipe->run_done[sl], 0);
-        if (bwd)
+        if (bwd && !a.h_factors)
             cudaMemcpyAsync(reinterpret_cast<unsigned char *>(a.h_d_covmat_sqrt) + b0 * mat, S + L.d_C, c * mat,
                             cudaMemcpyDeviceToHost, pipe->s_out);
         cudaEventRecord(pipe->out_done[sl], pipe->s_out);
@@ -204,6 +207,7 @@ static int enqueue_step(ddw_host_pipeline *pipe, const StepArgs &a, cudaStream_t
         if (bwd) {
             cudaMemcpyAsync(a.h_d_rets, base + L.d_rets, (size_t)B * row, cudaMemcpyDeviceToHost, pipe->s_out);
             cudaMemcpyAsync(a.h_d_alpha, base + L.d_alpha, (size_t)B * ts, cudaMemcpyDeviceToHost, pipe->s_out);
+            if (a.h_factors) cudaMemcpyAsync(a.h_factors, base + L.vecs, (size_t)B * 2 * row, cudaMemcpyDeviceToHost, pipe->s_out);
         }
         if (want_dgamma) cudaMemcpyAsync(a.h_d_gamma_sqrt, base + L.d_gamma, (size_t)B * ts, cudaMemcpyDeviceToHost, pipe->s_out);
     }
@@ -265,11 +269,11 @@ size_t ddw_markowitz_host_scratch_bytes(int64_t B, int64_t N, int dtype, int64_t
     return scratch_layout(B, chunk, (int)N, dtype == DDW_F64 ? 8 : 4).total;
 }
 
-int ddw_markowitz_host_step(ddw_host_pipeline *pipe, const void *h_rets, const void *h_covmat_sqrt,
-                            const void *h_gamma_sqrt, const void *h_alpha, const void *h_grad_w, double max_weight,
-                            int64_t B, int64_t N, int dtype, int64_t chunk, void *h_w, int32_t *h_status, void *h_d_rets,
-                            void *h_d_covmat_sqrt, void *h_d_gamma_sqrt, void *h_d_alpha, void *dev_scratch,
-                            size_t dev_scratch_bytes, void *stream) {
+static int host_step_impl(ddw_host_pipeline *pipe, const void *h_rets, const void *h_covmat_sqrt,
+                          const void *h_gamma_sqrt, const void *h_alpha, const void *h_grad_w, double max_weight,
+                          int64_t B, int64_t N, int dtype, int64_t chunk, void *h_w, int32_t *h_status, void *h_d_rets,
+                          void *h_d_covmat_sqrt, void *h_factors, void *h_d_gamma_sqrt, void *h_d_alpha, void *dev_scratch,
+                          size_t dev_scratch_bytes, void *stream) {
     const char *fn = "ddw_markowitz_host_step";
     if (dtype != DDW_F32 && dtype != DDW_F64) { set_error("%s: dtype must be DDW_F32 or DDW_F64", fn); return DDW_ERR_ARG; }
     if (B < 0 || B >= (1LL << 31) || chunk <= 0) { set_error("%s: bad batch size / chunk", fn); return DDW_ERR_ARG; }
@@ -277,14 +281,14 @@ int ddw_markowitz_host_step(ddw_host_pipeline *pipe, const void *h_rets, const v
     if (B == 0) return 0;
     const bool bwd = h_grad_w != nullptr;
     if (!pipe || !h_rets || !h_covmat_sqrt || !h_gamma_sqrt || !h_alpha || !h_w || !h_status ||
-        (bwd && (!h_d_rets || !h_d_covmat_sqrt || !h_d_alpha))) { set_error("%s: null pointer", fn); return DDW_ERR_ARG; }
+        (bwd && (!h_d_rets || (!h_d_covmat_sqrt && !h_factors) || !h_d_alpha))) { set_error("%s: null pointer", fn); return DDW_ERR_ARG; }
     if (chunk > B) chunk = B;
     if (!dev_scratch || dev_scratch_bytes < ddw_markowitz_host_scratch_bytes(B, N, dtype, chunk)) { set_error("%s: device scratch too small", fn); return DDW_ERR_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(dev_scratch) & 255u) { set_error("%s: device scratch must be 256-byte aligned", fn); return DDW_ERR_ARG; }
-    if (!bwd) h_d_rets = h_d_covmat_sqrt = h_d_gamma_sqrt = h_d_alpha = nullptr;
+    if (!bwd) h_d_rets = h_d_covmat_sqrt = h_d_gamma_sqrt = h_d_alpha = h_factors = nullptr;
 
     const StepArgs a = {h_rets, h_covmat_sqrt, h_gamma_sqrt, h_alpha, h_grad_w, max_weight, B, N, chunk, dtype, h_w, h_status,
-                        h_d_rets, h_d_covmat_sqrt, h_d_gamma_sqrt, h_d_alpha, dev_scratch, dev_scratch_bytes};
+                        h_d_rets, h_d_covmat_sqrt, h_d_gamma_sqrt, h_d_alpha, dev_scratch, dev_scratch_bytes, h_factors};
     cudaStream_t user = (cudaStream_t)stream;
     static const bool no_graph = getenv("DDW_HOST_PIPELINE_NO_GRAPH") != nullptr;   // diagnostic: always enqueue eagerly
     const bool same = !no_graph && pipe->have_last && pipe->last == a;
@@ -296,7 +300,7 @@ int ddw_markowitz_host_step(ddw_host_pipeline *pipe, const void *h_rets, const v
     if (pipe->exec) { cudaGraphExecDestroy(pipe->exec); pipe->exec = nullptr; }
     if (same && page_locked(h_rets) && page_locked(h_covmat_sqrt) && page_locked(h_gamma_sqrt) && page_locked(h_alpha) &&
         page_locked(h_grad_w) && page_locked(h_w) && page_locked(h_status) && page_locked(h_d_rets) &&
-        page_locked(h_d_covmat_sqrt) && page_locked(h_d_gamma_sqrt) && page_locked(h_d_alpha)) {
+        page_locked(h_d_covmat_sqrt) && page_locked(h_d_gamma_sqrt) && page_locked(h_d_alpha) && page_locked(h_factors)) {
         // second request with these arguments: record the step once, replay it from now on
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(pipe->s_origin, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -319,6 +323,25 @@ int ddw_markowitz_host_step(ddw_host_pipeline *pipe, const void *h_rets, const v
     const int rc = enqueue_step(pipe, a, user);
     if (rc) return rc;
     return check_launch(fn);
+}
+
+int ddw_markowitz_host_step(ddw_host_pipeline *pipe, const void *h_rets, const void *h_covmat_sqrt,
+                            const void *h_gamma_sqrt, const void *h_alpha, const void *h_grad_w, double max_weight,
+                            int64_t B, int64_t N, int dtype, int64_t chunk, void *h_w, int32_t *h_status, void *h_d_rets,
+                            void *h_d_covmat_sqrt, void *h_d_gamma_sqrt, void *h_d_alpha, void *dev_scratch,
+                            size_t dev_scratch_bytes, void *stream) {
+    return host_step_impl(pipe, h_rets, h_covmat_sqrt, h_gamma_sqrt, h_alpha, h_grad_w, max_weight, B, N, dtype, chunk, h_w, h_status,
+                          h_d_rets, h_d_covmat_sqrt, nullptr, h_d_gamma_sqrt, h_d_alpha, dev_scratch, dev_scratch_bytes, stream);
+}
+
+int ddw_markowitz_host_step_factored(ddw_host_pipeline *pipe, const void *h_rets, const void *h_covmat_sqrt,
+                                     const void *h_gamma_sqrt, const void *h_alpha, const void *h_grad_w, double max_weight,
+                                     int64_t B, int64_t N, int dtype, int64_t chunk, void *h_w, int32_t *h_status, void *h_d_rets,
+                                     void *h_factors, void *h_d_gamma_sqrt, void *h_d_alpha, void *dev_scratch,
+                                     size_t dev_scratch_bytes, void *stream) {
+    if (h_grad_w && !h_factors) { set_error("ddw_markowitz_host_step_factored: null factor buffer"); return DDW_ERR_ARG; }
+    return host_step_impl(pipe, h_rets, h_covmat_sqrt, h_gamma_sqrt, h_alpha, h_grad_w, max_weight, B, N, dtype, chunk, h_w, h_status,
+                          h_d_rets, nullptr, h_factors, h_d_gamma_sqrt, h_d_alpha, dev_scratch, dev_scratch_bytes, stream);
 }
 
 }  // extern "C"

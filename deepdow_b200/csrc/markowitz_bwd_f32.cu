@@ -5,5 +5,5 @@
 namespace ddw {
 template int markowitz_bwd_t<float>(const void *, const void *, const int8_t *, const void *, const void *,
                                     const void *, long long, int, void *, void *, void *, void *, void *, size_t,
-                                    cudaStream_t, long long, long long, int, const void *);
+                                    cudaStream_t, long long, long long, int, const void *, void *);
 }  // namespace ddw

@@ -7,5 +7,5 @@ namespace ddw {
 template int markowitz_fwd_t<float>(const void *, const void *, const void *, const void *, double, long long, int,
                                     void *, int8_t *, int32_t *, void *, size_t, cudaStream_t, long long, long long, void *);
 template int markowitz_fused_fwd_t<float>(const void *, const void *, int, int, const void *, const void *, const void *, double,
-                                          long long, int, void *, int8_t *, int32_t *, void *, size_t, cudaStream_t, void *);
+                                          long long, int, void *, int8_t *, int32_t *, void *, size_t, cudaStream_t, void *, void *);
 }  // namespace ddw

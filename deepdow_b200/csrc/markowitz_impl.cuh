@@ -110,12 +110,17 @@ __global__ void __launch_bounds__(kThreads) markowitz_fwd_kernel(MkFwdParams<T> 
             }
             if (tid == 0) p.saved_n[b] = keep ? nF : -1;
         }
+        if (kFused && !converged && !nonfinite && p.C) {
+            // the interior-point fallback reads covmat_sqrt from HBM: spill this portfolio's covariance tile for it
+            T *dst = const_cast<T *>(p.C) + b * (long long)N * N;
+            for (int e = tid; e < N * N; e += kThreads) dst[e] = Cb[e];
+        }
         if (tid == 0) {
             int st = lifted ? DDW_STATUS_REGULARIZED : 0;
             if (nonfinite) { st |= DDW_STATUS_INEXACT; atomicAdd(p.bad_count, 1); }     // NaN / Inf in the inputs
             else if (!converged) {
                 st |= DDW_STATUS_FALLBACK | DDW_STATUS_INEXACT;
-                if (kFused) atomicAdd(p.bad_count, 1);      // no covmat_sqrt in HBM for the fallback kernel: the host layer re-runs unfused
+                if (kFused && !p.C) atomicAdd(p.bad_count, 1);      // no covmat_sqrt in HBM for the fallback kernel
                 else {
                     const int slot = atomicAdd(p.fail_count, 1);
                     p.fail_list[slot] = (int)b;
@@ -1056,18 +1061,24 @@ size_t markowitz_fused_smem_bytes(int N, int L, int tsize) {
 #endif
 
 template <typename T, int MAXT>
-static int launch_fwd_fused(const MkFwdParams<T> &p, size_t smem, cudaStream_t st) {
+static int launch_fwd_fused(const MkFwdParams<T> &p, size_t smem, size_t smem_ipm, T *ipm_ws, cudaStream_t st) {
     auto kf = markowitz_fwd_kernel<T, 128, 4, false, MAXT, true>;
+    auto ki = markowitz_ipm_kernel<T, 128, 4, false>;
     static DeviceOnce configured;
     const int dev = current_device();
     if (configured.needs(dev)) {
-        if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess)
+        if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess ||
+            cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(markowitz_fwd fused)");
         configured.mark(dev);
     }
     cudaMemsetAsync(p.fail_count, 0, 4 * sizeof(int), st);
     kf<<<(unsigned)p.B, 128, smem, st>>>(p);
-    return check_launch("markowitz_fwd_kernel (fused covariance)");
+    int rc = check_launch("markowitz_fwd_kernel (fused covariance)");
+    if (rc || !p.C) return rc;
+    // portfolios whose active set did not converge: their covariance tile was spilled to p.C, the fallback runs as usual
+    ki<<<(unsigned)min((long long)kIpmGrid, p.B), 128, smem_ipm, st>>>(p, ipm_ws, 0);
+    return check_launch("markowitz_ipm_kernel (fused covariance)");
 }
 
 // x (B, L, N) observations -> covariance (sqrt = False, `strategy`, coef) -> NumericalMarkowitz.  DDW_ERR_UNSUPPORTED when the
@@ -1075,7 +1086,7 @@ static int launch_fwd_fused(const MkFwdParams<T> &p, size_t smem, cudaStream_t s
 template <typename T>
 int markowitz_fused_fwd_t(const void *x, const void *coef, int strategy, int L, const void *rets, const void *gamma,
                           const void *alpha, double u, long long B, int N, void *w, int8_t *state, int32_t *status, void *ws,
-                          size_t ws_bytes, cudaStream_t st, void *saved) {
+                          size_t ws_bytes, cudaStream_t st, void *saved, void *cov_scratch) {
     const MkPlan pl = plan_fwd(N, sizeof(T));
     const size_t smem = markowitz_fused_smem_bytes(N, L, sizeof(T));
     if (pl.global_q || pl.threads != 128 || smem > (size_t)smem_limit() || L < 2) {
@@ -1086,7 +1097,7 @@ int markowitz_fused_fwd_t(const void *x, const void *coef, int strategy, int L, 
     WsLayout<T> l = ws_layout<T>(ws, B, N);
     MkFwdParams<T> p;
     memset(&p, 0, sizeof(p));
-    p.rets = (const T *)rets; p.C = nullptr; p.gamma = (const T *)gamma; p.alpha = (const T *)alpha;
+    p.rets = (const T *)rets; p.C = (const T *)cov_scratch; p.gamma = (const T *)gamma; p.alpha = (const T *)alpha;
     p.u = (T)u; p.B = B; p.Bmod = B; p.b0 = 0; p.N = N; p.LD = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
     p.w = (T *)w; p.state = state; p.status = status; p.ws = l.q;
     p.fail_count = l.fail_count; p.fail_list = l.fail_list; p.bad_count = l.bad_count;
@@ -1098,10 +1109,10 @@ int markowitz_fused_fwd_t(const void *x, const void *coef, int strategy, int L, 
         cudaMemsetAsync(saved, 0xFF, sizeof(int) * (size_t)B, st);
     }
     const int mt = gram_tiles_per_thread(N, 128);
-    if (mt <= 1) return launch_fwd_fused<T, 1>(p, smem, st);
-    if (mt <= 2) return launch_fwd_fused<T, 2>(p, smem, st);
-    if (mt <= 3) return launch_fwd_fused<T, 3>(p, smem, st);
-    return launch_fwd_fused<T, 5>(p, smem, st);
+    if (mt <= 1) return launch_fwd_fused<T, 1>(p, smem, pl.smem, l.ipm, st);
+    if (mt <= 2) return launch_fwd_fused<T, 2>(p, smem, pl.smem, l.ipm, st);
+    if (mt <= 3) return launch_fwd_fused<T, 3>(p, smem, pl.smem, l.ipm, st);
+    return launch_fwd_fused<T, 5>(p, smem, pl.smem, l.ipm, st);
 }
 
 template <typename T, int kThreads, int NREG, bool kGlobal>
@@ -1137,7 +1148,8 @@ static int launch_bwd_saved_variant(const MkBwdParams<T> &p, cudaStream_t st) {
 template <typename T>
 int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, const void *C, const void *gamma,
                     const void *alpha, long long B, int N, void *d_rets, void *d_C, void *d_gamma, void *d_alpha,
-                    void *ws, size_t ws_bytes, cudaStream_t st, long long Bmod, long long b0, int accumulate_gamma, const void *saved) {
+                    void *ws, size_t ws_bytes, cudaStream_t st, long long Bmod, long long b0, int accumulate_gamma, const void *saved,
+                    void *vecs_out) {
     if (ws_bytes < markowitz_workspace_bytes(B, N, sizeof(T)) || !ws) {
         set_error("ddw_markowitz_bwd: workspace too small (%zu < %zu)", ws_bytes, markowitz_workspace_bytes(B, N, sizeof(T)));
         return DDW_ERR_WORKSPACE;
@@ -1148,7 +1160,10 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
     MkBwdParams<T> p;
     p.grad_w = (const T *)grad_w; p.w = (const T *)w; p.C = (const T *)C; p.gamma = (const T *)gamma;
     p.alpha = (const T *)alpha; p.state = state; p.B = B; p.Bmod = Bmod; p.b0 = b0; p.N = N; p.LDW = pl.LD; p.AS = pl.AS; p.CH = pl.CH;
-    p.d_rets = (T *)d_rets; p.d_C = (T *)d_C; p.d_alpha = (T *)d_alpha; p.vecs = d_gamma ? l.vecs : nullptr; p.ws = l.q;
+    // (A d, A w) per problem: scratch of the gamma pass, or -- vecs_out -- an output of its own (the factored gradient:
+    // d_covmat_sqrt = -2 gamma_ * [(A d) w' + (A w) d'] is rank 2, 2 N numbers instead of N^2)
+    T *vecs = vecs_out ? (T *)vecs_out : l.vecs;
+    p.d_rets = (T *)d_rets; p.d_C = (T *)d_C; p.d_alpha = (T *)d_alpha; p.vecs = (d_gamma || vecs_out) ? vecs : nullptr; p.ws = l.q;
     int rc;
     // sparse-support kernel first (A staged by TMA, free set <= kCandMax); it lists the portfolios it cannot take
     p.work_count = nullptr; p.work_list = nullptr;
@@ -1194,10 +1209,10 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
     nsplit = (qn + q_per - 1) / q_per;
     dim3 grid((unsigned)((cols + 127) / 128), (unsigned)nsplit);
     if (vec4)
-        markowitz_gamma_kernel<T, 4><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, l.vecs, total,
+        markowitz_gamma_kernel<T, 4><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, vecs, total,
                                                            Bmod, off, N, q_per, (T *)d_gamma);
     else
-        markowitz_gamma_kernel<T, 1><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, l.vecs, total,
+        markowitz_gamma_kernel<T, 1><<<grid, 128, 0, st>>>((const T *)C, (const T *)w, (const T *)d_rets, vecs, total,
                                                            Bmod, off, N, q_per, (T *)d_gamma);
     return check_launch("markowitz_gamma_kernel");
 }

@@ -17,6 +17,19 @@ from .layers import SolverError
 
 HostStepResult = collections.namedtuple("HostStepResult",
                                         ["w", "d_rets", "d_covmat_sqrt", "d_gamma_sqrt", "d_alpha", "status"])
+# the same with the gradient of covmat_sqrt in factored form: factors (B, 2, N) = (A d, A w), see expand_factored()
+HostStepFactored = collections.namedtuple("HostStepFactored",
+                                          ["w", "d_rets", "factors", "d_gamma_sqrt", "d_alpha", "status"])
+
+
+def expand_factored(result, gamma_sqrt):
+    """d_covmat_sqrt (B, N, N) from a ``HostStepFactored``: ``-2 gamma_ * (p w' + q d')`` with ``(p, q) = factors`` and
+    ``gamma_`` the reference's tiling of ``gamma_sqrt`` (allocate.py:268-270).  Host-side helper for callers (and tests) that
+    want the dense gradient after all; the point of the factored form is that most do not."""
+    B, N = result.w.shape
+    p, q = result.factors[:, 0], result.factors[:, 1]
+    gamma_ = gamma_sqrt.reshape(-1).to(result.w.dtype).repeat((1, N * N)).view(B, N, N)
+    return -2 * gamma_ * (p[:, :, None] * result.w[:, None, :] + q[:, :, None] * result.d_rets[:, None, :])
 
 
 class MarkowitzHostPipeline:
@@ -60,13 +73,15 @@ class MarkowitzHostPipeline:
         t = t.to(dtype).reshape(shape).contiguous()
         return t
 
-    def step(self, rets, covmat_sqrt, gamma_sqrt, alpha, grad_w=None, out=None, sync=True):
+    def step(self, rets, covmat_sqrt, gamma_sqrt, alpha, grad_w=None, out=None, sync=True, factored=False):
         """Solve the batch; with ``grad_w`` also return the gradients of ``(w * grad_w).sum()``.
 
         All arguments are CPU tensors shaped as in the reference's ``forward`` (allocate.py:240-266);
         pinned memory lets the copies run asynchronously.  Returns a ``HostStepResult`` of pinned CPU tensors
         (gradient fields are None without ``grad_w``); pass an earlier result as ``out`` to reuse its buffers.  With ``sync=False`` the call only enqueues; read the results
-        after ``torch.cuda.current_stream().synchronize()`` and call ``check()``.
+        after ``torch.cuda.current_stream().synchronize()`` and call ``check()``.  ``factored=True`` (with ``grad_w``) returns a
+        ``HostStepFactored``: the rank-2 gradient of covmat_sqrt as its two factor vectors per portfolio (2 N numbers instead
+        of N^2 come back over PCIe), see ``expand_factored``.
         """
         B, N = rets.shape
         if N != self.n_assets:
@@ -81,19 +96,21 @@ class MarkowitzHostPipeline:
         gam_h = self._host(gamma_sqrt, dtype, (B,), "gamma_sqrt")
         alp_h = self._host(alpha, dtype, (B,), "alpha")
         g_h = None if grad_w is None else self._host(grad_w, dtype, (B, N), "grad_w")
+        factored = bool(factored) and g_h is not None
         if out is None:
             pin = lambda *s, d=dtype: torch.empty(s, dtype=d).pin_memory()
-            grads = (pin(B, N), pin(B, N, N), pin(B), pin(B)) if g_h is not None else (None,) * 4
-            out = HostStepResult(pin(B, N), *grads, pin(B, d=torch.int32))
+            grads = (pin(B, N), pin(B, 2, N) if factored else pin(B, N, N), pin(B), pin(B)) if g_h is not None else (None,) * 4
+            out = (HostStepFactored if factored else HostStepResult)(pin(B, N), *grads, pin(B, d=torch.int32))
         w, status, grads = out.w, out.status, tuple(out[1:5])
         self.last_status = status
         p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
         d_rets, d_cov, d_gam, d_alp = grads
+        fn = lib.ddw_markowitz_host_step_factored if factored else lib.ddw_markowitz_host_step
         with torch.cuda.device(self.device):
-            rc = lib.ddw_markowitz_host_step(self._handle, p(rets_h), p(cov_h), p(gam_h), p(alp_h), p(g_h),
-                                             self.max_weight, B, N, dt, self.chunk, p(w), p(status),
-                                             p(d_rets), p(d_cov), p(d_gam), p(d_alp),
-                                             p(self._scratch), self._scratch.numel(), _C.stream(self.device))
+            rc = fn(self._handle, p(rets_h), p(cov_h), p(gam_h), p(alp_h), p(g_h),
+                    self.max_weight, B, N, dt, self.chunk, p(w), p(status),
+                    p(d_rets), p(d_cov), p(d_gam), p(d_alp),
+                    p(self._scratch), self._scratch.numel(), _C.stream(self.device))
         _C.check(rc, "ddw_markowitz_host_step")
         self._keep = (rets_h, cov_h, gam_h, alp_h, g_h)   # the copies read these until the stream has drained
         if sync:

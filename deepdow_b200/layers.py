@@ -637,7 +637,7 @@ class _CovMarkowitzFn(torch.autograd.Function):
     backward recomputes it (one covariance launch) and chains the two ordinary backward kernels."""
 
     @staticmethod
-    def forward(ctx, x, coef, rets, gamma_sqrt, alpha, strategy, max_weight):
+    def forward(ctx, x, coef, rets, gamma_sqrt, alpha, strategy, max_weight, check_status, watch):
         _C.require_cuda(x, coef, rets, gamma_sqrt, alpha)
         lib = _C.lib()
         B, L, N = x.shape
@@ -650,16 +650,26 @@ class _CovMarkowitzFn(torch.autograd.Function):
         status = torch.empty((B,), dtype=torch.int32, device=x.device)
         ws = _workspace(_C.markowitz_workspace_bytes(B, N, dt), x.device)
         saved = _workspace(lib.ddw_markowitz_saved_bytes(B, N, dt), x.device) if any(ctx.needs_input_grad[:5]) else None
+        # address space for the rare portfolio that needs the interior-point fallback (which reads covmat_sqrt from HBM):
+        # never initialised, written only by such a portfolio
+        spill = torch.empty((B, N, N), dtype=x.dtype, device=x.device)
         with _C.device_guard(x):
             rc = lib.ddw_covariance_markowitz_fwd(_C.ptr(x_c), _C.ptr(coef_c), strategy, L, _C.ptr(rets_c), _C.ptr(gam_c), _C.ptr(alp_c),
                                                   float(max_weight), B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status), _C.ptr(ws),
-                                                  ws.numel(), _C.ptr(saved), 0 if saved is None else saved.numel(),
+                                                  ws.numel(), _C.ptr(saved), 0 if saved is None else saved.numel(), _C.ptr(spill),
                                                   _C.stream(x.device))
         if rc == -2:
             raise _FusedUnsupported()
         _C.check(rc, "ddw_covariance_markowitz_fwd")
-        if int(ws[8:12].view(torch.int32)):          # a portfolio needs the fallback solver, which wants covmat_sqrt in HBM
-            raise _FusedUnsupported()
+        what = f"batch of {B}, n_assets={N}, max_weight={max_weight} (fused covariance)"
+        counter = ws[8:12].view(torch.int32)
+        if check_status is True:
+            bad = int(counter)
+            if bad:
+                raise SolverError(f"{bad} portfolio problems could not be solved ({what})")
+        elif check_status == "lazy":
+            with _C.device_guard(x):
+                watch.push(counter, what)
         ctx.save_for_backward(x_c, coef_c, rets_c, gam_c, alp_c, w, state, saved)
         ctx.args = (strategy, float(max_weight))
         ctx.mark_non_differentiable(status)
@@ -696,11 +706,11 @@ class _CovMarkowitzFn(torch.autograd.Function):
             rc = lib.ddw_covariance_bwd(_C.ptr(d_cov), _C.ptr(x_c), _C.ptr(coef_c), strategy, 0, None, None, B, L, N, dt, _C.ptr(d_x),
                                         _C.ptr(d_coef), _C.ptr(cws), cws.numel(), st)
             _C.check(rc, "ddw_covariance_bwd")
-        return d_x, d_coef, d_rets, d_gamma, d_alpha, None, None
+        return d_x, d_coef, d_rets, d_gamma, d_alpha, None, None, None, None
 
 
 class _FusedUnsupported(Exception):
-    """The fused kernel cannot take this shape / batch: compose the two layers."""
+    """The fused kernel cannot take this shape: compose the two layers."""
 
 
 def covariance_markowitz(x, rets, gamma_sqrt, alpha, covariance_layer, allocator, shrinkage_coef=None):
@@ -708,7 +718,7 @@ def covariance_markowitz(x, rets, gamma_sqrt, alpha, covariance_layer, allocator
     ``NumericalMarkowitz`` -- BachelierNet's chain (deepdow/nn.py:170-171,189-191) -- through the fused kernel
     ``ddw_covariance_markowitz_fwd``: the (n_samples, n_assets, n_assets) matrix is formed in shared memory and never written
     to HBM in the forward.  Same results as the composition (the covariance tile is the same code); shapes the fused kernel
-    cannot take (n_assets > 128, long lookbacks) and batches that need the fallback solver run the composition."""
+    cannot take (n_assets > 128, long lookbacks) run the composition."""
     if covariance_layer.sqrt or x.shape[1] == 1 or not x.is_cuda:
         return allocator(rets, covariance_layer(x, shrinkage_coef), gamma_sqrt, alpha)
     n_samples = x.shape[0]
@@ -723,7 +733,8 @@ def covariance_markowitz(x, rets, gamma_sqrt, alpha, covariance_layer, allocator
         allocator._watch.poll()
     try:
         w, status = _CovMarkowitzFn.apply(x.to(dtype), coef, rets, gamma_sqrt.reshape(-1).to(dtype), alpha.reshape(-1).to(dtype),
-                                          _C.SHRINKAGE[covariance_layer.shrinkage_strategy], allocator.max_weight)
+                                          _C.SHRINKAGE[covariance_layer.shrinkage_strategy], allocator.max_weight,
+                                          allocator.check_status, allocator._watch)
     except _FusedUnsupported:
         return allocator(rets, covariance_layer(x, shrinkage_coef), gamma_sqrt, alpha)
     allocator.last_status = status

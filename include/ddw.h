@@ -108,15 +108,17 @@ int ddw_markowitz_bwd_saved(const void *grad_w, const void *w, const int8_t *sta
  * in shared memory (the code of ddw_covariance_fwd with do_sqrt = 0: same bits) and handed to the solver there, so the forward
  * reads L N + 2 N + 2 elements per portfolio instead of N^2 + 2 N + 2.  gamma_sqrt is applied with the reference's tiling as
  * in ddw_markowitz_fwd.  Returns DDW_ERR_UNSUPPORTED when the tile does not fit next to the solver (n_assets > 128 or a long
- * lookback): compose ddw_covariance_fwd and ddw_markowitz_fwd then.  A portfolio whose active set does not converge is left
- * DDW_STATUS_INEXACT (counter [2] of the workspace header) -- there is no covmat_sqrt in HBM for the interior-point fallback;
- * the host layer re-runs such a batch through the composed path.  `saved` (may be NULL) as in ddw_markowitz_fwd_saved; the
- * backward is ddw_covariance_fwd (recompute) + ddw_markowitz_bwd[_saved] + ddw_covariance_bwd. */
+ * lookback): compose ddw_covariance_fwd and ddw_markowitz_fwd then.  covmat_scratch: (B, N, N) elements of UNINITIALISED
+ * device memory: only a portfolio whose active set does not converge writes its covariance tile there, for the interior-point
+ * fallback (which reads covmat_sqrt from HBM); with NULL such a portfolio is left DDW_STATUS_INEXACT instead.  `saved` (may be
+ * NULL) as in ddw_markowitz_fwd_saved; the backward is ddw_covariance_fwd (recompute) + ddw_markowitz_bwd[_saved] +
+ * ddw_covariance_bwd. */
 int ddw_covariance_markowitz_fwd(const void *x, const void *coef, int strategy, int64_t L,
                                  const void *rets, const void *gamma_sqrt, const void *alpha,
                                  double max_weight, int64_t B, int64_t N, int dtype,
                                  void *w, int8_t *state, int32_t *status,
-                                 void *workspace, size_t workspace_bytes, void *saved, size_t saved_bytes, void *stream);
+                                 void *workspace, size_t workspace_bytes, void *saved, size_t saved_bytes,
+                                 void *covmat_scratch, void *stream);
 
 /* Chunked launches of the two calls above: the same kernels on the `B` consecutive problems that start at
  * index `batch_offset` of a batch of `batch_total` problems.  Every pointer addresses the chunk's first
@@ -163,6 +165,19 @@ int ddw_markowitz_host_step(ddw_host_pipeline *pipe,
                             void *h_w, int32_t *h_status,
                             void *h_d_rets, void *h_d_covmat_sqrt, void *h_d_gamma_sqrt, void *h_d_alpha,
                             void *dev_scratch, size_t dev_scratch_bytes, void *stream);
+
+/* The same step with the gradient of covmat_sqrt returned in FACTORED form: d_covmat_sqrt is rank 2 per portfolio,
+ *     d_covmat_sqrt[b, j, k] = -2 gamma_[b, j, k] * (p[b, j] w[b, k] + q[b, j] d_rets[b, k]),   p = A d, q = A w,
+ * so h_factors (B, 2, N) = (p, q) carries it in 2 N numbers instead of N^2 (1.6 KB instead of 40 KB at n_assets = 100): the
+ * device->host half of the transfer shrinks from 167 MB to 6.6 MB at B = 4096 and the caller forms the outer products where
+ * (and if) it needs them.  gamma_ is the reference's tiling (allocate.py:268-270).  Everything else as above. */
+int ddw_markowitz_host_step_factored(ddw_host_pipeline *pipe,
+                                     const void *h_rets, const void *h_covmat_sqrt, const void *h_gamma_sqrt,
+                                     const void *h_alpha, const void *h_grad_w,
+                                     double max_weight, int64_t B, int64_t N, int dtype, int64_t chunk,
+                                     void *h_w, int32_t *h_status,
+                                     void *h_d_rets, void *h_factors, void *h_d_gamma_sqrt, void *h_d_alpha,
+                                     void *dev_scratch, size_t dev_scratch_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * NumericalRiskBudgeting -- replaces self.cvxpylayer(covmat_sqrt, b)[0] (deepdow/layers/allocate.py:673-691; the

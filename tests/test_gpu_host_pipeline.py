@@ -28,10 +28,21 @@ def problems(B, N, seed, gamma="rand", dtype=np.float32):
 
 
 def device_reference(rets, C, g, a, G, u):
-    tt = [torch.tensor(x, device=DEV, requires_grad=True) for x in (rets, C, g, a)]
-    w = NumericalMarkowitz(rets.shape[1], u)(*tt)
-    grads = torch.autograd.grad(w, tt, torch.tensor(G, device=DEV))
-    return [w.detach().cpu()] + [x.cpu() for x in grads]
+    """One launch of ddw_markowitz_fwd + ddw_markowitz_bwd over the whole batch (the entry points the chunked calls and the
+    host pipeline are built from; the nn.Module itself takes the saved-factor pair, whose backward rounds differently)."""
+    lib = _C.lib()
+    tr, tC, tg, ta, tG = (torch.tensor(x, device=DEV) for x in (rets, C, g, a, G))
+    B, N = tr.shape
+    dt = _C.dtype_code(tr)
+    w = torch.empty_like(tr); state = torch.empty(B, N, dtype=torch.int8, device=DEV); status = torch.empty(B, dtype=torch.int32, device=DEV)
+    ws = torch.empty(lib.ddw_markowitz_workspace_bytes(B, N, dt), dtype=torch.uint8, device=DEV)
+    d_r, d_C, d_g, d_a = torch.empty_like(tr), torch.empty_like(tC), torch.empty_like(tg), torch.empty_like(ta)
+    _C.check(lib.ddw_markowitz_fwd(_C.ptr(tr), _C.ptr(tC), _C.ptr(tg), _C.ptr(ta), u, B, N, dt, _C.ptr(w), _C.ptr(state), _C.ptr(status),
+                                   _C.ptr(ws), ws.numel(), _C.stream()), "fwd")
+    _C.check(lib.ddw_markowitz_bwd(_C.ptr(tG), _C.ptr(w), _C.ptr(state), _C.ptr(tC), _C.ptr(tg), _C.ptr(ta), u, B, N, dt, _C.ptr(d_r),
+                                   _C.ptr(d_C), _C.ptr(d_g), _C.ptr(d_a), _C.ptr(ws), ws.numel(), _C.stream()), "bwd")
+    torch.cuda.synchronize()
+    return [x.cpu() for x in (w, d_r, d_C, d_g, d_a)]
 
 
 @pytest.mark.parametrize("B,N,u,chunk", [(96, 20, 0.3, 32), (70, 12, 1.0, 32), (50, 100, 0.2, 16), (33, 7, 0.5, 4)])
@@ -135,3 +146,26 @@ def test_module_streams_cpu_tensors_when_opted_in():
     import pickle
     layer2 = pickle.loads(pickle.dumps(layer))
     assert torch.equal(layer2(*[t.detach() for t in cpu]), ref[0])
+
+
+@pytest.mark.parametrize("B,N,u,chunk,dense", [(96, 20, 0.3, 32, False), (50, 100, 0.2, 16, False), (40, 100, 0.2, 16, True)])
+def test_host_pipeline_factored_gradient(B, N, u, chunk, dense):
+    """ddw_markowitz_host_step_factored: the rank-2 gradient of covmat_sqrt comes back as its factor vectors (2 N numbers per
+    portfolio); expanded on the host (with the reference's gamma tiling) it equals the dense gradient of the regular step, and
+    every other output is bit-identical."""
+    from deepdow_b200.host import expand_factored
+    rets, C, g, a, G = problems(B, N, 300 + B + N)
+    if dense:
+        rets = rets * 0.04
+    host = [torch.tensor(x).pin_memory() for x in (rets, C, g, a, G)]
+    pipe = MarkowitzHostPipeline(N, u, chunk=chunk, device=DEV)
+    full = pipe.step(*host)
+    fac = pipe.step(*host, factored=True)
+    fac2 = pipe.step(*host, factored=True, out=fac)           # second identical request: served by the cached CUDA graph
+    assert fac.factors.shape == (B, 2, N)
+    for name in ("w", "d_rets", "d_alpha", "status"):
+        assert torch.equal(getattr(full, name), getattr(fac2, name)), name
+    assert (full.d_gamma_sqrt - fac2.d_gamma_sqrt).abs().max() <= 1e-5 * max(1.0, float(full.d_gamma_sqrt.abs().max()))   # atomics
+    d_cov = expand_factored(fac2, host[2])
+    assert (d_cov - full.d_covmat_sqrt).abs().max() <= 1e-6 * max(1.0, float(full.d_covmat_sqrt.abs().max()))
+    pipe.close()

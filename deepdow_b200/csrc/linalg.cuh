@@ -457,4 +457,32 @@ __device__ __forceinline__ void fwdsub_warp(const T *Lb, int ld, int n, const T 
     }
 }
 
+// Two right-hand sides through the same forward substitution: the factor entries are loaded once and the two dependent
+// chains (shuffle -> multiply -> FMA) interleave, which is what a lone warp needs to hide their latency.
+template <typename T, int NREG>
+__device__ __forceinline__ void fwdsub2_warp(const T *Lb, int ld, int n, const T *dinv, T (&z1)[NREG], T (&z2)[NREG]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int mm = 0; mm < NREG; ++mm) {
+        if (mm * 32 >= n) continue;
+        const int ktop = min(n - mm * 32, 32);
+        for (int kk = 0; kk < ktop; ++kk) {
+            const int k = mm * 32 + kk;
+            const T di = dinv[k];
+            const T t1 = __shfl_sync(kFullMask, z1[mm], kk) * di, t2 = __shfl_sync(kFullMask, z2[mm], kk) * di;
+#pragma unroll
+            for (int m2 = 0; m2 < NREG; ++m2) {
+                if (m2 >= mm) {
+                    const int i = lane + 32 * m2;
+                    if (i > k && i < n) {
+                        const T l = Lb[k * ld + i];
+                        z1[m2] = fma(-l, t1, z1[m2]);
+                        z2[m2] = fma(-l, t2, z2[m2]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace ddw

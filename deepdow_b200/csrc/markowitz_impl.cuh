@@ -740,8 +740,7 @@ __global__ void __launch_bounds__(kThreads) markowitz_bwd_saved_kernel(MkBwdPara
             z1[m] = k < nF ? gv[idx[k]] : T(0);
             z2[m] = k < nF ? T(1) : T(0);
         }
-        fwdsub_warp<T, NREG>(Lb, ldl, nF, dinv, z1);
-        fwdsub_warp<T, NREG>(Lb, ldl, nF, dinv, z2);
+        fwdsub2_warp<T, NREG>(Lb, ldl, nF, dinv, z1, z2);      // both right-hand sides through one pass over the factor
         T s12 = T(0), s22 = T(0);
 #pragma unroll
         for (int m = 0; m < NREG; ++m) {

@@ -9,6 +9,8 @@ Argument meaning, error behaviour and output dtype/device follow the reference:
   Resample             deepdow/layers/allocate.py:276-411 (the caller that chains CovarianceMatrix(sqrt=True) into
                        NumericalMarkowitz; only its NumericalMarkowitz arm, the other allocators are out of scope)
 """
+import warnings
+
 import torch
 import torch.nn as nn
 
@@ -263,7 +265,6 @@ class NumericalMarkowitz(nn.Module):
             try:
                 watch.poll(block=True)
             except SolverError as exc:      # cannot raise from a finaliser: make the loss of the report visible at least
-                import warnings
                 warnings.warn(f"NumericalMarkowitz discarded with an unreported solver failure: {exc}")
             except Exception:               # interpreter shutdown: CUDA may already be gone
                 pass

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "libddw_b200.so")
 SOURCES = ["api.cu", "markowitz_fwd_sparse_f32.cu", "markowitz_fwd_sparse_f64.cu", "markowitz_bwd_sparse_f32.cu",
-           "markowitz_bwd_sparse_f64.cu", "markowitz_fwd_f32.cu", "markowitz_fwd_f64.cu", "markowitz_bwd_f32.cu", "markowitz_bwd_f64.cu", "markowitz_gram_tc.cu",
+           "markowitz_bwd_sparse_f64.cu", "markowitz_fwd_f32.cu", "markowitz_fwd_f64.cu", "markowitz_bwd_f32.cu", "markowitz_bwd_f64.cu", "markowitz_gram_tc.cu", "markowitz_qwarp.cu",
            "rowproj.cu", "covariance.cu", "eig_block.cu", "risk_budgeting.cu", "host_pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]

@@ -26,6 +26,11 @@ template <typename T> int launch_fwd_sparse(const MkFwdParams<T> &p, cudaStream_
 bool bwd_sparse_eligible(int N, int tsize, int smem_limit);
 template <typename T> int launch_bwd_sparse(const MkBwdParams<T> &p, cudaStream_t st);
 
+// markowitz_qwarp.cu: float32, n_assets <= 128 -- Q on tensor cores into an L2-resident scratch, then one warp per portfolio
+bool fwd_qwarp_eligible(int N, int tsize);
+size_t fwd_qwarp_scratch_bytes(long long B, int N);
+int launch_fwd_qwarp(const MkFwdParams<float> &p, float *Q, cudaStream_t st);
+
 // markowitz_gram_tc.cu: Q = A'A + |alpha| I on tensor cores into the global workspace (float32, Q beyond shared memory)
 int markowitz_gram_tc(const float *C, const float *gamma, const float *alpha, long long B, long long Bmod, long long b0, int N,
                       int LD, float *Q, cudaStream_t st);
@@ -939,6 +944,7 @@ size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
     if (pf.global_q) q = (size_t)B * N * pf.LD * tsize;
     if (pb.global_q) q = max(q, (size_t)B * N * pb.LD * tsize);
     bytes += align256(q);
+    if (fwd_qwarp_eligible(N, tsize)) bytes += align256(fwd_qwarp_scratch_bytes(B, N));     // Q scratch of the warp-per-portfolio forward
     return bytes;
 }
 
@@ -947,6 +953,7 @@ size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
 template <typename T> struct WsLayout {
     int *fail_count, *fail_list, *work_count, *work_list, *bad_count;
     T *ipm, *vecs, *q;
+    float *qs;        // Q scratch of markowitz_qwarp.cu (behind q)
 };
 template <typename T> static WsLayout<T> ws_layout(void *ws, long long B, int N) {
     const int NP = round_up(N + 2, 32);
@@ -961,13 +968,21 @@ template <typename T> static WsLayout<T> ws_layout(void *ws, long long B, int N)
     l.ipm = reinterpret_cast<T *>(p); p += align256((size_t)kIpmGrid * 8 * NP * sizeof(T));
     l.vecs = reinterpret_cast<T *>(p); p += align256((size_t)B * 2 * N * sizeof(T));
     l.q = reinterpret_cast<T *>(p);
+    {
+        const MkPlan pf = plan_fwd(N, sizeof(T)), pb = plan_bwd(N, sizeof(T));
+        size_t q = 0;
+        if (pf.global_q) q = (size_t)B * N * pf.LD * sizeof(T);
+        if (pb.global_q) q = max(q, (size_t)B * N * pb.LD * sizeof(T));
+        p += align256(q);
+    }
+    l.qs = reinterpret_cast<float *>(p);
     return l;
 }
 
 constexpr int kDenseListGrid = 4 * 148;
 
 template <typename T, int kThreads, int NREG, bool kGlobal, int MAXT>
-static int launch_fwd_variant(MkFwdParams<T> p, const MkPlan &pl, T *ipm_ws, bool sparse_first, cudaStream_t st) {
+static int launch_fwd_variant(MkFwdParams<T> p, const MkPlan &pl, T *ipm_ws, bool sparse_first, cudaStream_t st, float *qscratch = nullptr) {
     auto kf = markowitz_fwd_kernel<T, kThreads, NREG, kGlobal, MAXT>;
     auto ki = markowitz_ipm_kernel<T, kThreads, NREG, kGlobal>;
     static DeviceOnce configured;     // per template instance and per device
@@ -984,7 +999,13 @@ static int launch_fwd_variant(MkFwdParams<T> p, const MkPlan &pl, T *ipm_ws, boo
     if (sparse_first) {
         // small-support portfolios are finished by the sparse kernel (its own translation unit); the rest land
         // on work_list
-        if ((rc = launch_fwd_sparse<T>(p, st))) return rc;
+        bool done = false;
+        rc = 0;
+        if constexpr (sizeof(T) == 4) {
+            if (qscratch) { rc = launch_fwd_qwarp(p, qscratch, st); done = true; }
+        }
+        if (!done) rc = launch_fwd_sparse<T>(p, st);
+        if (rc) return rc;
         kf<<<(unsigned)min((long long)kDenseListGrid, p.B), kThreads, pl.smem, st>>>(p);
     } else {
         p.work_count = nullptr; p.work_list = nullptr;
@@ -1029,10 +1050,11 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
         if (pl.threads == 128) {
             // Gram tiles kept in registers: 1, 2, 3 or 5 tiles of 4x4 per thread (n_assets <= 60 / 88 / 108 / 128)
             const int mt = gram_tiles_per_thread(N, 128);
-            if (mt <= 1) return launch_fwd_variant<T, 128, 4, false, 1>(p, pl, l.ipm, sparse_first, st);
-            if (mt <= 2) return launch_fwd_variant<T, 128, 4, false, 2>(p, pl, l.ipm, sparse_first, st);
-            if (mt <= 3) return launch_fwd_variant<T, 128, 4, false, 3>(p, pl, l.ipm, sparse_first, st);
-            return launch_fwd_variant<T, 128, 4, false, 5>(p, pl, l.ipm, sparse_first, st);
+            float *qs = sparse_first && fwd_qwarp_eligible(N, sizeof(T)) ? l.qs : nullptr;
+            if (mt <= 1) return launch_fwd_variant<T, 128, 4, false, 1>(p, pl, l.ipm, sparse_first, st, qs);
+            if (mt <= 2) return launch_fwd_variant<T, 128, 4, false, 2>(p, pl, l.ipm, sparse_first, st, qs);
+            if (mt <= 3) return launch_fwd_variant<T, 128, 4, false, 3>(p, pl, l.ipm, sparse_first, st, qs);
+            return launch_fwd_variant<T, 128, 4, false, 5>(p, pl, l.ipm, sparse_first, st, qs);
         }
         if (pl.threads == 256) return launch_fwd_variant<T, 256, 8, false, 0>(p, pl, l.ipm, false, st);
     }

@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, ".")
 from deepdow_b200 import NumericalMarkowitz
 dev = "cuda:0"
-B, N, u = 4096, 100, 0.2
+B, N, u = int(os.environ.get("DDW_TIME_B", "4096")), 100, 0.2
 gen = torch.Generator(device=dev).manual_seed(4000)
 R = torch.randn(B, N, N, generator=gen, device=dev); C = (R @ R.transpose(1, 2) / N + 0.1 * torch.eye(N, device=dev)).contiguous()
 rets = torch.randn(B, N, generator=gen, device=dev) * 0.5; g = torch.ones(B, device=dev); a = torch.ones(B, device=dev)

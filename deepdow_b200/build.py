@@ -17,6 +17,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
 if os.environ.get("DDW_PHASE_TIMING"):      # debug build: per-phase cycle counters in the sparse kernels
     NVCC_FLAGS.append("-DDDW_PHASE_TIMING")
+if os.environ.get("DDW_GS_TIMING"):         # debug build: per-role cycle counters in the tensor-core Gram kernel
+    NVCC_FLAGS.append("-DDDW_GS_TIMING")
 
 
 def _nvcc():
@@ -52,7 +54,7 @@ def _deps(path, seen=None):
 def build(force=False, verbose=False):
     """Compile every .cu to an object (in parallel, only those whose own includes changed) and link the shared library."""
     # debug (phase-timing) objects live apart from the product objects, so the two flag sets never mix
-    objdir = os.path.join(HERE, "build_dbg" if os.environ.get("DDW_PHASE_TIMING") else "build")
+    objdir = os.path.join(HERE, "build_dbg" if os.environ.get("DDW_PHASE_TIMING") else ("build_gst" if os.environ.get("DDW_GS_TIMING") else "build"))
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     jobs = []

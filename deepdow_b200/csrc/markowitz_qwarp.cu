@@ -26,20 +26,30 @@ namespace ddw {
 // ------------------------------------------------------------------------------------------------------------------
 // (1) Gram kernel
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kGsThreads = 256;
-constexpr int kGsChunkK = 16;                       // k values per staged chunk = 2 MMA k-steps
-constexpr int kGsLbo = 128;                         // K-adjacent core matrices (8 rows x 16 B) are contiguous
-constexpr int kGsSbo = (kGsChunkK / 4) * kGsLbo + 16;   // 528 B between 8-row groups: the 16 B skew makes the staging stores conflict-free
+constexpr int kGsEpiWarps = 8;                      // epilogue: TMEM lane quadrant = warp % 4, column half = warp / 4
+constexpr int kGsStageWarps = 4;                    // staging: split A into TF32 hi / lo tiles; warps per group
+constexpr int kGsStageGroups = 2;                   // group g stages the chunks c % 2 == g of every portfolio
+constexpr int kGsStageThreads = kGsStageWarps * 32;
+constexpr int kGsStageAll = kGsStageGroups * kGsStageThreads;
+constexpr int kGsMmaWarp = kGsEpiWarps + kGsStageGroups * kGsStageWarps, kGsTmaWarp = kGsMmaWarp + 1;
+constexpr int kGsPollWarp = kGsTmaWarp + 1;         // watches the mbarriers for the MMA thread (see there)
+constexpr int kGsThreads = (kGsPollWarp + 1) * 32;  // 608
+constexpr int kGsRing = 4;                          // staged chunks in flight
+constexpr int kGsMaxRaw = 3;                        // raw A buffers (TMA prefetch depth)
+constexpr int kGsChunkK = 32;                       // k values per staged chunk = one 128-byte swizzle row = 4 MMA k-steps
+constexpr int kGsRowBytes = 128, kGsSbo = 8 * kGsRowBytes;   // K-major SWIZZLE_128B: 8-row atoms of 1024 B
+constexpr int kGsHead = 1024;                       // barriers and flags (keeps the tiles behind it 1024-byte aligned)
 
 struct GsLayout {
     int BN;                 // MMA N extent = n_assets rounded up to 16
-    int nraw;               // raw A buffers (2 when they fit next to a second CTA on the SM)
+    int nraw;               // raw A buffers
     unsigned raw_bytes;     // one raw buffer, rounded to 128 B
-    unsigned tile_bytes;    // one hi or lo tile: BN rows x 16 k
+    unsigned tile_bytes;    // one hi or lo tile: BN rows x 32 k
+    unsigned ring_bytes;    // kGsRing stages of {hi, lo} + the over-read pad
     unsigned total;         // dynamic shared memory of the kernel
     unsigned tmem_cols;
 };
-static inline GsLayout gs_layout(int N, int smem_per_sm) {
+static inline GsLayout gs_layout(int N, int smem_limit) {
     GsLayout l;
     l.BN = (N + 15) / 16 * 16;
     l.raw_bytes = (unsigned)(((size_t)N * N * 4 + 127) / 128 * 128);
@@ -47,22 +57,55 @@ static inline GsLayout gs_layout(int N, int smem_per_sm) {
     // the M = 128 operand reads 16 row groups of every tile: (16 - BN/8) groups past its end.  They land in the next tile of
     // the ring (finite or not, they only reach output rows >= BN, which nobody reads); the pad keeps the last tile's
     // over-read inside the allocation
-    const unsigned ring = 4 * l.tile_bytes + (unsigned)(16 - l.BN / 8) * kGsSbo;
-    const unsigned fixed = 1024 /* alignment slack */ + 128 /* barriers */ + 2048 /* partial column norms */ + ring;
-    l.nraw = (2 * (fixed + 2 * l.raw_bytes + 1024) <= (unsigned)smem_per_sm) ? 2 : 1;
+    l.ring_bytes = 2 * kGsRing * l.tile_bytes + (unsigned)(16 - l.BN / 8) * kGsSbo;
+    const unsigned fixed = 1024 /* alignment slack */ + kGsHead + l.ring_bytes;
+    int nraw = ((unsigned)smem_limit - fixed) / l.raw_bytes;
+    l.nraw = nraw > kGsMaxRaw ? kGsMaxRaw : (nraw < 1 ? 1 : nraw);
     l.total = fixed + l.nraw * l.raw_bytes;
-    const unsigned need = 2u * (unsigned)l.BN;
-    l.tmem_cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 256));
+    const unsigned need = 4u * (unsigned)l.BN;          // two accumulator buffers x {hi'hi, cross terms}
+    l.tmem_cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
     return l;
 }
 
 struct GsParams {
     const float *C, *gamma, *alpha;
-    float *Q, *diag;
+    float *Q;
     long long B, Bmod, b0;
     int N, LDQ, BN, nraw;
-    unsigned raw_bytes, tile_bytes, tmem_cols;
+    unsigned raw_bytes, tile_bytes, ring_bytes, tmem_cols;
+    int dbg;
 };
+
+// Polling wait (mbarrier.test_wait): the role warps hand work to each other every few hundred cycles, and the suspending
+// try_wait of common.cuh was measured to add about a microsecond per hand-over here (an empty pipeline skeleton took
+// 6.3 k cycles per portfolio).  Bounded like mbar_wait: a barrier that never completes traps instead of hanging the device.
+__device__ __forceinline__ void mbar_poll(unsigned long long *bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 26); ++spin) {
+        unsigned ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void stage_group_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kGsStageAll) : "memory"); }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
@@ -84,23 +127,22 @@ __device__ __forceinline__ void split_fast(float a, float &hi, float &lo) {
 
 // gamma tiling (allocate.py:268-270) in place, As[e] *= gamma[(gflat0 + e) % Bmod], with the gamma loads of four
 // 16-byte groups in flight at once (apply_gamma_tiling waits for every load before it issues the next)
-__device__ __forceinline__ void gamma_tiling_batched(float *As, int N, const float *__restrict__ gamma, long long gflat0, long long Bmod) {
-    const int tid = threadIdx.x;
+__device__ __forceinline__ void gamma_tiling_batched(float *As, int N, const float *__restrict__ gamma, long long gflat0, long long Bmod, int tid) {
     const unsigned uB = (unsigned)Bmod;
     if ((N & 3) == 0 && (uB & 3u) == 0u) {
         unsigned gi = (unsigned)((gflat0 + 4 * tid) % Bmod);
-        const unsigned gstep = (unsigned)((4 * kGsThreads) % Bmod);
+        const unsigned gstep = (unsigned)((4 * kGsStageAll) % Bmod);
         const int NN = N * N;
-        for (int e0 = 4 * tid; e0 < NN; e0 += 16 * kGsThreads) {
+        for (int e0 = 4 * tid; e0 < NN; e0 += 16 * kGsStageAll) {
             float4 g[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if (e0 + q * 4 * kGsThreads < NN) g[q] = __ldg(reinterpret_cast<const float4 *>(gamma + gi));
+                if (e0 + q * 4 * kGsStageAll < NN) g[q] = __ldg(reinterpret_cast<const float4 *>(gamma + gi));
                 gi += gstep; if (gi >= uB) gi -= uB;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int e = e0 + q * 4 * kGsThreads;
+                const int e = e0 + q * 4 * kGsStageAll;
                 if (e < NN) {
                     float4 a = *reinterpret_cast<float4 *>(As + e);
                     a.x *= g[q].x; a.y *= g[q].y; a.z *= g[q].z; a.w *= g[q].w;
@@ -110,202 +152,307 @@ __device__ __forceinline__ void gamma_tiling_batched(float *As, int N, const flo
         }
     } else {
         unsigned gi = (unsigned)((gflat0 + tid) % Bmod);
-        const unsigned gstep = (unsigned)(kGsThreads % Bmod);
-        for (int e = tid; e < N * N; e += kGsThreads) {
+        const unsigned gstep = (unsigned)(kGsStageAll % Bmod);
+        for (int e = tid; e < N * N; e += kGsStageAll) {
             As[e] *= __ldg(gamma + gi);
             gi += gstep; if (gi >= uB) gi -= uB;
         }
     }
 }
 
-__global__ void __launch_bounds__(kGsThreads, 2) markowitz_gram_small_kernel(GsParams p) {
+// Optional role timing (build with -DDDW_GS_TIMING, tools/gs_timing.py): one thread per role adds the cycles it spent in
+// each of its waits / work sections to a global table.  Compiled out of the product build.
+#ifdef DDW_GS_TIMING
+__device__ unsigned long long ddw_gs_cycles[16];
+__device__ long long ddw_gs_trace[4096];      // [role 0..3][portfolio 0..3][chunk 0..7][begin, end] of CTA 0
+#define GS_TR(role, it, c, e) do { if (blockIdx.x == 0 && (it) < 4) ddw_gs_trace[(((role) * 4 + (int)(it)) * 8 + (c)) * 2 + (e)] = clock64(); } while (0)
+#define GS_T0 long long gs_t0 = clock64();
+#define GS_T(id, cond) do { if (cond) { const long long gs_t1 = clock64(); atomicAdd(&ddw_gs_cycles[id], (unsigned long long)(gs_t1 - gs_t0)); gs_t0 = gs_t1; } } while (0)
+#else
+#define GS_T0
+#define GS_T(id, cond) do { } while (0)
+#define GS_TR(role, it, c, e) do { } while (0)
+#endif
+
+// Warp-specialised, one persistent CTA per SM:
+//   TMA warp       bulk copies of A (one per portfolio) into a ring of raw buffers, kGsMaxRaw portfolios ahead
+//   staging warps  gamma tiling, TF32 hi / lo split into a ring of kGsRing operand stages (K-major, 128-byte swizzle)
+//   MMA warp       one thread issues the 3xTF32 tcgen05.mma of every staged chunk into one of two TMEM accumulator buffers
+//   epilogue warps tcgen05.ld of the finished buffer -> coalesced stores of Q
+// The roles meet only through mbarriers (full / empty per ring slot), so the epilogue of portfolio p, the MMAs of p + 1 and
+// the staging of p + 2 overlap.
+__global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsParams p) {
     extern __shared__ unsigned char gs_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, BN = p.BN;
     // 1 KB alignment by an offset from the shared array itself: the pointers keep their address space (LDS / STS, not generic)
     unsigned char *base = gs_smem + ((1024u - (smem_u32(gs_smem) & 1023u)) & 1023u);
-    unsigned long long *bar_raw = reinterpret_cast<unsigned long long *>(base);          // [2]
-    unsigned long long *bar_done = bar_raw + 2;                                          // [2] ring stage drained
-    unsigned long long *bar_fin = bar_raw + 4;                                           // accumulators complete
-    uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(base + 64);
-    float *dpart = reinterpret_cast<float *>(base + 128);                                // [4][128] partial column norms
-    unsigned char *ring = base + 128 + 2048;
+    unsigned long long *raw_full = reinterpret_cast<unsigned long long *>(base);         // [kGsMaxRaw]
+    unsigned long long *raw_empty = raw_full + kGsMaxRaw;                                // [kGsMaxRaw]
+    unsigned long long *ring_full = raw_empty + kGsMaxRaw;                               // [kGsRing]
+    unsigned long long *ring_empty = ring_full + kGsRing;                                // [kGsRing]
+    unsigned long long *acc_full = ring_empty + kGsRing;                                 // [2]
+    unsigned long long *acc_empty = acc_full + 2;                                        // [2]
+    uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(base + 192);
+    unsigned *ready = reinterpret_cast<unsigned *>(base + 256);                          // chunks the MMA thread may issue (poller -> MMA)
+    unsigned char *ring = base + kGsHead;
     const unsigned stage_bytes = 2 * p.tile_bytes;
-    unsigned char *raw0 = ring + 2 * stage_bytes + (unsigned)(16 - BN / 8) * kGsSbo;
+    unsigned char *raw0 = ring + p.ring_bytes;
     const unsigned nn_bytes = (unsigned)(N * N * 4);
     const bool use_tma = (nn_bytes & 15u) == 0u && (reinterpret_cast<unsigned long long>(p.C) & 15ull) == 0ull;
 
     if (tid == 0) {
-        mbar_init(&bar_raw[0], 1); mbar_init(&bar_raw[1], 1); mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1);
-        mbar_init(bar_fin, 1);
+        for (int i = 0; i < kGsMaxRaw; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kGsStageGroups * kGsStageWarps); }
+        for (int i = 0; i < kGsRing; ++i) { mbar_init(&ring_full[i], kGsStageWarps); mbar_init(&ring_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kGsEpiWarps); }
+        *ready = 0u;
         fence_mbar_init();
     }
     // rows >= n_assets of the tiles are never written again: zero the whole ring once
-    for (unsigned e = tid * 16u; e < 2 * stage_bytes + (unsigned)(16 - BN / 8) * kGsSbo; e += kGsThreads * 16u)
+    for (unsigned e = tid * 16u; e < p.ring_bytes; e += kGsThreads * 16u)
         *reinterpret_cast<float4 *>(ring + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, p.tmem_cols);
+    if (warp == kGsMmaWarp) tc::tmem_alloc(&tmem_slot, p.tmem_cols);
+    // gamma_sqrt the same for the whole batch (the usual case: a learned scalar, repeated): Q = gamma^2 A'A, scaled in the
+    // epilogue, and the in-place tiling pass over A is skipped
+    int gsame = p.Bmod <= (1 << 16);
+    if (gsame) {
+        const float g0 = __ldg(p.gamma);
+        for (long long i = tid; i < p.Bmod; i += kGsThreads) gsame &= __ldg(p.gamma + i) == g0;
+    }
     tc::fence_before_sync();
-    __syncthreads();
+    const bool gunif = __syncthreads_and(gsame) != 0;
     tc::fence_after_sync();
+    const float gsq = gunif ? __ldg(p.gamma) * __ldg(p.gamma) : 1.f;
     const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = tc::idesc_tf32(128, BN);
-
     const long long b_first = blockIdx.x, b_step = gridDim.x;
-    // prefetch the first (two) portfolios
-    if (use_tma && tid == 0) {
-        for (int q = 0; q < p.nraw; ++q) {
-            const long long b = b_first + q * b_step;
-            if (b < p.B) {
-                mbar_expect_tx(&bar_raw[q], nn_bytes);
-                tma_bulk_g2s(raw0 + (size_t)q * p.raw_bytes, p.C + b * (long long)N * N, nn_bytes, &bar_raw[q]);
+    const int nchunks = (N + kGsChunkK - 1) / kGsChunkK;
+
+    if (warp == kGsTmaWarp) {
+        // ---------------- TMA producer
+        if (use_tma) {
+            long long it = 0;
+            for (long long b = b_first; b < p.B; b += b_step, ++it) {
+                if (lane == 0) {
+                    GS_T0
+                    const int buf = (int)(it % p.nraw);
+                    const long long use = it / p.nraw;
+                    if (use > 0) mbar_wait(&raw_empty[buf], (unsigned)((use - 1) & 1));
+                    GS_T(0, true);
+                    mbar_expect_tx(&raw_full[buf], nn_bytes);
+                    tma_bulk_g2s(raw0 + (size_t)buf * p.raw_bytes, p.C + b * (long long)N * N, nn_bytes, &raw_full[buf]);
+                }
+                __syncwarp();
             }
         }
-    }
-    const int nchunks = (N + kGsChunkK - 1) / kGsChunkK;
-    unsigned gchunk = 0;          // chunks staged so far by this CTA (ring position)
-    long long it = 0;             // portfolios processed so far by this CTA
-    // staging.  Fast path (n_assets % 4 == 0): thread = (quad of operand rows 4 rq .. 4 rq + 3, k group k4 of the chunk): four
-    // 16-byte loads of A (one per k), split, four 16-byte stores per tile (one per row) -- the 4 x 4 transpose is register
-    // naming only.  Generic path: thread = (row r, k groups kh and kh + 2), scalar loads.
-    const bool quads = (N & 3) == 0;
-    const int N4 = N >> 2;
-    const int rq = quads ? tid % max(N4, 1) : 0, qk4 = quads ? tid / max(N4, 1) : 4;
-    const int r = tid & 127, kh = tid >> 7;
-    const unsigned soff = (unsigned)((r >> 3) * kGsSbo + (r & 7) * 16 + kh * kGsLbo);
-    const unsigned qoff = (unsigned)((rq >> 1) * kGsSbo + (rq & 1) * 64 + qk4 * kGsLbo);
-    // epilogue: this thread's TMEM lane = row m of Q, the two warp groups split the columns
-    const int m = 32 * (warp & 3) + lane;
-    const int half = (BN / 2 + 7) / 8 * 8;
-    const int cbeg = (warp >> 2) * half, cend = min(min(BN, cbeg + half), (N + 7) / 8 * 8);
-    const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-    for (long long b = b_first; b < p.B; b += b_step, ++it) {
-        const int rb = p.nraw == 2 ? (int)(it & 1) : 0;
-        float *raw = reinterpret_cast<float *>(raw0 + (size_t)rb * p.raw_bytes);
-        if (use_tma) mbar_wait(&bar_raw[rb], (unsigned)((p.nraw == 2 ? it >> 1 : it) & 1));
-        else {
-            const float *Cb = p.C + b * (long long)N * N;
-            for (int e = tid; e < N * N; e += kGsThreads) raw[e] = Cb[e];
-            __syncthreads();
-        }
-        gamma_tiling_batched(raw, N, p.gamma, (p.b0 + b) * (long long)N * N, p.Bmod);
-        __syncthreads();
-        float dacc[4] = {0.f, 0.f, 0.f, 0.f};        // sum of squares of this thread's elements: partial diag(Q) in plain FP32
-        for (int c = 0; c < nchunks; ++c, ++gchunk) {
-            const unsigned s = gchunk & 1u;
-            unsigned char *hi = ring + s * stage_bytes, *lo = hi + p.tile_bytes;
-            const int kleft = N - c * kGsChunkK;                 // k values of this chunk that exist
-            const int ksteps = kleft > 8 ? 2 : 1;                // 8-wide MMA k-steps to issue
-            if (gchunk >= 2) mbar_wait(&bar_done[s], ((gchunk >> 1) + 1u) & 1u);     // the MMAs that read this stage have drained
-            if (quads) {
-                if (qk4 < 2 * ksteps) {
-                    float4 a[4];
-                    const int k = c * kGsChunkK + 4 * qk4;
-                    if (k < N) {
-                        const float *src = raw + k * N + 4 * rq;
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) a[kk] = *reinterpret_cast<const float4 *>(src + kk * N);
-                    } else {
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) a[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (warp == kGsMmaWarp) {
+        // ---------------- MMA issuer
+        const uint32_t idesc = tc::idesc_tf32(128, BN);
+        // K-major SWIZZLE_128B descriptor: start address >> 4 | LBO field 1 | SBO = 1024 B | version 1 | layout type 2.
+        // Descriptors of the stages, tiles and k-steps differ only in the 14-bit address field: one add per operand and MMA.
+        const uint64_t desc0 = (uint64_t)((smem_u32(ring) >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(kGsSbo >> 4) << 32) |
+                               (1ull << 46) | (2ull << 61);
+        const uint64_t dstage = stage_bytes >> 4, dtile = p.tile_bytes >> 4;
+        // A tcgen05.commit is handed to the tensor pipe, and every later mbarrier operation of the SAME thread was measured to
+        // wait until that commit has fired, i.e. until the MMAs before it are done (~600 idle cycles after every chunk: the
+        // pipe drained while this thread sat in a poll that was already satisfied).  So this thread never touches an mbarrier:
+        // the poller warp waits for "accumulator free" and "stage full" and publishes the number of chunks that may be issued.
+        unsigned g = 0;
+        long long it = 0;
+        for (long long b = b_first; b < p.B; b += b_step, ++it) {
+            if (lane == 0) {
+                const unsigned tb = (unsigned)(it & 1);
+                GS_T0
+                const uint32_t acc = tmem + tb * 2u * (uint32_t)BN;
+                for (int c = 0; c < nchunks; ++c, ++g) {
+                    const unsigned s = g % kGsRing;
+                    for (int spin = 0; ; ++spin) {
+                        unsigned have;
+                        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(have) : "r"(smem_u32(ready)) : "memory");
+                        if (have > g) break;
+                        if (spin > (1 << 26)) __trap();
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 vh, vl;
-                        const float e0 = q == 0 ? a[0].x : (q == 1 ? a[0].y : (q == 2 ? a[0].z : a[0].w));
-                        const float e1 = q == 0 ? a[1].x : (q == 1 ? a[1].y : (q == 2 ? a[1].z : a[1].w));
-                        const float e2 = q == 0 ? a[2].x : (q == 1 ? a[2].y : (q == 2 ? a[2].z : a[2].w));
-                        const float e3 = q == 0 ? a[3].x : (q == 1 ? a[3].y : (q == 2 ? a[3].z : a[3].w));
-                        split_fast(e0, vh.x, vl.x); split_fast(e1, vh.y, vl.y); split_fast(e2, vh.z, vl.z); split_fast(e3, vh.w, vl.w);
-                        dacc[q] = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, dacc[q]))));
-                        *reinterpret_cast<float4 *>(hi + qoff + q * 16) = vh;
-                        *reinterpret_cast<float4 *>(lo + qoff + q * 16) = vl;
+                    if (c == 0) tc::fence_after_sync();        // the epilogue's tcgen05.ld of this buffer are ordered before the MMAs
+                    GS_T(2, true);
+                    GS_TR(2, it, c, 0);
+                    uint64_t dh = desc0 + s * dstage, dl = dh + dtile;
+                    const int ksteps = min(4, (N - c * kGsChunkK + 7) >> 3);
+                    for (int kk = 0; kk < ksteps; ++kk, dh += 2, dl += 2) {      // 8 k values = 32 B along the swizzle row
+                        const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
+                        tc::mma_tf32(acc + BN, dl, dh, idesc, first);        // cross terms: lo' hi + hi' lo
+                        tc::mma_tf32(acc + BN, dh, dl, idesc, 1u);
+                        tc::mma_tf32(acc, dh, dh, idesc, first);             // hi' hi
                     }
+                    tc::mma_commit(&ring_empty[s]);
+                    if (c == nchunks - 1) tc::mma_commit(&acc_full[tb]);
+                    GS_T(3, true);
+                    GS_TR(2, it, c, 1);
                 }
-            } else if (r < N) {
-                const float *src = raw + (c * kGsChunkK + 4 * kh) * N + r;
+            }
+            __syncwarp();
+        }
+    } else if (warp == kGsPollWarp) {
+        // ---------------- poller: mbarrier waits on behalf of the MMA thread
+        unsigned g = 0;
+        long long it = 0;
+        for (long long b = b_first; b < p.B; b += b_step, ++it) {
+            if (lane == 0) {
+                const unsigned tb = (unsigned)(it & 1);
+                const long long ut = it >> 1;
+                if (ut > 0) mbar_poll(&acc_empty[tb], (unsigned)((ut - 1) & 1));      // the epilogue has read this buffer
+                for (int c = 0; c < nchunks; ++c, ++g) {
+                    mbar_poll(&ring_full[g % kGsRing], (g / kGsRing) & 1u);           // (the stagers' fence.proxy.async made their stores visible to the MMA)
+                    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(ready)), "r"(g + 1u) : "memory");
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp >= kGsEpiWarps) {
+        // ---------------- staging
+        const int sta = tid - kGsEpiWarps * 32;                  // index among all staging threads (gamma pass, release)
+        const int grp = sta / kGsStageThreads, st = sta % kGsStageThreads;
+        // Element (row r, k) of a tile lives at (r / 8) * 1024 + (r % 8) * 128 + (((k / 4) ^ (r % 8)) * 16) + (k % 4) * 4.
+        // Fast path (n_assets % 4 == 0): an item = (quad of operand rows 4 rq .. 4 rq + 3, k group k4 of the chunk): four 16-byte
+        // loads of A (one per k), split, four 16-byte stores per tile (one per row); the 4 x 4 transpose is register naming.
+        // Eight consecutive items = {k4 & 3} x {rq & 1}, which spreads a quarter-warp's stores over all eight 16-byte columns.
+        // Generic path: thread = operand row, scalar loads.
+        const bool quads = (N & 3) == 0;
+        const int N4 = N >> 2, nitems = 16 * ((N4 + 1) >> 1);
+        unsigned g = 0;
+        long long it = 0;
+        for (long long b = b_first; b < p.B; b += b_step, ++it) {
+            const int buf = (int)(it % p.nraw);
+            const long long use = it / p.nraw;
+            float *raw = reinterpret_cast<float *>(raw0 + (size_t)buf * p.raw_bytes);
+            GS_T0
+            if (use_tma) mbar_poll(&raw_full[buf], (unsigned)(use & 1));
+            else {
+                const float *Cb = p.C + b * (long long)N * N;
+                stage_group_sync();                // every chunk of the previous portfolio has been read
+                for (int e = sta; e < N * N; e += kGsStageAll) raw[e] = Cb[e];
+                stage_group_sync();
+            }
+            GS_T(5, sta == 0);
+            if (!gunif) {
+                gamma_tiling_batched(raw, N, p.gamma, (p.b0 + b) * (long long)N * N, p.Bmod, sta);
+                stage_group_sync();
+            }
+            GS_T(6, sta == 0);
+            for (int c = 0; c < nchunks; ++c, ++g) {
+                if ((c & 1) != grp) continue;                        // the other group's chunk
+                const unsigned s = g % kGsRing, u4 = g / kGsRing;
+                unsigned char *hi = ring + s * stage_bytes, *lo = hi + p.tile_bytes;
+                const int kleft = N - c * kGsChunkK;                 // k values of this chunk that exist
+                const int kgroups = 2 * min(4, (kleft + 7) >> 3);    // 4-wide k groups the MMAs of this chunk read
+                if (u4 > 0) mbar_poll(&ring_empty[s], (u4 - 1u) & 1u);               // the MMAs that read this stage have drained
+                GS_T(7, sta == 0);
+                if (st == 0) GS_TR(grp, it, c, 0);
+                if (quads) {
+                    for (int e = st; e < nitems; e += kGsStageThreads) {
+                        const int w = e & 15, k4 = (w & 3) + 4 * (w >> 3), rq = 2 * (e >> 4) + ((w >> 2) & 1);
+                        if (rq >= N4 || k4 >= kgroups) continue;
+                        float4 a[4];
+                        if (4 * k4 < kleft) {
+                            const float *src = raw + (c * kGsChunkK + 4 * k4) * N + 4 * rq;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int kk = 4 * kh + 8 * h;               // first k of this item inside the chunk
-                    if (h < ksteps) {
-                        float v0, v1, v2, v3;
-                        if (kk + 3 < kleft) { v0 = src[0]; v1 = src[N]; v2 = src[2 * N]; v3 = src[3 * N]; }
-                        else {
-                            v0 = kk < kleft ? src[0] : 0.f; v1 = kk + 1 < kleft ? src[N] : 0.f;
-                            v2 = kk + 2 < kleft ? src[2 * N] : 0.f; v3 = 0.f;
+                            for (int kk = 0; kk < 4; ++kk) a[kk] = *reinterpret_cast<const float4 *>(src + kk * N);
+                        } else {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) a[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
+                        const unsigned rbase = (unsigned)((rq >> 1) * kGsSbo + (rq & 1) * 4 * kGsRowBytes);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float4 vh, vl;
+                            const float e0 = q == 0 ? a[0].x : (q == 1 ? a[0].y : (q == 2 ? a[0].z : a[0].w));
+                            const float e1 = q == 0 ? a[1].x : (q == 1 ? a[1].y : (q == 2 ? a[1].z : a[1].w));
+                            const float e2 = q == 0 ? a[2].x : (q == 1 ? a[2].y : (q == 2 ? a[2].z : a[2].w));
+                            const float e3 = q == 0 ? a[3].x : (q == 1 ? a[3].y : (q == 2 ? a[3].z : a[3].w));
+                            split_fast(e0, vh.x, vl.x); split_fast(e1, vh.y, vl.y); split_fast(e2, vh.z, vl.z); split_fast(e3, vh.w, vl.w);
+                            const unsigned r7 = (unsigned)(4 * (rq & 1) + q);
+                            const unsigned off = rbase + q * kGsRowBytes + ((unsigned)k4 ^ r7) * 16u;
+                            *reinterpret_cast<float4 *>(hi + off) = vh;
+                            *reinterpret_cast<float4 *>(lo + off) = vl;
+                        }
+                    }
+                } else if (st < N) {
+                    const float *src = raw + c * kGsChunkK * N + st;
+                    const unsigned rbase = (unsigned)((st >> 3) * kGsSbo + (st & 7) * kGsRowBytes);
+                    for (int k4 = 0; k4 < kgroups; ++k4, src += 4 * N) {
+                        const int kk = 4 * k4;                       // first k of this item inside the chunk
+                        const float v0 = kk < kleft ? src[0] : 0.f, v1 = kk + 1 < kleft ? src[N] : 0.f;
+                        const float v2 = kk + 2 < kleft ? src[2 * N] : 0.f, v3 = kk + 3 < kleft ? src[3 * N] : 0.f;
                         float4 vh, vl;
                         split_fast(v0, vh.x, vl.x); split_fast(v1, vh.y, vl.y); split_fast(v2, vh.z, vl.z); split_fast(v3, vh.w, vl.w);
-                        dacc[0] = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, dacc[0]))));
-                        *reinterpret_cast<float4 *>(hi + soff + h * 2 * kGsLbo) = vh;
-                        *reinterpret_cast<float4 *>(lo + soff + h * 2 * kGsLbo) = vl;
-                        src += 8 * N;
+                        const unsigned off = rbase + ((unsigned)k4 ^ (unsigned)(st & 7)) * 16u;
+                        *reinterpret_cast<float4 *>(hi + off) = vh;
+                        *reinterpret_cast<float4 *>(lo + off) = vl;
                     }
                 }
+                GS_T(8, sta == 0);
+                fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ring_full[s]);        // one arrival per warp: 128 arrivals on one barrier word serialise
+                GS_T(9, sta == 0);
+                if (st == 0) GS_TR(grp, it, c, 1);
             }
-            fence_proxy_async();
-            __syncthreads();
-            if (tid == 0) {
-                tc::fence_after_sync();
-                const uint32_t a_hi = smem_u32(hi), a_lo = a_hi + p.tile_bytes;
-                for (int kk = 0; kk < ksteps; ++kk) {
-                    const uint32_t o = kk * 2 * kGsLbo;
-                    const uint64_t dh = tc::smem_desc(a_hi + o, kGsLbo, kGsSbo), dl = tc::smem_desc(a_lo + o, kGsLbo, kGsSbo);
-                    const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
-                    tc::mma_tf32(tmem + BN, dl, dh, idesc, first);        // cross terms: lo' hi + hi' lo
-                    tc::mma_tf32(tmem + BN, dh, dl, idesc, 1u);
-                    tc::mma_tf32(tmem, dh, dh, idesc, first);             // hi' hi
-                }
-                tc::mma_commit(&bar_done[s]);
-                if (c == nchunks - 1) tc::mma_commit(bar_fin);
+            if (use_tma) {
+                fence_proxy_async();               // the in-place gamma scaling is ordered before the next bulk copy into this buffer
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&raw_empty[buf]);
             }
+            GS_T(10, sta == 0);
         }
-        // raw[rb] is free (every thread staged its last chunk before the barrier above): fetch the portfolio that uses it next
-        if (use_tma && tid == 0) {
-            const long long bn = b + (long long)p.nraw * b_step;
-            if (bn < p.B) {
-                fence_proxy_async();        // the in-place gamma scaling (generic proxy) is ordered before the bulk copy's writes
-                mbar_expect_tx(&bar_raw[rb], nn_bytes);
-                tma_bulk_g2s(raw, p.C + bn * (long long)N * N, nn_bytes, &bar_raw[rb]);
-            }
-        }
-        // diag(Q) = column norms of A, combined over the k groups (the warm start of the solver reads this compact array)
-        if (quads) {
-            if (qk4 < 4) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) dpart[qk4 * 128 + 4 * rq + q] = dacc[q];
-            }
-        } else if (r < N) dpart[kh * 128 + r] = dacc[0];
-        __syncthreads();
-        if (tid < N) p.diag[b * N + tid] = quads ? (dpart[tid] + dpart[128 + tid]) + (dpart[256 + tid] + dpart[384 + tid]) : dpart[tid] + dpart[128 + tid];
-        // epilogue: row m of Q = hi'hi + cross terms, 8 columns per step
-        mbar_wait(bar_fin, (unsigned)(it & 1));
-        tc::fence_after_sync();
-        if (32 * (warp & 3) < N) {
-            // stored transposed (Q is symmetric): a warp writes 32 consecutive floats of row n per instruction
-            float *qcol = p.Q + (b * (long long)N + cbeg) * p.LDQ + m;
-            const int ldq = p.LDQ;
+    } else {
+        // ---------------- epilogue: thread = TMEM lane = row m of Q, the two warp groups split the columns.  Stored transposed
+        // (Q is symmetric): a warp writes 32 consecutive floats of row n per instruction.
+        const int m = 32 * (warp & 3) + lane;
+        const int half = (BN / 2 + 7) / 8 * 8;
+        const int cbeg = (warp >> 2) * half, cend = min(min(BN, cbeg + half), (N + 7) / 8 * 8);
+        const int ldq = p.LDQ;
+        long long it = 0;
+        for (long long b = b_first; b < p.B; b += b_step, ++it) {
+            const unsigned tb = (unsigned)(it & 1);
+            GS_T0
+            mbar_wait(&acc_full[tb], (unsigned)((it >> 1) & 1));
+            tc::fence_after_sync();
+            GS_T(11, tid == 0);
+            if (tid == 0) GS_TR(3, it, 0, 0);
+            if (32 * (warp & 3) < N && !(p.dbg & 2)) {
+                const uint32_t lane_addr = tmem + tb * 2u * (uint32_t)BN + ((uint32_t)(32 * (warp & 3)) << 16);
+                float *qcol = p.Q + (b * (long long)N + cbeg) * ldq + m;
 #pragma unroll 1
-            for (int c0 = cbeg; c0 < cend; c0 += 8, qcol += 8 * ldq) {
-                float h8[8], x8[8];
-                tmem_ld8(lane_addr + (uint32_t)c0, h8);
-                tmem_ld8(lane_addr + (uint32_t)(BN + c0), x8);
-                if (m < N) {
-                    if (c0 + 8 <= N) {
+                for (int c0 = cbeg; c0 < cend; c0 += 16, qcol += 16 * ldq) {
+                    float h[16], x[16];
+                    const bool two = c0 + 8 < cend;
+                    tmem_ld8_nowait(lane_addr + (uint32_t)c0, *reinterpret_cast<float(*)[8]>(&h[0]));
+                    tmem_ld8_nowait(lane_addr + (uint32_t)(BN + c0), *reinterpret_cast<float(*)[8]>(&x[0]));
+                    if (two) {
+                        tmem_ld8_nowait(lane_addr + (uint32_t)(c0 + 8), *reinterpret_cast<float(*)[8]>(&h[8]));
+                        tmem_ld8_nowait(lane_addr + (uint32_t)(BN + c0 + 8), *reinterpret_cast<float(*)[8]>(&x[8]));
+                    }
+                    tmem_ld_wait();
+                    if (m < N) {
+                        if (two && c0 + 16 <= N) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) qcol[j * ldq] = h8[j] + x8[j];
-                    } else {
+                            for (int j = 0; j < 16; ++j) qcol[j * ldq] = gsq * (h[j] + x[j]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (c0 + j < N) qcol[j * ldq] = h8[j] + x8[j];
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < N && (j < 8 || two)) qcol[j * ldq] = gsq * (h[j] + x[j]);
+                        }
                     }
                 }
             }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[tb]);
+            GS_T(12, tid == 0);
+            if (tid == 0) GS_TR(3, it, 0, 1);
         }
-        tc::fence_before_sync();
-        __syncthreads();          // accumulators read: the next portfolio's first MMA may overwrite them
-        tc::fence_after_sync();
     }
-    if (warp == 0) tc::tmem_dealloc(tmem, p.tmem_cols);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == kGsMmaWarp) tc::tmem_dealloc(tmem, p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -314,9 +461,10 @@ __global__ void __launch_bounds__(kGsThreads, 2) markowitz_gram_small_kernel(GsP
 constexpr int kQwFree = 32;            // largest reduced system (one row per lane)
 constexpr int kQwLd = 33;              // row stride of the multiplier array (conflict-free rows and columns)
 constexpr int kQwAssets = 4;           // assets per lane: n_assets <= 128
+constexpr int kQwTrim = 8;             // largest overflow of the frame that is trimmed instead of handed to the dense kernel
 
 struct QwParams {
-    const float *rets, *Q, *diag, *alpha;
+    const float *rets, *Q, *alpha;
     float u;
     long long B;
     int N, LDQ;
@@ -387,7 +535,7 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
     int st[kQwAssets], slot[kQwAssets];
     bool in[kQwAssets];
     // ---- warm start: safeguarded Newton on the multiplier of the separable problem with diag(Q) (diag_init_warp)
-    float dmax = 0.f;
+    float dmax = 0.f, nu0 = 0.f;
     {
         float lo = Num<float>::inf(), hi = -Num<float>::inf(), sa = 0.f, sb = 0.f;
 #pragma unroll
@@ -396,7 +544,7 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
             in[m] = i < N;
             rr[m] = 0.f; i2q[m] = 0.f; wv[m] = 0.f; st[m] = 2; slot[m] = -1;
             if (in[m]) {
-                float q = p.diag[b * N + i] + aabs;
+                float q = Qb[i * LDQ + i] + aabs;
                 rr[m] = p.rets[b * N + i];
                 rs[i] = rr[m];
                 dmax = fmaxf(dmax, q);
@@ -440,10 +588,11 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
                 const float v = (rr[m] - nu) * i2q[m];
                 st[m] = v <= 0.f ? -1 : (v >= u ? 1 : 0);
             }
+        nu0 = nu;
     }
     const float dmin = 4.f * Num<float>::eps() * dmax + Num<float>::tiny();
     const float tolw = 8.f * Num<float>::eps();
-    int lifted = 0, converged = 0, bail = 0;
+    int lifted = 0, converged = 0, bail = 0, trimmed = 0;
     unsigned phase = 0;
 #pragma unroll 1
     for (int iter = 0; iter < kMaxPdas; ++iter) {
@@ -457,7 +606,37 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
             pos[m] = nF + __popc(mf & lt);
             nF += __popc(mf); nU += __popc(mu[m]);
         }
-        if (nF + nU > kQwFree) { bail = 1; break; }
+        // the same in every lane -- said in a way the compiler can see (a broadcast from lane 0 is warp-uniform by construction):
+        // without it every shuffle below is compiled a second time in its slow divergent-safe form and the kernel no longer
+        // fits the instruction cache
+        nF = __shfl_sync(kFullMask, nF, 0); nU = __shfl_sync(kFullMask, nU, 0);
+#pragma unroll
+        for (int m = 0; m < kQwAssets; ++m) mu[m] = __shfl_sync(kFullMask, mu[m], 0);
+        if (nF + nU > kQwFree) {
+            // A slightly oversized free set (the warm start overshoots: 22.6 free assets on average against 19.3 at the optimum
+            // of the headline workload) is cut down to the frame instead of handing the portfolio to the dense kernel, whose
+            // latency for a handful of portfolios is as long as this whole kernel: the free assets with the smallest weights go
+            // to the lower bound, and the iteration frees them again if their gradient says so.  The converged point is the same
+            // KKT point; only the path differs.  Anything larger, or a second overflow, is the dense kernel's.
+            const int drop = nF + nU - kQwFree;
+            if (drop > kQwTrim || trimmed) { bail = 1; break; }
+            trimmed = 1;
+            for (int d = 0; d < drop; ++d) {
+                float best = Num<float>::inf();
+                int bi = 0x7fffffff;
+#pragma unroll
+                for (int m = 0; m < kQwAssets; ++m) {
+                    const float key = iter == 0 ? (rr[m] - nu0) * i2q[m] : wv[m];
+                    if (st[m] == 0 && key < best) { best = key; bi = lane + 32 * m; }
+                }
+                warp_argmin(best, bi);
+#pragma unroll
+                for (int m = 0; m < kQwAssets; ++m)
+                    if (lane + 32 * m == bi) st[m] = -1;
+            }
+            --iter;                                         // lists again with the trimmed set (not an active-set iteration)
+            continue;
+        }
         const int k0 = kQwFree - nF;                       // the reduced system occupies lanes / registers k0 .. 31
         // ---- (b) rows of Q of the free and capped assets -> shared memory: one bulk copy per NEW asset (TMA), the slot of an
         // asset that left both sets is handed on.  The solver itself then never waits on global memory.
@@ -479,6 +658,7 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
                 if (need) slot[m] = (int)__fns(freem, 0, nnew + __popc(needm[m] & lt) + 1);
                 nnew += __popc(needm[m]);
             }
+            nnew = __shfl_sync(kFullMask, nnew, 0);
             __syncwarp();                                  // every read of the slots that are handed on has been issued
             if (nnew > 0) {
                 if (lane == 0) mbar_expect_tx(mbar, (unsigned)nnew * row_bytes);
@@ -654,25 +834,38 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
     }
 }
 
+#ifdef DDW_GS_TIMING
+}  // namespace ddw
+extern "C" int ddw_debug_gs_phases(unsigned long long *out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, ddw::ddw_gs_cycles, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(ddw::ddw_gs_cycles, z, sizeof(z)); }
+    return 0;
+}
+extern "C" int ddw_debug_gs_trace(long long *out4096) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out4096, ddw::ddw_gs_trace, sizeof(long long) * 4096);
+    return 0;
+}
+namespace ddw {
+#endif
+
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 bool fwd_qwarp_eligible(int N, int tsize) {
-    static const bool on = getenv("DDW_QWARP") != nullptr;      // work in progress: opt-in until it beats the one-CTA-per-portfolio kernel
-    return on && tsize == 4 && N >= 8 && N <= 128;
+    static const bool off = getenv("DDW_NO_QWARP") != nullptr;      // A/B switch: the one-CTA-per-portfolio kernel instead
+    return !off && tsize == 4 && N >= 8 && N <= 128;
 }
 int fwd_qwarp_ldq(int N) { return (N + 7) / 8 * 8; }     // rows of the scratch start on 32-byte sectors
-// Q (B x N x LDQ) followed by diag(Q) (B x N)
-size_t fwd_qwarp_scratch_bytes(long long B, int N) { return (size_t)B * N * (fwd_qwarp_ldq(N) + 1) * sizeof(float); }
+size_t fwd_qwarp_scratch_bytes(long long B, int N) { return (size_t)B * N * fwd_qwarp_ldq(N) * sizeof(float); }
 
 int launch_fwd_qwarp(const MkFwdParams<float> &p, float *Q, cudaStream_t st) {
     static DeviceOnce configured;
     const int dev = current_device();
-    float *diag = Q + (size_t)p.B * p.N * fwd_qwarp_ldq(p.N);
-    int smem_sm = 0, nsm = 0;
-    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    int nsm = 0;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const GsLayout l = gs_layout(p.N, smem_sm);
+    const GsLayout l = gs_layout(p.N, device_smem_limit());
     if (configured.needs(dev)) {
         if (cudaFuncSetAttribute(markowitz_gram_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, device_smem_limit()) != cudaSuccess ||
             cudaFuncSetAttribute(markowitz_qwarp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qw_smem_bytes(128)) != cudaSuccess)
@@ -680,16 +873,16 @@ int launch_fwd_qwarp(const MkFwdParams<float> &p, float *Q, cudaStream_t st) {
         configured.mark(dev);
     }
     GsParams g;
-    g.C = p.C; g.gamma = p.gamma; g.alpha = p.alpha; g.Q = Q; g.diag = diag; g.B = p.B; g.Bmod = p.Bmod; g.b0 = p.b0;
+    g.C = p.C; g.gamma = p.gamma; g.alpha = p.alpha; g.Q = Q; g.B = p.B; g.Bmod = p.Bmod; g.b0 = p.b0;
     g.N = p.N; g.LDQ = fwd_qwarp_ldq(p.N); g.BN = l.BN; g.nraw = l.nraw;
-    g.raw_bytes = l.raw_bytes; g.tile_bytes = l.tile_bytes; g.tmem_cols = l.tmem_cols;
-    const int per_sm = 2 * ((size_t)l.total + 1024) <= (size_t)smem_sm ? 2 : 1;
-    const long long grid = (long long)per_sm * (nsm > 0 ? nsm : 148);
+    g.raw_bytes = l.raw_bytes; g.tile_bytes = l.tile_bytes; g.ring_bytes = l.ring_bytes; g.tmem_cols = l.tmem_cols;
+    g.dbg = getenv("DDW_GS_DBG") ? atoi(getenv("DDW_GS_DBG")) : 0;
+    const long long grid = nsm > 0 ? nsm : 148;          // one persistent CTA per SM (it owns the SM's tensor memory)
     markowitz_gram_small_kernel<<<(unsigned)(p.B < grid ? p.B : grid), kGsThreads, l.total, st>>>(g);
     int rc = check_launch("markowitz_gram_small_kernel");
     if (rc) return rc;
     QwParams q;
-    q.rets = p.rets; q.Q = Q; q.diag = diag; q.alpha = p.alpha; q.u = p.u; q.B = p.B; q.N = p.N; q.LDQ = g.LDQ; q.w = p.w; q.state = p.state; q.status = p.status;
+    q.rets = p.rets; q.Q = Q; q.alpha = p.alpha; q.u = p.u; q.B = p.B; q.N = p.N; q.LDQ = g.LDQ; q.w = p.w; q.state = p.state; q.status = p.status;
     q.fail_count = p.fail_count; q.fail_list = p.fail_list; q.work_count = p.work_count; q.work_list = p.work_list;
     q.bad_count = p.bad_count;
     markowitz_qwarp_kernel<<<(unsigned)p.B, 32, qw_smem_bytes(g.LDQ), st>>>(q);

@@ -867,8 +867,8 @@ def test_layers_on_a_second_gpu_in_the_same_process():
                                                       (32, 40, 50, 1.0, "identity", 2.0)])
 def test_fused_covariance_markowitz_equals_the_composition(dtype, B, L, N, u, strategy, rscale):
     """ddw_covariance_markowitz_fwd against CovarianceMatrix(sqrt=False) -> NumericalMarkowitz: in the diversified regime both
-    run the dense solver on the same bits (weights bit for bit); with concentrated optima the composition takes the
-    sparse-support kernel, so weights agree to rounding.  Gradients flow to x, coef, rets, gamma and alpha; oracle check."""
+    run the dense solver on the same bits (weights bit for bit); with concentrated optima or small universes the composition
+    takes the sparse-support / warp-per-portfolio kernels, so weights agree to rounding.  Gradients flow to x, coef, rets, gamma and alpha; oracle check."""
     from deepdow_b200.layers import covariance_markowitz
     rng = np.random.default_rng(B + L + N)
     x = rng.standard_normal((B, L, N)) * 0.01
@@ -888,7 +888,9 @@ def test_fused_covariance_markowitz_equals_the_composition(dtype, B, L, N, u, st
             w = alloc(tr, cov_layer(tx, tc), tg, ta)
         (w * t(G, dtype)).sum().backward()
         res.append((w.detach(), tx.grad, tr.grad, tg.grad, ta.grad, None if tc is None else tc.grad))
-    dense = rscale < 1.0
+    # float32 with at most 32 + 8 free assets: the composition runs the warp-per-portfolio solver on the tensor-core Gram
+    # (markowitz_qwarp.cu), the fused call the dense solver -- equal to rounding, not bit for bit
+    dense = rscale < 1.0 and (dtype == torch.float64 or N > 40)
     if dense:
         assert torch.equal(res[0][0], res[1][0])
     else:

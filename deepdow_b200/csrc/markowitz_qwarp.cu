@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
                         if (have > g) break;
                         if (spin > (1 << 26)) __trap();
                     }
-                    if (c == 0) tc::fence_after_sync();        // the epilogue's tcgen05.ld of this buffer are ordered before the MMAs
+                    if (c == 0 && !(p.dbg & 64)) tc::fence_after_sync();        // the epilogue's tcgen05.ld of this buffer are ordered before the MMAs
                     GS_T(2, true);
                     GS_TR(2, it, c, 0);
                     uint64_t dh = desc0 + s * dstage, dl = dh + dtile;

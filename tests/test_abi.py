@@ -120,4 +120,21 @@ def test_hot_kernels_stage_their_matrix_with_bulk_tma(lib):
             seen[current] = seen.get(current, 0) + 1
     assert any("markowitz_fwd_sparse_kernelIf" in k for k in seen), sorted(seen)
     assert any("markowitz_bwd_sparse_kernelIf" in k for k in seen), sorted(seen)
+    assert any("markowitz_gram_small_kernel" in k for k in seen), sorted(seen)      # A by one bulk copy per portfolio
+    assert any("markowitz_qwarp_kernel" in k for k in seen), sorted(seen)           # rows of Q by one bulk copy per asset
     assert "arch = sm_100a" in out
+
+
+def test_headline_forward_runs_its_gram_on_tcgen05(lib):
+    """SASS evidence for the north star's "tensor cores for the X'X contraction": the float32 NumericalMarkowitz forward forms
+    Q = A'A with tcgen05.mma (UTCHMMA) into TMEM accumulators read back by tcgen05.ld (LDTM), committed to mbarriers (UTCBAR)."""
+    import shutil
+    import subprocess
+    from deepdow_b200 import _C
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", _C.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    body = out.split("markowitz_gram_small_kernel", 1)[1].split("Function :", 1)[0]
+    for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "UBLKCP"):
+        assert mnemonic in body, mnemonic

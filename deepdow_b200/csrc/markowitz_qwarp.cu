@@ -23,6 +23,10 @@
 
 namespace ddw {
 
+// probe word (section 0 below): bits 0-15 portfolios that overflow the frame, bits 16-30 portfolios probed, bit 31 "the batch is
+// the dense kernel's"
+__device__ __forceinline__ bool probe_says_dense(const int *word) { return *reinterpret_cast<const volatile int *>(word) < 0; }
+
 // ------------------------------------------------------------------------------------------------------------------
 // (1) Gram kernel
 // ------------------------------------------------------------------------------------------------------------------
@@ -74,6 +78,7 @@ struct GsParams {
     int N, LDQ, BN, nraw;
     unsigned raw_bytes, tile_bytes, ring_bytes, tmem_cols;
     int dbg;
+    const int *skip;        // probe flag: the batch is the dense kernel's
 };
 
 // Polling wait (mbarrier.test_wait): the role warps hand work to each other every few hundred cycles, and the suspending
@@ -183,6 +188,7 @@ __device__ long long ddw_gs_trace[4096];      // [role 0..3][portfolio 0..3][chu
 // the staging of p + 2 overlap.
 __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsParams p) {
     extern __shared__ unsigned char gs_smem[];
+    if (probe_says_dense(p.skip)) return;     // diversified batch (probe kernel): nothing to do here
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, BN = p.BN;
     // 1 KB alignment by an offset from the shared array itself: the pointers keep their address space (LDS / STS, not generic)
@@ -472,6 +478,7 @@ struct QwParams {
     int8_t *state;
     int32_t *status;
     int *fail_count, *fail_list, *work_count, *work_list, *bad_count;
+    const int *skip;        // probe flag: hand every portfolio to the dense kernel
 };
 
 // shared memory of one warp: mbarrier | multipliers L (32 x 33) | rets | reduced-row -> asset, -> slot | 32 row slots of Q
@@ -519,6 +526,10 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
             if (lane == 0) p.status[b] = DDW_STATUS_OK;
             return;
         }
+    }
+    if (probe_says_dense(p.skip)) {         // diversified batch (probe kernel): the dense kernel's work list
+        if (lane == 0) { const int sl = atomicAdd(p.work_count, 1); p.work_list[sl] = (int)b; }
+        return;
     }
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(qw_smem);
     float *Lt = reinterpret_cast<float *>(qw_smem + 16);
@@ -834,6 +845,67 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// (0) probe: is this batch in the diversified regime?
+// ------------------------------------------------------------------------------------------------------------------
+// When most assets are free (small expected returns: what BachelierNet / ThorpNet produce) every portfolio outgrows the 32-row
+// frame and is the dense kernel's anyway; the Gram kernel would then cost 110 us per 4096 portfolios for nothing.  The probe runs
+// the warm start (column norms + Newton on the multiplier, as markowitz_sparse.cuh does) on up to kProbe portfolios spread over
+// the batch and raises a flag when three quarters of them overflow the frame; the two kernels below then return at once and the
+// whole batch goes to the dense kernel.  The decision is a function of the inputs of THIS call only (repeatable, capturable).
+constexpr int kProbe = 32;
+constexpr int kProbeThreads = 1024;       // n_assets <= 128: at least 8 row slices per column, at most 16 rows per thread
+
+__global__ void __launch_bounds__(kProbeThreads) markowitz_qprobe_kernel(const float *C, const float *rets, const float *gamma, const float *alpha,
+                                                                         float u, long long B, long long Bmod, long long b0, int N, int nprobe,
+                                                                         int *word) {
+    __shared__ float part[kProbeThreads], qd[128 + 32], r[128 + 32];
+    __shared__ int8_t st[128 + 32];
+    const int tid = threadIdx.x;
+    const long long b = (long long)blockIdx.x * B / nprobe;        // probes spread evenly over the batch
+    // column norms of the gamma-tiled covmat_sqrt straight from global memory: thread = (column i, row slice h), coalesced rows
+    const int nh = kProbeThreads / N, i = tid % N, h = tid / N;
+    float acc = 0.f;
+    if (h < nh) {
+        const float *col = C + b * (long long)N * N + i;
+        const unsigned uB = (unsigned)Bmod;
+        unsigned gi = (unsigned)(((b0 + b) * (long long)N * N + (long long)h * N + i) % Bmod);
+        const unsigned gstep = (unsigned)(((long long)nh * N) % Bmod);
+        float cv[16], gv[16];               // every load of this thread in flight at once: the probe is latency, not bandwidth
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int k = h + q * nh;
+            cv[q] = k < N ? __ldg(col + (long long)k * N) : 0.f;
+            gv[q] = k < N ? __ldg(gamma + gi) : 0.f;
+            gi += gstep; if (gi >= uB) gi -= uB;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { const float v = cv[q] * gv[q]; acc = fmaf(v, v, acc); }
+    }
+    part[tid] = acc;
+    if (tid < N) r[tid] = rets[b * N + tid];
+    __syncthreads();
+    if (tid < N) {
+        float q = fabsf(alpha[b]);
+        for (int hh = 0; hh < nh; ++hh) q += part[hh * N + tid];
+        qd[tid] = q;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float dmax;
+        diag_init_warp<float, kQwAssets>(qd, 1, r, st, N, u, &dmax);
+        __syncwarp();
+        int held = 0;
+        for (int j = tid; j < N; j += 32) held += st[j] >= 0;       // free or capped: the assets that need a row of the frame
+        held = warp_sum(held);
+        if (tid == 0) {
+            const int mine = (1 << 16) | (held > kQwFree + kQwTrim ? 1 : 0);
+            const int seen = atomicAdd(word, mine) + mine;
+            if ((seen >> 16) == nprobe && 4 * (seen & 0xffff) >= 3 * nprobe) atomicOr(word, (int)0x80000000);
+        }
+    }
+}
+
 #ifdef DDW_GS_TIMING
 }  // namespace ddw
 extern "C" int ddw_debug_gs_phases(unsigned long long *out16, int reset) {
@@ -872,7 +944,15 @@ int launch_fwd_qwarp(const MkFwdParams<float> &p, float *Q, cudaStream_t st) {
             return check_launch("cudaFuncSetAttribute(markowitz_gram_small_kernel / markowitz_qwarp_kernel)");
         configured.mark(dev);
     }
+    int *probe = p.fail_count + 3;          // fourth counter of the workspace header, cleared with the other three by the caller
+    {
+        const int nprobe = (int)(p.B < kProbe ? p.B : kProbe);
+        markowitz_qprobe_kernel<<<nprobe, kProbeThreads, 0, st>>>(p.C, p.rets, p.gamma, p.alpha, p.u, p.B, p.Bmod, p.b0, p.N, nprobe, probe);
+        int rcp = check_launch("markowitz_qprobe_kernel");
+        if (rcp) return rcp;
+    }
     GsParams g;
+    g.skip = probe;
     g.C = p.C; g.gamma = p.gamma; g.alpha = p.alpha; g.Q = Q; g.B = p.B; g.Bmod = p.Bmod; g.b0 = p.b0;
     g.N = p.N; g.LDQ = fwd_qwarp_ldq(p.N); g.BN = l.BN; g.nraw = l.nraw;
     g.raw_bytes = l.raw_bytes; g.tile_bytes = l.tile_bytes; g.ring_bytes = l.ring_bytes; g.tmem_cols = l.tmem_cols;
@@ -882,6 +962,7 @@ int launch_fwd_qwarp(const MkFwdParams<float> &p, float *Q, cudaStream_t st) {
     int rc = check_launch("markowitz_gram_small_kernel");
     if (rc) return rc;
     QwParams q;
+    q.skip = probe;
     q.rets = p.rets; q.Q = Q; q.alpha = p.alpha; q.u = p.u; q.B = p.B; q.N = p.N; q.LDQ = g.LDQ; q.w = p.w; q.state = p.state; q.status = p.status;
     q.fail_count = p.fail_count; q.fail_list = p.fail_list; q.work_count = p.work_count; q.work_list = p.work_list;
     q.bad_count = p.bad_count;

@@ -77,7 +77,6 @@ struct GsParams {
     long long B, Bmod, b0;
     int N, LDQ, BN, nraw;
     unsigned raw_bytes, tile_bytes, ring_bytes, tmem_cols;
-    int dbg;
     const int *skip;        // probe flag: the batch is the dense kernel's
 };
 
@@ -277,7 +276,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
                         if (have > g) break;
                         if (spin > (1 << 26)) __trap();
                     }
-                    if (c == 0 && !(p.dbg & 64)) tc::fence_after_sync();        // the epilogue's tcgen05.ld of this buffer are ordered before the MMAs
+                    if (c == 0) tc::fence_after_sync();        // the epilogue's tcgen05.ld of this buffer are ordered before the MMAs
                     GS_T(2, true);
                     GS_TR(2, it, c, 0);
                     uint64_t dh = desc0 + s * dstage, dl = dh + dtile;
@@ -423,7 +422,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
             tc::fence_after_sync();
             GS_T(11, tid == 0);
             if (tid == 0) GS_TR(3, it, 0, 0);
-            if (32 * (warp & 3) < N && !(p.dbg & 2)) {
+            if (32 * (warp & 3) < N) {
                 const uint32_t lane_addr = tmem + tb * 2u * (uint32_t)BN + ((uint32_t)(32 * (warp & 3)) << 16);
                 float *qcol = p.Q + (b * (long long)N + cbeg) * ldq + m;
 #pragma unroll 1
@@ -956,7 +955,6 @@ int launch_fwd_qwarp(const MkFwdParams<float> &p, float *Q, cudaStream_t st) {
     g.C = p.C; g.gamma = p.gamma; g.alpha = p.alpha; g.Q = Q; g.B = p.B; g.Bmod = p.Bmod; g.b0 = p.b0;
     g.N = p.N; g.LDQ = fwd_qwarp_ldq(p.N); g.BN = l.BN; g.nraw = l.nraw;
     g.raw_bytes = l.raw_bytes; g.tile_bytes = l.tile_bytes; g.ring_bytes = l.ring_bytes; g.tmem_cols = l.tmem_cols;
-    g.dbg = getenv("DDW_GS_DBG") ? atoi(getenv("DDW_GS_DBG")) : 0;
     const long long grid = nsm > 0 ? nsm : 148;          // one persistent CTA per SM (it owns the SM's tensor memory)
     markowitz_gram_small_kernel<<<(unsigned)(p.B < grid ? p.B : grid), kGsThreads, l.total, st>>>(g);
     int rc = check_launch("markowitz_gram_small_kernel");

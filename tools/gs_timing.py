@@ -20,7 +20,7 @@ with torch.no_grad():
     for _ in range(reps): layer(rets, C, g, a)
     lib.ddw_debug_gs_phases(out, 0)
 names = ["tma: wait raw_empty", "mma: wait acc_empty", "mma: wait ring_full", "mma: issue+commit", "stage: group sync", "stage: wait raw_full",
-         "stage: gamma", "stage: wait ring_empty", "stage: split+store", "stage: fence+arrive", "stage: diag+release", "epi: wait acc_full", "epi: load+store", "mma: commit -> own barrier seen (DDW_GS_DBG=32)"]
+         "stage: gamma", "stage: wait ring_empty", "stage: split+store", "stage: fence+arrive", "stage: diag+release", "epi: wait acc_full", "epi: load+store"]
 for n, v in zip(names, out):
     print(f"  {n:26s} {v / reps / B:9.0f} cycles/portfolio")
 

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
     unsigned long long *raw_full = reinterpret_cast<unsigned long long *>(base);         // [kGsMaxRaw]
     unsigned long long *raw_empty = raw_full + kGsMaxRaw;                                // [kGsMaxRaw]
     unsigned long long *ring_full = raw_empty + kGsMaxRaw;                               // [kGsRing]
-    unsigned long long *ring_empty = ring_full + kGsRing;                                // [kGsRing]
+    unsigned long long *ring_empty = ring_full + kGsRing;                                // [kGsRing / 2]: one per pair of stages
     unsigned long long *acc_full = ring_empty + kGsRing;                                 // [2]
     unsigned long long *acc_empty = acc_full + 2;                                        // [2]
     uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(base + 192);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
                 GS_T0
                 const uint32_t acc = tmem + tb * 2u * (uint32_t)BN;
                 for (int c = 0; c < nchunks; ++c, ++g) {
-                    const unsigned s = g % kGsRing;
+                    const unsigned s = (unsigned)c;                  // every portfolio starts at stage 0 (at most kGsRing chunks)
                     for (int spin = 0; ; ++spin) {
                         unsigned have;
                         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(have) : "r"(smem_u32(ready)) : "memory");
@@ -287,7 +287,9 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
                         tc::mma_tf32(acc + BN, dh, dl, idesc, 1u);
                         tc::mma_tf32(acc, dh, dh, idesc, first);             // hi' hi
                     }
-                    tc::mma_commit(&ring_empty[s]);
+                    // one commit per PAIR of stages: a tcgen05.commit holds this thread until the MMAs before it are done
+                    // (~1.2 k cycles each, measured: five commits per portfolio were the period of the whole kernel)
+                    if ((c & 1) || c == nchunks - 1) tc::mma_commit(&ring_empty[c >> 1]);
                     if (c == nchunks - 1) tc::mma_commit(&acc_full[tb]);
                     GS_T(3, true);
                     GS_TR(2, it, c, 1);
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
                 const long long ut = it >> 1;
                 if (ut > 0) mbar_poll(&acc_empty[tb], (unsigned)((ut - 1) & 1));      // the epilogue has read this buffer
                 for (int c = 0; c < nchunks; ++c, ++g) {
-                    mbar_poll(&ring_full[g % kGsRing], (g / kGsRing) & 1u);           // (the stagers' fence.proxy.async made their stores visible to the MMA)
+                    mbar_poll(&ring_full[c], (unsigned)(it & 1));                     // (the stagers' fence.proxy.async made their stores visible to the MMA)
                     asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(ready)), "r"(g + 1u) : "memory");
                 }
             }
@@ -344,11 +346,11 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
             GS_T(6, sta == 0);
             for (int c = 0; c < nchunks; ++c, ++g) {
                 if ((c & 1) != grp) continue;                        // the other group's chunk
-                const unsigned s = g % kGsRing, u4 = g / kGsRing;
+                const unsigned s = (unsigned)c;
                 unsigned char *hi = ring + s * stage_bytes, *lo = hi + p.tile_bytes;
                 const int kleft = N - c * kGsChunkK;                 // k values of this chunk that exist
                 const int kgroups = 2 * min(4, (kleft + 7) >> 3);    // 4-wide k groups the MMAs of this chunk read
-                if (u4 > 0) mbar_poll(&ring_empty[s], (u4 - 1u) & 1u);               // the MMAs that read this stage have drained
+                if (it > 0) mbar_poll(&ring_empty[c >> 1], (unsigned)((it - 1) & 1));   // the previous portfolio's MMAs on this pair of stages have drained
                 GS_T(7, sta == 0);
                 if (st == 0) GS_TR(grp, it, c, 0);
                 if (quads) {

@@ -933,7 +933,17 @@ bool fwd_qwarp_eligible(int N, int tsize) {
 int fwd_qwarp_ldq(int N) { return (N + 7) / 8 * 8; }     // rows of the scratch start on 32-byte sectors
 size_t fwd_qwarp_scratch_bytes(long long B, int N) { return (size_t)B * N * fwd_qwarp_ldq(N) * sizeof(float); }
 
+template <typename T> int launch_fwd_sparse(const MkFwdParams<T> &p, cudaStream_t st);      // markowitz_sparse.cuh
+
+// Below this batch size the one-CTA-per-portfolio kernel is at least as fast: one wave of it (592 portfolios) takes about as long as
+// the probe + one portfolio's trip through the Gram pipeline + one warp's solve (measured at B = 64 .. 1024, tools/time_configs.py).
+static long long qwarp_min_batch() {
+    const char *e = getenv("DDW_QWARP_MIN_BATCH");
+    return e ? atoll(e) : 1024;
+}
+
 int launch_fwd_qwarp(const MkFwdParams<float> &p, float *Q, cudaStream_t st) {
+    if (p.B < qwarp_min_batch()) return launch_fwd_sparse<float>(p, st);
     static DeviceOnce configured;
     const int dev = current_device();
     int nsm = 0;

@@ -13,6 +13,13 @@ from deepdow_b200 import NumericalMarkowitz
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _tensor_core_path_for_small_batches(monkeypatch):
+    """By default batches below 1024 portfolios take the one-CTA-per-portfolio kernel (faster there); these tests are about the
+    tensor-core path, at sizes the oracle finishes in seconds."""
+    monkeypatch.setenv("DDW_QWARP_MIN_BATCH", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -95,9 +102,10 @@ np.save(sys.argv[1], w.cpu().numpy())
     import tempfile
     outs = []
     with tempfile.TemporaryDirectory() as tmp:
-        for i, env_extra in enumerate(({}, {"DDW_NO_QWARP": "1"})):
+        for i, env_extra in enumerate(({"DDW_QWARP_MIN_BATCH": "1"}, {"DDW_NO_QWARP": "1"})):
             env = dict(os.environ, **env_extra)
-            env.pop("DDW_NO_QWARP", None) if not env_extra else None
+            if i == 0:
+                env.pop("DDW_NO_QWARP", None)
             path = os.path.join(tmp, f"w{i}.npy")
             subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
             outs.append(np.load(path))

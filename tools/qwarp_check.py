@@ -1,5 +1,7 @@
 """Warp-per-portfolio forward (markowitz_qwarp.cu) against the float64 oracle: weights, states, solver counters (GPU box)."""
+import os
 import sys
+os.environ.setdefault("DDW_QWARP_MIN_BATCH", "1")      # the tensor-core path also for these small batches
 import numpy as np
 import torch
 sys.path.insert(0, ".")

@@ -544,10 +544,12 @@ def main():
     assert torch.equal(outf.w, out.w) and torch.equal(outf.d_rets, out.d_rets)
     clocks = sampler.stop()          # sampled over the timed regions (device-resident and end-to-end)
     n_chunks = (B + args.chunk - 1) // args.chunk
-    # the pipelined host path must reproduce the device path bit for bit (same kernels, chunked)
+    # the pipelined host path must reproduce the device path: to rounding (its chunks of 128 portfolios take the one-CTA-per-portfolio
+    # forward, the resident batch of 4096 the tensor-core Gram + warp-per-portfolio kernels), with the same supports
     with torch.no_grad():
-        w_dev = layer(*[t.detach() for t in inputs])
-    assert torch.equal(out.w, w_dev.cpu()), "host pipeline and device path disagree"
+        w_dev = layer(*[t.detach() for t in inputs]).cpu()
+    assert float((out.w - w_dev).abs().max()) < 2e-6, "host pipeline and device path disagree"
+    assert bool(((out.w > 0) == (w_dev > 0)).all()), "host pipeline and device path disagree on the supports"
 
     host_out = [torch.empty(s, dtype=torch.float32).pin_memory() for s in ((B, N), (B, N), (B, N, N), (B,), (B,))]
 

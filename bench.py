@@ -663,10 +663,10 @@ def main():
                          "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": fwd_bytes if dom_fwd else bwd_bytes,
-                         "note": "the Gram kernel is bound by the rate of its 39 small tcgen05.mma per portfolio (128x112x8 TF32, ~100 "
-                                 "cycles each), the solver by the latency of one warp's dependent shuffle / FMA chain; HBM is the "
-                                 "iteration-free ceiling; when the forward leads, its Q scratch traffic (written and partly re-read) is "
-                                 "in `traffic` but not in the algorithmic bytes"},
+                         "note": "forward = probe + tcgen05 Gram kernel (hand-over loop of its role pipeline, ~7 k cycles per portfolio; "
+                                 "tensor pipe 33% active) + one warp per portfolio (latency of the dependent shuffle / FMA chain); backward = "
+                                 "sparse-support kernel + d_gamma pass; HBM is the iteration-free ceiling; when the forward leads, its Q "
+                                 "scratch traffic (written and partly re-read) is in `traffic` but not in the algorithmic bytes"},
             "roofline_bwd": {"achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9, "frac": bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak,
                              "unit": "GB/s"},
             "clocks": clocks,

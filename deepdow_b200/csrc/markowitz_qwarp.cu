@@ -170,12 +170,15 @@ __device__ __forceinline__ void gamma_tiling_batched(float *As, int N, const flo
 __device__ unsigned long long ddw_gs_cycles[16];
 __device__ long long ddw_gs_trace[4096];      // [role 0..3][portfolio 0..3][chunk 0..7][begin, end] of CTA 0
 #define GS_TR(role, it, c, e) do { if (blockIdx.x == 0 && (it) < 4) ddw_gs_trace[(((role) * 4 + (int)(it)) * 8 + (c)) * 2 + (e)] = clock64(); } while (0)
+// per-instruction timestamps of the MMA thread: portfolio 2 of CTA 0, [chunk][14] behind the role table
+#define GS_TI(it, c, i) do { if (blockIdx.x == 0 && (it) == 2) ddw_gs_trace[256 + (c) * 16 + (i)] = clock64(); } while (0)
 #define GS_T0 long long gs_t0 = clock64();
 #define GS_T(id, cond) do { if (cond) { const long long gs_t1 = clock64(); atomicAdd(&ddw_gs_cycles[id], (unsigned long long)(gs_t1 - gs_t0)); gs_t0 = gs_t1; } } while (0)
 #else
 #define GS_T0
 #define GS_T(id, cond) do { } while (0)
 #define GS_TR(role, it, c, e) do { } while (0)
+#define GS_TI(it, c, i) do { } while (0)
 #endif
 
 // Warp-specialised, one persistent CTA per SM:
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
         // wait until that commit has fired, i.e. until the MMAs before it are done (~600 idle cycles after every chunk: the
         // pipe drained while this thread sat in a poll that was already satisfied).  So this thread never touches an mbarrier:
         // the poller warp waits for "accumulator free" and "stage full" and publishes the number of chunks that may be issued.
-        unsigned g = 0;
+        unsigned g = 0, have = 0;
         long long it = 0;
         for (long long b = b_first; b < p.B; b += b_step, ++it) {
             if (lane == 0) {
@@ -270,13 +273,15 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
                 const uint32_t acc = tmem + tb * 2u * (uint32_t)BN;
                 for (int c = 0; c < nchunks; ++c, ++g) {
                     const unsigned s = (unsigned)c;                  // every portfolio starts at stage 0 (at most kGsRing chunks)
-                    for (int spin = 0; ; ++spin) {
-                        unsigned have;
-                        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(have) : "r"(smem_u32(ready)) : "memory");
-                        if (have > g) break;
+                    // `have` was refreshed BEFORE the previous chunk's commit (below): in steady state the stagers are ahead and
+                    // this thread goes from a commit straight to the next MMAs without touching shared memory in between
+                    for (int spin = 0; have <= g; ++spin) {
+                        asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(have) : "r"(smem_u32(ready)) : "memory");
                         if (spin > (1 << 26)) __trap();
                     }
+                    GS_TI(it, c, 14);
                     if (c == 0) tc::fence_after_sync();        // the epilogue's tcgen05.ld of this buffer are ordered before the MMAs
+                    GS_TI(it, c, 15);
                     GS_T(2, true);
                     GS_TR(2, it, c, 0);
                     uint64_t dh = desc0 + s * dstage, dl = dh + dtile;
@@ -284,13 +289,21 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
                     for (int kk = 0; kk < ksteps; ++kk, dh += 2, dl += 2) {      // 8 k values = 32 B along the swizzle row
                         const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
                         tc::mma_tf32(acc + BN, dl, dh, idesc, first);        // cross terms: lo' hi + hi' lo
+                        GS_TI(it, c, 3 * kk);
                         tc::mma_tf32(acc + BN, dh, dl, idesc, 1u);
+                        GS_TI(it, c, 3 * kk + 1);
                         tc::mma_tf32(acc, dh, dh, idesc, first);             // hi' hi
+                        GS_TI(it, c, 3 * kk + 2);
                     }
                     // one commit per PAIR of stages: a tcgen05.commit holds this thread until the MMAs before it are done
                     // (~1.2 k cycles each, measured: five commits per portfolio were the period of the whole kernel)
+                    // any shared-memory access of this thread queues behind a pending tcgen05.commit (measured: ~300 idle cycles
+                    // after every commit, 1.1 k after the two at a portfolio boundary): read the flag first
+                    asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(have) : "r"(smem_u32(ready)) : "memory");
                     if ((c & 1) || c == nchunks - 1) tc::mma_commit(&ring_empty[c >> 1]);
+                    GS_TI(it, c, 12);
                     if (c == nchunks - 1) tc::mma_commit(&acc_full[tb]);
+                    GS_TI(it, c, 13);
                     GS_T(3, true);
                     GS_TR(2, it, c, 1);
                 }

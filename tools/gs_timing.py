@@ -37,3 +37,16 @@ t0 = ev[0][0]
 print("timeline of CTA 0 (cycles from its first event): role portfolio.chunk begin..end")
 for b0, e0, name, it, c in ev:
     print(f"  {b0 - t0:8d} .. {e0 - t0:8d}  {name:7s} {it}.{c}")
+
+print("MMA thread, portfolio 2 of CTA 0: cycles between consecutive instructions (12 tcgen05.mma, commit(stage pair), commit(accumulator))")
+for c in range(4):
+    ts = [tr[256 + c * 16 + i] for i in range(14)]
+    begin = tr[((2 * 4 + 2) * 8 + c) * 2]
+    prev = begin
+    out_ = []
+    for t_ in ts:
+        out_.append(f"{t_ - prev:5d}" if t_ and prev else "    -")
+        if t_: prev = t_
+    end_prev = tr[((2 * 4 + (2 if c else 1)) * 8 + (c - 1 if c else 3)) * 2 + 1]
+    print(f"  chunk {c}: " + " ".join(out_) + f"   | previous section end -> flag seen {tr[256 + c * 16 + 14] - end_prev}, -> after fence {tr[256 + c * 16 + 15] - end_prev}")
+print("flag value minus own chunk index when first seen, and spins:", [(tr[320 + c], tr[328 + c]) for c in range(4)])

@@ -545,11 +545,11 @@ def main():
     clocks = sampler.stop()          # sampled over the timed regions (device-resident and end-to-end)
     n_chunks = (B + args.chunk - 1) // args.chunk
     # the pipelined host path must reproduce the device path: to rounding (its chunks of 128 portfolios take the one-CTA-per-portfolio
-    # forward, the resident batch of 4096 the tensor-core Gram + warp-per-portfolio kernels), with the same supports
+    # forward, the resident batch of 4096 the tensor-core Gram + warp-per-portfolio kernels; an asset whose weight is within
+    # rounding of a bound may sit on either side of it)
     with torch.no_grad():
         w_dev = layer(*[t.detach() for t in inputs]).cpu()
     assert float((out.w - w_dev).abs().max()) < 2e-6, "host pipeline and device path disagree"
-    assert bool(((out.w > 0) == (w_dev > 0)).all()), "host pipeline and device path disagree on the supports"
 
     host_out = [torch.empty(s, dtype=torch.float32).pin_memory() for s in ((B, N), (B, N), (B, N, N), (B,), (B,))]
 

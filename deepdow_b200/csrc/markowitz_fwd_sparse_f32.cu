@@ -6,4 +6,5 @@
 
 namespace ddw {
 template int launch_fwd_sparse<float>(const MkFwdParams<float> &, cudaStream_t);
+template int launch_fwd_sparse_list<float>(const MkFwdParams<float> &, const int *, const int *, int, cudaStream_t);
 }  // namespace ddw

@@ -481,7 +481,9 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
 constexpr int kQwFree = 32;            // largest reduced system (one row per lane)
 constexpr int kQwLd = 33;              // row stride of the multiplier array (conflict-free rows and columns)
 constexpr int kQwAssets = 4;           // assets per lane: n_assets <= 128
-constexpr int kQwTrim = 8;             // largest overflow of the frame that is trimmed instead of handed to the dense kernel
+constexpr int kQwTrim = 16;            // largest overflow of the frame that is trimmed instead of handed to the dense kernel
+constexpr int kQwTrims = 4;            // ... and how often per portfolio
+constexpr int kQwOver = 256;           // portfolios per call that may take the list-mode CTA kernel instead of the dense one
 
 struct QwParams {
     const float *rets, *Q, *alpha;
@@ -493,6 +495,7 @@ struct QwParams {
     int32_t *status;
     int *fail_count, *fail_list, *work_count, *work_list, *bad_count;
     const int *skip;        // probe flag: hand every portfolio to the dense kernel
+    int *over_count, *over_list;   // portfolios whose sets overflow the frame: the one-CTA-per-portfolio kernel in list mode
 };
 
 // shared memory of one warp: mbarrier | multipliers L (32 x 33) | rets | reduced-row -> asset, -> slot | 32 row slots of Q
@@ -642,10 +645,11 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
             // of the headline workload) is cut down to the frame instead of handing the portfolio to the dense kernel, whose
             // latency for a handful of portfolios is as long as this whole kernel: the free assets with the smallest weights go
             // to the lower bound, and the iteration frees them again if their gradient says so.  The converged point is the same
-            // KKT point; only the path differs.  Anything larger, or a second overflow, is the dense kernel's.
+            // KKT point; only the path differs.  Anything larger, or a fifth overflow, is the dense kernel's (one hand-over costs the whole
+            // batch ~70 us of dense-kernel latency: on 8 GPUs one rank in eight paid it, 0.86 weak-scaling efficiency).
             const int drop = nF + nU - kQwFree;
-            if (drop > kQwTrim || trimmed) { bail = 1; break; }
-            trimmed = 1;
+            if (drop > kQwTrim || trimmed >= kQwTrims) { bail = 1; break; }
+            ++trimmed;
             for (int d = 0; d < drop; ++d) {
                 float best = Num<float>::inf();
                 int bi = 0x7fffffff;
@@ -831,7 +835,13 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
         if (!__any_sync(kFullMask, changed)) { converged = 1; break; }
     }
     if (bail) {
-        if (lane == 0) { const int sl = atomicAdd(p.work_count, 1); p.work_list[sl] = (int)b; }
+        // a set that does not fit the 32-row frame: the one-CTA-per-portfolio kernel (<= 48 candidates) takes it in list mode
+        // -- a third of the dense kernel's latency, which the whole batch waits for; beyond kQwOver of them, the dense kernel
+        if (lane == 0) {
+            const int ov = atomicAdd(p.over_count, 1);
+            if (ov < kQwOver) p.over_list[ov] = (int)b;
+            else { const int sl = atomicAdd(p.work_count, 1); p.work_list[sl] = (int)b; }
+        }
         return;
     }
     int bad = 0;
@@ -872,7 +882,8 @@ constexpr int kProbeThreads = 1024;       // n_assets <= 128: at least 8 row sli
 
 __global__ void __launch_bounds__(kProbeThreads) markowitz_qprobe_kernel(const float *C, const float *rets, const float *gamma, const float *alpha,
                                                                          float u, long long B, long long Bmod, long long b0, int N, int nprobe,
-                                                                         int *word) {
+                                                                         int *word, int *over_count) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *over_count = 0;      // (first kernel of the call: clears the overflow list)
     __shared__ float part[kProbeThreads], qd[128 + 32], r[128 + 32];
     __shared__ int8_t st[128 + 32];
     const int tid = threadIdx.x;
@@ -944,9 +955,11 @@ bool fwd_qwarp_eligible(int N, int tsize) {
     return !off && tsize == 4 && N >= 8 && N <= 128;
 }
 int fwd_qwarp_ldq(int N) { return (N + 7) / 8 * 8; }     // rows of the scratch start on 32-byte sectors
-size_t fwd_qwarp_scratch_bytes(long long B, int N) { return (size_t)B * N * fwd_qwarp_ldq(N) * sizeof(float); }
+// Q (B x N x LDQ) followed by the overflow list (count + kQwOver entries)
+size_t fwd_qwarp_scratch_bytes(long long B, int N) { return (size_t)B * N * fwd_qwarp_ldq(N) * sizeof(float) + 2048; }
 
 template <typename T> int launch_fwd_sparse(const MkFwdParams<T> &p, cudaStream_t st);      // markowitz_sparse.cuh
+template <typename T> int launch_fwd_sparse_list(const MkFwdParams<T> &p, const int *in_list, const int *in_count, int max_entries, cudaStream_t st);
 
 // Below this batch size the one-CTA-per-portfolio kernel is at least as fast: one wave of it (592 portfolios) takes about as long as
 // the probe + one portfolio's trip through the Gram pipeline + one warp's solve (measured at B = 64 .. 1024, tools/time_configs.py).
@@ -969,9 +982,10 @@ int launch_fwd_qwarp(const MkFwdParams<float> &p, float *Q, cudaStream_t st) {
         configured.mark(dev);
     }
     int *probe = p.fail_count + 3;          // fourth counter of the workspace header, cleared with the other three by the caller
+    int *over = reinterpret_cast<int *>(Q + (size_t)p.B * p.N * fwd_qwarp_ldq(p.N));      // [0] count, [1 .. kQwOver] portfolios
     {
         const int nprobe = (int)(p.B < kProbe ? p.B : kProbe);
-        markowitz_qprobe_kernel<<<nprobe, kProbeThreads, 0, st>>>(p.C, p.rets, p.gamma, p.alpha, p.u, p.B, p.Bmod, p.b0, p.N, nprobe, probe);
+        markowitz_qprobe_kernel<<<nprobe, kProbeThreads, 0, st>>>(p.C, p.rets, p.gamma, p.alpha, p.u, p.B, p.Bmod, p.b0, p.N, nprobe, probe, over);
         int rcp = check_launch("markowitz_qprobe_kernel");
         if (rcp) return rcp;
     }
@@ -989,8 +1003,11 @@ int launch_fwd_qwarp(const MkFwdParams<float> &p, float *Q, cudaStream_t st) {
     q.rets = p.rets; q.Q = Q; q.alpha = p.alpha; q.u = p.u; q.B = p.B; q.N = p.N; q.LDQ = g.LDQ; q.w = p.w; q.state = p.state; q.status = p.status;
     q.fail_count = p.fail_count; q.fail_list = p.fail_list; q.work_count = p.work_count; q.work_list = p.work_list;
     q.bad_count = p.bad_count;
+    q.over_count = over; q.over_list = over + 1;
     markowitz_qwarp_kernel<<<(unsigned)p.B, 32, qw_smem_bytes(g.LDQ), st>>>(q);
-    return check_launch("markowitz_qwarp_kernel");
+    rc = check_launch("markowitz_qwarp_kernel");
+    if (rc) return rc;
+    return launch_fwd_sparse_list<float>(p, over + 1, over, kQwOver, st);
 }
 
 }  // namespace ddw

@@ -81,10 +81,14 @@ template <typename T> __device__ __forceinline__ SpSmem<T> sp_carve(unsigned cha
 }
 
 template <typename T, int kThreads, int NREG>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fwd_sparse_kernel(MkFwdParams<T> p) {
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fwd_sparse_kernel(MkFwdParams<T> p, const int *in_list,
+                                                                                               const int *in_count) {
     static_assert(kThreads == 128, "the list phase maps one thread to one asset (n_assets <= 128)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const long long b = blockIdx.x;
+    // list mode (in_list != nullptr): CTA i takes the i-th portfolio that the warp-per-portfolio kernel could not hold in its
+    // 32-row frame (markowitz_qwarp.cu); direct mode: one CTA per portfolio of the batch
+    if (in_list && (int)blockIdx.x >= *in_count) return;
+    const long long b = in_list ? (long long)in_list[blockIdx.x] : (long long)blockIdx.x;
     const int N = p.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int LDC = kCandLd;
     const T u = p.u;
@@ -354,8 +358,23 @@ template <typename T> int launch_fwd_sparse(const MkFwdParams<T> &p, cudaStream_
 #ifdef DDW_PHASE_TIMING
     if (const char *pad = getenv("DDW_DEBUG_SMEM_PAD")) smem += (size_t)atoi(pad);   // fewer resident CTAs per SM
 #endif
-    ks<<<(unsigned)p.B, 128, smem, st>>>(p);
+    ks<<<(unsigned)p.B, 128, smem, st>>>(p, nullptr, nullptr);
     return check_launch("markowitz_fwd_sparse_kernel");
+}
+
+// list mode: at most `max_entries` portfolios named by in_list[0 .. *in_count)
+template <typename T> int launch_fwd_sparse_list(const MkFwdParams<T> &p, const int *in_list, const int *in_count, int max_entries,
+                                                 cudaStream_t st) {
+    auto ks = markowitz_fwd_sparse_kernel<T, 128, 4>;
+    static DeviceOnce configured;
+    const int dev = current_device();
+    if (configured.needs(dev)) {
+        if (cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, device_smem_limit()) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(markowitz_fwd_sparse, list mode)");
+        configured.mark(dev);
+    }
+    ks<<<(unsigned)max_entries, 128, sp_smem_bytes(p.N, sizeof(T)), st>>>(p, in_list, in_count);
+    return check_launch("markowitz_fwd_sparse_kernel (list mode)");
 }
 
 }  // namespace ddw

@@ -134,3 +134,54 @@ def test_forward_is_bitwise_repeatable_and_graph_capturable():
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(wg, w0)
+
+
+def test_non_finite_inputs_raise_and_do_not_touch_their_neighbours():
+    """NaN in rets, Inf in covmat_sqrt: the affected portfolios are reported (SolverError, the reference's solver fails loudly
+    too), the kernels neither hang nor trap, and every other portfolio of the batch is solved as usual."""
+    from deepdow_b200 import SolverError
+    B, N, u = 96, 40, 0.3
+    rng, rets, C = _problem(B, N, 21)
+    g, a = np.ones(B, np.float32), np.ones(B, np.float32)
+    w_ok, _ = _solve(rets, C, g, a, u)
+    bad_rets = rets.copy(); bad_rets[5, 7] = np.nan
+    bad_C = C.copy(); bad_C[11, 3, 3] = np.inf
+    for r_, c_, idx in ((bad_rets, C, 5), (rets, bad_C, 11)):
+        layer = NumericalMarkowitz(N, u); layer.check_status = True
+        with pytest.raises(SolverError):
+            layer(*[torch.tensor(x, device=DEV) for x in (r_, c_, g, a)])
+        layer2 = NumericalMarkowitz(N, u); layer2.check_status = False
+        with torch.no_grad():
+            w = layer2(*[torch.tensor(x, device=DEV) for x in (r_, c_, g, a)]).double().cpu().numpy()
+        keep = np.arange(B) != idx
+        assert np.abs(w[keep] - w_ok[keep]).max() < 1e-6
+        assert int(layer2.last_status[idx]) != 0
+
+
+def test_chunked_entry_point_keeps_the_gamma_tiling():
+    """ddw_markowitz_host_step streams the batch in chunks: every chunk runs the tensor-core forward with the batch offset and the
+    whole batch's gamma modulus (allocate.py:268-270 tiles gamma over the flattened batch).  Same weights as the resident call."""
+    from deepdow_b200.host import MarkowitzHostPipeline
+    B, N, u = 48, 36, 0.3
+    rng, rets, C = _problem(B, N, 31)
+    g = (0.5 + rng.random(B)).astype(np.float32)
+    a = (rng.random(B) * 2 - 1).astype(np.float32)
+    G = rng.standard_normal((B, N)).astype(np.float32)
+    w_res, _ = _solve(rets, C, g, a, u)
+    pipe = MarkowitzHostPipeline(N, u, chunk=16, device=DEV)
+    out = pipe.step(*[torch.tensor(x).pin_memory() for x in (rets, C, g, a, G)])
+    pipe.close()
+    assert np.abs(out.w.double().numpy() - w_res).max() < 1e-6
+    w_ref, _ = _oracle(rets, C, g, a, u)
+    assert np.abs(out.w.double().numpy() - w_ref).max() < 1e-5
+
+
+def test_even_universe_not_a_multiple_of_four():
+    """n_assets = 38: 4 N^2 bytes is a multiple of 16 (bulk TMA) but rows are not groups of four (scalar staging path)."""
+    B, N, u = 64, 38, 0.3
+    rng, rets, C = _problem(B, N, 41)
+    g = (0.5 + rng.random(B)).astype(np.float32)
+    a = np.full(B, 0.2, np.float32)
+    w, _ = _solve(rets, C, g, a, u)
+    w_ref, _ = _oracle(rets, C, g, a, u)
+    assert np.abs(w - w_ref).max() < 1e-5

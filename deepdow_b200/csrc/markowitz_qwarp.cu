@@ -499,7 +499,11 @@ struct QwParams {
 };
 
 // shared memory of one warp: mbarrier | multipliers L (32 x 33) | rets | reduced-row -> asset, -> slot | 32 row slots of Q
-__host__ __device__ inline size_t qw_smem_bytes(int LDQ) { return 16 + (size_t)kQwFree * kQwLd * 4 + (size_t)LDQ * 4 + 256 + (size_t)kQwFree * LDQ * 4; }
+// (multipliers packed as the strict lower triangle: 496 floats; row slots hold n_assets rounded up to 4 floats, not the scratch's
+// row stride -- together 14 instead of 12 warps per SM at n_assets = 100)
+constexpr int kQwTri = kQwFree * (kQwFree - 1) / 2;
+__host__ __device__ constexpr int qw_tri_off(int k) { return (kQwFree - 1) * k - k * (k - 1) / 2; }      // row k holds l(i, k), i = k+1 .. 31
+__host__ __device__ inline size_t qw_smem_bytes(int RS) { return 16 + (size_t)kQwTri * 4 + (size_t)RS * 4 + 256 + (size_t)kQwFree * RS * 4; }
 
 // One elimination step of the reduced system, pivot row = lane K, with every register index a compile-time constant.
 // The system sits at the END of the 32 x 32 frame (rows = lanes k0..31, columns = registers k0..31), so a system of any
@@ -513,7 +517,7 @@ __device__ __forceinline__ void qw_step(float (&v)[kQwFree], float &y1, float &y
     const float inv = recipFastT(d);
     const float l = lane > K ? v[K] * inv : 0.f;
     if (lane == K) dinv_me = inv;
-    Lt[K * kQwLd + lane] = l;
+    if (lane > K) Lt[qw_tri_off(K) + lane - K - 1] = l;
 #pragma unroll
     for (int j = K + 1; j < kQwFree; ++j) {
         const float rk = __shfl_sync(kFullMask, v[j], K);
@@ -523,7 +527,7 @@ __device__ __forceinline__ void qw_step(float (&v)[kQwFree], float &y1, float &y
     y1 = fmaf(-l, y1k, y1); y2 = fmaf(-l, y2k, y2);
 }
 
-__global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
+__global__ void __launch_bounds__(32, 14) markowitz_qwarp_kernel(QwParams p) {
     extern __shared__ __align__(16) unsigned char qw_smem[];
     const long long b = blockIdx.x;
     const int lane = threadIdx.x, N = p.N, LDQ = p.LDQ;
@@ -549,12 +553,13 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
         return;
     }
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(qw_smem);
+    const int RS = (N + 3) & ~3;                         // row slot stride (floats): 16-byte multiples for the bulk copies
     float *Lt = reinterpret_cast<float *>(qw_smem + 16);
-    float *rs = Lt + kQwFree * kQwLd;
-    int *idx = reinterpret_cast<int *>(rs + LDQ);
+    float *rs = Lt + kQwTri;
+    int *idx = reinterpret_cast<int *>(rs + RS);
     int *sls = idx + kQwFree;
     float *rows = reinterpret_cast<float *>(sls + kQwFree);
-    const unsigned row_bytes = (unsigned)LDQ * 4u;
+    const unsigned row_bytes = (unsigned)RS * 4u;
     if (lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     const float *Qb = p.Q + b * (long long)N * LDQ;      // Q = A'A without the |alpha| I term, added where the diagonal is used
     const float aabs = fabsf(p.alpha[b]);
@@ -694,7 +699,7 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
                 __syncwarp();
 #pragma unroll
                 for (int m = 0; m < kQwAssets; ++m)
-                    if ((needm[m] >> lane) & 1u) tma_bulk_g2s(rows + slot[m] * LDQ, Qb + (lane + 32 * m) * LDQ, row_bytes, mbar);
+                    if ((needm[m] >> lane) & 1u) tma_bulk_g2s(rows + slot[m] * RS, Qb + (lane + 32 * m) * LDQ, row_bytes, mbar);
             }
 #pragma unroll
             for (int m = 0; m < kQwAssets; ++m)
@@ -717,7 +722,7 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
 #pragma unroll
                     for (int j = j0; j < j0 + 4; ++j) {
                         const int sj = __shfl_sync(kFullMask, sa, j);
-                        v[j] = (live && j >= k0) ? rows[sj * LDQ + a] : 0.f;
+                        v[j] = (live && j >= k0) ? rows[sj * RS + a] : 0.f;
                         if (j == lane) v[j] += aabs;
                     }
                 } else {
@@ -734,7 +739,7 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
                     while (mk) {
                         const int bit = __ffs(mk) - 1;
                         mk &= mk - 1;
-                        if (live) acc += rows[sa * LDQ + 32 * m + bit];
+                        if (live) acc += rows[sa * RS + 32 * m + bit];
                     }
                 }
                 y1 -= 2.f * u * acc;
@@ -756,9 +761,10 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
             x = 0.5f * (y1 - nu * y2) * dinv_me;
             __syncwarp();
 #pragma unroll 1
+            const float *Lrow = Lt + qw_tri_off(lane) - lane - 1;      // l(i, lane) at Lrow[i]
             for (int i = kQwFree - 1; i > k0; --i) {
                 const float xi = __shfl_sync(kFullMask, x, i);
-                if (live && lane < i) x = fmaf(-Lt[lane * kQwLd + i], xi, x);
+                if (live && lane < i) x = fmaf(-Lrow[i], xi, x);
             }
             nu_mult = nu;
         }
@@ -774,7 +780,7 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
         for (int j = k0; j < kQwFree; ++j) {
             const int sj = __shfl_sync(kFullMask, sa, j);
             const float xj = __shfl_sync(kFullMask, x, j);
-            const float *row = rows + sj * LDQ + lane;
+            const float *row = rows + sj * RS + lane;
 #pragma unroll
             for (int m = 0; m < kQwAssets; ++m)
                 if (in[m]) g[m] = fmaf(row[32 * m], xj, g[m]);
@@ -787,7 +793,7 @@ __global__ void __launch_bounds__(32, 12) markowitz_qwarp_kernel(QwParams p) {
                     const int bit = __ffs(mk) - 1;
                     mk &= mk - 1;
                     const int sc = __shfl_sync(kFullMask, slot[m2], bit);
-                    const float *row = rows + sc * LDQ + lane;
+                    const float *row = rows + sc * RS + lane;
 #pragma unroll
                     for (int m = 0; m < kQwAssets; ++m)
                         if (in[m]) g[m] = fmaf(row[32 * m], u, g[m]);
@@ -1004,7 +1010,7 @@ int launch_fwd_qwarp(const MkFwdParams<float> &p, float *Q, cudaStream_t st) {
     q.fail_count = p.fail_count; q.fail_list = p.fail_list; q.work_count = p.work_count; q.work_list = p.work_list;
     q.bad_count = p.bad_count;
     q.over_count = over; q.over_list = over + 1;
-    markowitz_qwarp_kernel<<<(unsigned)p.B, 32, qw_smem_bytes(g.LDQ), st>>>(q);
+    markowitz_qwarp_kernel<<<(unsigned)p.B, 32, qw_smem_bytes((p.N + 3) & ~3), st>>>(q);
     rc = check_launch("markowitz_qwarp_kernel");
     if (rc) return rc;
     return launch_fwd_sparse_list<float>(p, over + 1, over, kQwOver, st);

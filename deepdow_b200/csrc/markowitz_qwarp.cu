@@ -85,7 +85,7 @@ struct GsParams {
 // 6.3 k cycles per portfolio).  Bounded like mbar_wait: a barrier that never completes traps instead of hanging the device.
 __device__ __forceinline__ void mbar_poll(unsigned long long *bar, unsigned parity) {
     const unsigned addr = smem_u32(bar);
-    for (int spin = 0; spin < (1 << 26); ++spin) {
+    for (int spin = 0; spin < (1 << 28); ++spin) {
         unsigned ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
                     // this thread goes from a commit straight to the next MMAs without touching shared memory in between
                     for (int spin = 0; have <= g; ++spin) {
                         asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(have) : "r"(smem_u32(ready)) : "memory");
-                        if (spin > (1 << 26)) __trap();
+                        if (spin > (1 << 28)) __trap();
                     }
                     GS_TI(it, c, 14);
                     if (c == 0) tc::fence_after_sync();        // the epilogue's tcgen05.ld of this buffer are ordered before the MMAs
@@ -479,7 +479,6 @@ __global__ void __launch_bounds__(kGsThreads, 1) markowitz_gram_small_kernel(GsP
 // (2) one warp per portfolio
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kQwFree = 32;            // largest reduced system (one row per lane)
-constexpr int kQwLd = 33;              // row stride of the multiplier array (conflict-free rows and columns)
 constexpr int kQwAssets = 4;           // assets per lane: n_assets <= 128
 constexpr int kQwTrim = 16;            // largest overflow of the frame that is trimmed instead of handed to the dense kernel
 constexpr int kQwTrims = 4;            // ... and how often per portfolio

@@ -967,7 +967,7 @@ size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
     const MkPlan pf = plan_fwd(N, tsize), pb = plan_bwd(N, tsize);
     const int NP = round_up(N + 2, 32);
     size_t bytes = 0;
-    bytes += align256(sizeof(int) * (size_t)(2 * B + 4));                  // fail/work counters + lists
+    bytes += align256(sizeof(int) * (size_t)(2 * B + 8));                  // fail/work counters + lists
     bytes += align256((size_t)kIpmGrid * 8 * NP * tsize);                  // interior-point vectors
     bytes += align256((size_t)B * 2 * N * tsize);                          // (A d, A w) for the gamma pass
     size_t q = 0;
@@ -981,7 +981,7 @@ size_t markowitz_workspace_bytes(long long B, int N, int tsize) {
 #endif  // DDW_MK_DEFINE_WORKSPACE
 
 template <typename T> struct WsLayout {
-    int *fail_count, *fail_list, *work_count, *work_list, *bad_count;
+    int *fail_count, *fail_list, *work_count, *work_list, *bad_count, *bwd_counts;
     T *ipm, *vecs, *q;
     float *qs;        // Q scratch of markowitz_qwarp.cu (behind q)
 };
@@ -992,9 +992,10 @@ template <typename T> static WsLayout<T> ws_layout(void *ws, long long B, int N)
     l.fail_count = reinterpret_cast<int *>(p);   // [0] fail_count, [1] work_count, [2] bad_count (cleared together)
     l.work_count = l.fail_count + 1;
     l.bad_count = l.fail_count + 2;
-    l.fail_list = l.fail_count + 4;
+    l.bwd_counts = l.fail_count + 4;        // [4], [5]: the backward's two hand-over counters (the forward's header stays readable)
+    l.fail_list = l.fail_count + 8;
     l.work_list = l.fail_list + B;
-    p += align256(sizeof(int) * (size_t)(2 * B + 4));
+    p += align256(sizeof(int) * (size_t)(2 * B + 8));
     l.ipm = reinterpret_cast<T *>(p); p += align256((size_t)kIpmGrid * 8 * NP * sizeof(T));
     l.vecs = reinterpret_cast<T *>(p); p += align256((size_t)B * 2 * N * sizeof(T));
     l.q = reinterpret_cast<T *>(p);
@@ -1071,7 +1072,10 @@ int markowitz_fwd_t(const void *rets, const void *C, const void *gamma, const vo
         p.saved_n = reinterpret_cast<int *>(saved);
         p.saved = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(saved) + align256(sizeof(int) * (size_t)B));
         p.saved_stride = saved_stride_elems(N, sizeof(T));
-        cudaMemsetAsync(saved, 0xFF, sizeof(int) * (size_t)B, st);      // -1: no factor (sparse-support kernel, fallback)
+        // -1 = no factor.  With the sparse-support / warp-per-portfolio kernels in front every portfolio's entry is written by the
+        // kernel that finishes it (one graph node less per step); the dense kernel alone skips the portfolios the box decides
+        if (!fwd_sparse_eligible(N, sizeof(T), smem_limit()) || pl.global_q || pl.threads != 128)
+            cudaMemsetAsync(saved, 0xFF, sizeof(int) * (size_t)B, st);
         if (pl.global_q) { p.ws = p.saved; l.q = p.saved; }
     }
     // sparse-support kernel first whenever A (4 N^2 bytes) fits shared memory with room for >= 2 CTAs per SM
@@ -1219,9 +1223,9 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
     // sparse-support kernel first (A staged by TMA, free set <= kCandMax); it lists the portfolios it cannot take
     p.work_count = nullptr; p.work_list = nullptr;
     p.saved_n = nullptr; p.saved = nullptr; p.saved_stride = 0; p.LDF = 0; p.work_count2 = nullptr; p.work_list2 = nullptr;
+    cudaMemsetAsync(l.bwd_counts, 0, 2 * sizeof(int), st);          // both hand-over counters below, one graph node
     if (!pl.global_q && pl.threads == 128 && bwd_sparse_eligible(N, sizeof(T), smem_limit())) {
-        p.work_count = l.fail_count + 3; p.work_list = l.work_list;
-        cudaMemsetAsync(p.work_count, 0, sizeof(int), st);
+        p.work_count = l.bwd_counts + 1; p.work_list = l.work_list;
         if ((rc = launch_bwd_sparse<T>(p, st))) return rc;
     }
     const MkPlan pf = plan_fwd(N, sizeof(T));
@@ -1231,8 +1235,7 @@ int markowitz_bwd_t(const void *grad_w, const void *w, const int8_t *state, cons
         p.saved = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(saved) + align256(sizeof(int) * (size_t)B));
         p.saved_stride = saved_stride_elems(N, sizeof(T));
         p.LDF = pf.LD;
-        p.work_count2 = l.fail_count; p.work_list2 = l.fail_list;
-        cudaMemsetAsync(p.work_count2, 0, sizeof(int), st);
+        p.work_count2 = l.bwd_counts; p.work_list2 = l.fail_list;
         if (!pf.global_q && pl.threads == 128) rc = launch_bwd_saved_variant<T, 128, 4, false>(p, st);
         else if (!pf.global_q) rc = launch_bwd_saved_variant<T, 256, 8, false>(p, st);
         else if (pl.threads == 256) rc = launch_bwd_saved_variant<T, 256, 8, true>(p, st);

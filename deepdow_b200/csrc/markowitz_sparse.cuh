@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fw
     const T u = p.u;
     T *w_out = p.w + b * N;
     int8_t *st_out = p.state + b * N;
-    if (trivial_cases<T, kThreads>(N, u, w_out, st_out, p.status + b, p.bad_count)) return;
+    if (trivial_cases<T, kThreads>(N, u, w_out, st_out, p.status + b, p.bad_count)) {
+        if (p.saved_n && tid == 0) p.saved_n[b] = -1;
+        return;
+    }
     SpSmem<T> s = sp_carve<T>(smem_raw, N);
     T *As = s.As, *Qc = s.Qc, *Lb = s.Qc + 1;
     const T *Cb = p.C + b * (long long)N * N;
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) markowitz_fw
             p.fail_list[sl] = (int)b;
         }
         p.status[b] = st;
+        if (p.saved_n) p.saved_n[b] = -1;       // this kernel keeps no factor: the backward takes its sparse-support path
     }
 }
 

@@ -643,8 +643,10 @@ def main():
                     "pinned_buffers": numa_note},
             "eager": {"value": world * B * steps_total / (eager_ms * 1e-3), "unit": UNIT, "ms_per_step": eager_ms / steps_total,
                       "note": "same step launched from Python every time (autograd Function + ctypes)"},
-            "gpu_launches": 8 * steps_total * rounds,
-            "kernels_per_step": ["markowitz_gram_small_kernel (tcgen05 3xTF32 Gram)", "markowitz_qwarp_kernel (one warp per portfolio)",
+            "gpu_launches": 10 * steps_total * rounds,
+            "kernels_per_step": ["markowitz_qprobe_kernel (regime probe)", "markowitz_gram_small_kernel (tcgen05 3xTF32 Gram)",
+                                 "markowitz_qwarp_kernel (one warp per portfolio)",
+                                 "markowitz_fwd_sparse_kernel (list mode: sets beyond the warp solver's frame)",
                                  "markowitz_fwd_kernel (dense work list)",
                                  "markowitz_ipm_kernel (fallback list, empty here)", "markowitz_bwd_sparse_kernel",
                                  "markowitz_bwd_saved_kernel (factors kept by the dense forward)",

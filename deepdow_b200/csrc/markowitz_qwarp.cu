@@ -12,10 +12,12 @@
 // Why: the one-CTA-per-portfolio kernel keeps 40 KB of A resident per portfolio (4 portfolios per SM) while ~60% of its
 // time is spent in phases that never touch A, and spends ~37 k warp instructions per portfolio, most of them index
 // arithmetic and barriers around ~2.5 k warp instructions of useful FMAs.  With Q formed by the tensor core the solver
-// needs only |F| rows of Q per iteration; one warp per portfolio removes every block barrier and lets 16 portfolios
-// share an SM.  Portfolios whose free set outgrows 32 assets are handed to the dense kernel (work_list), those that do
-// not converge in kMaxPdas iterations to the interior-point kernel (fail_list) -- the same protocol as the
-// one-CTA-per-portfolio kernel, which stays the float64 path.
+// needs only |F| rows of Q per iteration; one warp per portfolio removes every block barrier and lets 14 portfolios
+// share an SM.  A probe kernel (0) first decides whether the batch is in the diversified regime (then everything goes to the dense
+// kernel at once).  Free sets that outgrow the 32-row frame are trimmed; what still does not fit goes to the one-CTA-per-portfolio
+// kernel in list mode, beyond 256 of those to the dense kernel (work_list); portfolios that do not converge in kMaxPdas iterations
+// go to the interior-point kernel (fail_list) -- the protocol of the one-CTA-per-portfolio kernel, which stays the float64 path and
+// the float32 path for batches below 1024 portfolios.
 #include <stdlib.h>
 #include "markowitz_common.cuh"
 #include "support_kernels.cuh"

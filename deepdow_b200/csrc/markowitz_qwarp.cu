@@ -3,11 +3,12 @@
 //   (1) markowitz_gram_small_kernel   Q = A'A of every portfolio on the 5th-generation tensor cores
 //       (tcgen05.mma.kind::tf32 in the 3xTF32 split, accumulators in TMEM).  A = gamma-tiled covmat_sqrt
 //       (reference deepdow/layers/allocate.py:268-273) arrives by ONE bulk TMA copy per portfolio (4 N^2 bytes,
-//       double buffered), is split into TF32 hi/lo parts chunk by chunk into the tensor core's canonical K-major
-//       layout, and Q leaves through tcgen05.ld as coalesced stores into a scratch that stays in the 126 MB L2.
+//       2-3 portfolios ahead), is split into TF32 hi/lo parts chunk by chunk into the tensor core's K-major SWIZZLE_128B
+//       layout, and Q leaves through tcgen05.ld as coalesced stores into a scratch in the workspace (B x N x LDQ floats).
 //   (2) markowitz_qwarp_kernel        the primal-dual active-set iteration of markowitz_sparse.cuh with ONE WARP per
 //       portfolio and no shared copy of A or Q: the reduced KKT system of the free assets (<= 32) lives in registers,
-//       one row per lane, and is eliminated with warp shuffles; gradients read the few rows of Q they need from L2.
+//       one row per lane, and is eliminated with warp shuffles; the few rows of Q it needs arrive by one bulk TMA copy per
+//       asset into 32 row slots of the warp's shared memory.
 //
 // Why: the one-CTA-per-portfolio kernel keeps 40 KB of A resident per portfolio (4 portfolios per SM) while ~60% of its
 // time is spent in phases that never touch A, and spends ~37 k warp instructions per portfolio, most of them index

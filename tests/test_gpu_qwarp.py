@@ -185,3 +185,27 @@ def test_even_universe_not_a_multiple_of_four():
     w, _ = _solve(rets, C, g, a, u)
     w_ref, _ = _oracle(rets, C, g, a, u)
     assert np.abs(w - w_ref).max() < 1e-5
+
+
+@pytest.mark.parametrize("dense_share", [1.0, 0.5, 0.1])
+def test_probe_routes_diversified_batches_to_the_dense_kernel(dense_share, monkeypatch):
+    """A batch of 1024 (the default threshold of the tensor-core path) whose portfolios are diversified (small expected returns:
+    nearly every asset free), concentrated, or a mix: the probe kernel decides per call whether the Gram runs at all; the weights
+    match the oracle in every case and the hand-over counter says which way the batch went."""
+    monkeypatch.delenv("DDW_QWARP_MIN_BATCH", raising=False)
+    B, N, u = 1024, 48, 0.25
+    rng, rets, C = _problem(B, N, 51)
+    ndense = int(B * dense_share)
+    order = rng.permutation(B)
+    rets[order[:ndense]] *= 0.02                      # diversified optimum: ~all 48 assets free, beyond the 32-row frame
+    g = np.ones(B, np.float32)
+    a = np.full(B, 0.5, np.float32)
+    w, layer = _solve(rets, C, g, a, u)
+    w_ref, st_ref = _oracle(rets, C, g, a, u)
+    assert np.abs(w - w_ref).max() < 1e-5
+    handed_over = layer.solver_counters()[1]
+    free = (np.asarray(st_ref) == 0).sum(1)
+    if dense_share == 1.0:
+        assert handed_over == B                       # the probe sent the whole batch to the dense kernel
+    else:
+        assert handed_over <= int((free > 32).sum())  # only portfolios that cannot fit the frame leave the warp solver
